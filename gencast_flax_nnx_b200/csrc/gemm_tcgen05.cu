@@ -1,0 +1,226 @@
+// bf16 tensor-core linear layer for sm_100a: TMA-staged operand tiles, tcgen05.mma
+// with the fp32 accumulator in tensor memory, fused epilogue read back with tcgen05.ld.
+//
+// One CTA computes a 128 x 128 output tile.  Warp roles:
+//   warp 0     TMA producer (one elected lane): A[128 x 64] and W[128 x 64] bf16 tiles,
+//              128-byte swizzle, STAGES-deep ring guarded by full/empty mbarriers
+//   warp 1     allocates 128 TMEM columns, issues tcgen05.mma (M=128, N=128, K=16) x 4
+//              per stage, releases stages with tcgen05.commit
+//   warps 2-5  epilogue: each warp owns the 32 TMEM lanes (= output rows) of its
+//              quarter, reads 16 columns at a time and applies the fused epilogue
+//              of common.cuh (bias / addend / row gathers / activation / residual).
+// Two CTAs fit per SM (3 x 32 KB stages each, 128 of 512 TMEM columns each), so one
+// CTA's epilogue overlaps the other's main loop.
+//
+// The K dimension may be split in up to three (A_s, W_s) segments: this is how the
+// [e | sender | receiver] and [node | aggregate] concatenations of the reference
+// (common/typed_graph_net.py:301-305, :315-326) are consumed without being built.
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace gc {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int BK = 64;
+constexpr int STAGES = 3;
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int B_STAGE_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/;
+constexpr uint32_t TMEM_COLS = 128;
+
+struct GemmMaps {
+  CUtensorMap a[GC_MAX_SEGMENTS];
+  CUtensorMap w[GC_MAX_SEGMENTS];
+};
+
+struct GemmShape {
+  int kblocks[GC_MAX_SEGMENTS];
+  int num_segments;
+  int n_tiles;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shape, const EpilogueParams ep) {
+  using namespace sm100;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + STAGES * A_STAGE_BYTES;
+  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+  // barrier block: full[STAGES] | empty[STAGES] | tmem_full | tmem_ptr
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * STAGES);
+  const uint32_t tmem_ptr_smem = bars + 8u * (2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_blk = blockIdx.x % shape.n_tiles;
+  const int m_blk = blockIdx.x / shape.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < shape.num_segments; ++s) {
+      prefetch_tensormap(&maps.a[s]);
+      prefetch_tensormap(&maps.w[s]);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = 0; s < shape.num_segments; ++s) {
+        for (int kb = 0; kb < shape.kblocks[s]; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          tma_load_2d(smem_a + stage * A_STAGE_BYTES, &maps.a[s], full_bar(stage), kb * BK, m_blk * BM);
+          tma_load_2d(smem_b + stage * B_STAGE_BYTES, &maps.w[s], full_bar(stage), kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16_f32(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t accumulate = 0;
+      for (int s = 0; s < shape.num_segments; ++s) {
+        for (int kb = 0; kb < shape.kblocks[s]; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t da = desc_kmajor_sw128(smem_a + stage * A_STAGE_BYTES);
+          const uint64_t db = desc_kmajor_sw128(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle span: +2 in the (>>4) address field
+            umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // Epilogue: TMEM lane quarter is fixed by warp id modulo 4.
+    const int q = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int64_t row = static_cast<int64_t>(m_blk) * BM + q * 32 + lane;
+    const float alpha = ep.alpha_dev != nullptr ? __ldg(ep.alpha_dev) : 1.0f;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(taddr + c, r);
+      tc_wait_ld();
+      if (row < ep.m) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        epilogue_row_segment<16>(ep, alpha, row, n_blk * BN + c, v);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    if (q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+}  // namespace
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return GC_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu)", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+    return GC_ERR_CUDA;
+  }
+  return GC_OK;
+}
+
+int launch_gemm_tcgen05(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
+  GemmMaps maps;
+  GemmShape shape;
+  shape.num_segments = a.num_segments;
+  shape.n_tiles = a.n / BN;
+  for (int s = 0; s < GC_MAX_SEGMENTS; ++s) shape.kblocks[s] = 0;
+  for (int s = 0; s < a.num_segments; ++s) {
+    shape.kblocks[s] = a.k[s] / BK;
+    int rc = make_tmap_bf16_2d(&maps.a[s], a.a[s], (uint64_t)a.m, (uint64_t)a.k[s], (uint64_t)a.lda[s], BK, BM);
+    if (rc != GC_OK) return rc;
+    rc = make_tmap_bf16_2d(&maps.w[s], a.w[s], (uint64_t)a.n, (uint64_t)a.k[s], (uint64_t)a.ldw[s], BK, BN);
+    if (rc != GC_OK) return rc;
+  }
+  for (int s = a.num_segments; s < GC_MAX_SEGMENTS; ++s) {
+    maps.a[s] = maps.a[0];
+    maps.w[s] = maps.w[0];
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel)");
+    attr_set = true;
+  }
+  const int64_t m_tiles = (a.m + BM - 1) / BM;
+  const int64_t grid = m_tiles * shape.n_tiles;
+  if (grid > 0x7fffffffLL) {
+    set_error("gc_gemm: too many tiles (%lld)", (long long)grid);
+    return GC_ERR_INVALID_ARGUMENT;
+  }
+  gemm_bf16_tcgen05_kernel<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, stream>>>(maps, shape, ep);
+  GC_CHECK_LAUNCH("gemm_bf16_tcgen05_kernel");
+  return GC_OK;
+}
+
+}  // namespace gc

@@ -1,0 +1,423 @@
+// HBM-bound row-wise kernels: LayerNorm + conditional affine, the deterministic
+// receiver-sorted segment sum, noise-level conditioning tables, affine folding,
+// the DPM-Solver++ 2S update, layout glue and ensemble accumulation.
+//
+// All of them move each byte once with 128-bit accesses, one warp per row, fp32
+// statistics; grids are sized in multiples of the SM count for the large inputs.
+#include "common.cuh"
+
+namespace gc {
+
+namespace {
+
+constexpr float LN_EPS = 1e-6f;  // flax.nnx.LayerNorm epsilon used by the reference (common/mlp.py:95-103)
+
+// Each lane owns NV = cols/32 elements of the row, as NV/4 chunks of 4 interleaved
+// across the warp so that every access is a fully coalesced 512 B (f32) or 256 B
+// (bf16) request.
+template <int NV>
+__device__ __forceinline__ void load_row(const void* base, int dtype, int64_t row_off, int lane, float (&v)[NV]) {
+#pragma unroll
+  for (int j = 0; j < NV / 4; ++j) {
+    float t[4];
+    load_as_float<4>(base, dtype, row_off + (j * 32 + lane) * 4, t);
+    v[j * 4] = t[0]; v[j * 4 + 1] = t[1]; v[j * 4 + 2] = t[2]; v[j * 4 + 3] = t[3];
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void store_row(void* base, int dtype, int64_t row_off, int lane, const float (&v)[NV]) {
+#pragma unroll
+  for (int j = 0; j < NV / 4; ++j) {
+    float t[4] = {v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]};
+    store_from_float<4>(base, dtype, row_off + (j * 32 + lane) * 4, t);
+  }
+}
+
+// LayerNorm statistics exactly as flax's fast-variance path: var = E[x^2] - E[x]^2, clipped at 0.
+template <int NV>
+__device__ __forceinline__ void layer_norm_inplace(float (&v)[NV], int cols) {
+  float s = 0.0f, ss = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { s += v[i]; ss = fmaf(v[i], v[i], ss); }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  const float inv_n = 1.0f / static_cast<float>(cols);
+  const float mean = s * inv_n;
+  const float var = fmaxf(ss * inv_n - mean * mean, 0.0f);
+  const float rstd = rsqrtf(var + LN_EPS);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = (v[i] - mean) * rstd;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) ln_cond_kernel(const void* __restrict__ x, int x_dtype, int64_t ldx,
+                                                      const float* __restrict__ scale_offset, int do_ln,
+                                                      const void* __restrict__ residual, int res_dtype, int64_t ld_res,
+                                                      void* __restrict__ out, int out_dtype, int64_t ldo,
+                                                      int64_t rows) {
+  constexpr int cols = NV * 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  float sc[NV], of[NV];
+  if (scale_offset != nullptr) {
+    load_row<NV>(scale_offset, GC_F32, 0, lane, sc);
+    load_row<NV>(scale_offset, GC_F32, cols, lane, of);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { sc[i] = 1.0f; of[i] = 0.0f; }
+  }
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+    float v[NV];
+    load_row<NV>(x, x_dtype, row * ldx, lane, v);
+    if (do_ln) layer_norm_inplace<NV>(v, cols);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = fmaf(v[i], sc[i], of[i]);
+    if (residual != nullptr) {
+      float r[NV];
+      load_row<NV>(residual, res_dtype, row * ld_res, lane, r);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] += r[i];
+    }
+    store_row<NV>(out, out_dtype, row * ldo, lane, v);
+  }
+}
+
+// One warp per receiver.  Receivers whose in-degree exceeds HEAVY are deferred
+// and then summed by the whole block (each warp a contiguous slice of the edge
+// range, partial sums combined in warp order): the polar mesh nodes collect
+// hundreds to thousands of grid edges and would otherwise
+// be a serial tail.  Summation order is a pure function of (row_ptr, edge_perm),
+// so results are bitwise reproducible.
+constexpr int SEG_WARPS = 8;
+constexpr int HEAVY = 96;
+
+template <int NV>
+__global__ void __launch_bounds__(SEG_WARPS * 32) ln_cond_segment_sum_kernel(
+    const void* __restrict__ y, int y_dtype, int64_t ldy, const float* __restrict__ scale_offset, int do_ln,
+    const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ edge_perm, void* __restrict__ out,
+    int out_dtype, int64_t ldo, int64_t num_segments) {
+  constexpr int cols = NV * 32;
+  __shared__ float partial[SEG_WARPS][cols];
+  __shared__ int heavy_seg[SEG_WARPS];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  float sc[NV], of[NV];
+  if (scale_offset != nullptr) {
+    load_row<NV>(scale_offset, GC_F32, 0, lane, sc);
+    load_row<NV>(scale_offset, GC_F32, cols, lane, of);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { sc[i] = 1.0f; of[i] = 0.0f; }
+  }
+
+  auto accumulate_range = [&](int beg, int end, float (&acc)[NV]) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
+    for (int j = beg; j < end; ++j) {
+      const int64_t e = edge_perm != nullptr ? __ldg(edge_perm + j) : j;
+      float v[NV];
+      load_row<NV>(y, y_dtype, e * ldy, lane, v);
+      if (do_ln) layer_norm_inplace<NV>(v, cols);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] += fmaf(v[i], sc[i], of[i]);
+    }
+  };
+
+  for (int64_t seg0 = static_cast<int64_t>(blockIdx.x) * SEG_WARPS; seg0 < num_segments;
+       seg0 += static_cast<int64_t>(gridDim.x) * SEG_WARPS) {
+    const int64_t seg = seg0 + warp;
+    int is_heavy = 0;
+    if (seg < num_segments) {
+      const int beg = __ldg(row_ptr + seg), end = __ldg(row_ptr + seg + 1);
+      if (end - beg > HEAVY) {
+        is_heavy = 1;
+      } else {
+        float acc[NV];
+        accumulate_range(beg, end, acc);
+        store_row<NV>(out, out_dtype, seg * ldo, lane, acc);
+      }
+    }
+    if (lane == 0) heavy_seg[warp] = is_heavy;
+    __syncthreads();
+    for (int w = 0; w < SEG_WARPS; ++w) {
+      if (!heavy_seg[w]) continue;            // block-uniform
+      const int64_t hseg = seg0 + w;
+      const int beg = __ldg(row_ptr + hseg), end = __ldg(row_ptr + hseg + 1);
+      const int per = (end - beg + SEG_WARPS - 1) / SEG_WARPS;
+      const int b = min(beg + warp * per, end), e = min(b + per, end);
+      float acc[NV];
+      accumulate_range(b, e, acc);
+#pragma unroll
+      for (int j = 0; j < NV / 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) partial[warp][(j * 32 + lane) * 4 + i] = acc[j * 4 + i];
+      __syncthreads();
+      if (warp == 0) {
+        float tot[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) tot[i] = 0.0f;
+        for (int ww = 0; ww < SEG_WARPS; ++ww)
+#pragma unroll
+          for (int j = 0; j < NV / 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tot[j * 4 + i] += partial[ww][(j * 32 + lane) * 4 + i];
+        store_row<NV>(out, out_dtype, hseg * ldo, lane, tot);
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ float gelu_tanh_exact(float x) {
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(u));
+}
+
+// grid = (layers, num_sigma); every block recomputes the 16-wide noise encoding
+// (64 -> 32 -> 16, a few kFLOP) and then writes its layer's (1 + s | o) row.
+__global__ void __launch_bounds__(128) cond_tables_kernel(const float* __restrict__ sigma, const float* __restrict__ w0,
+                                                          const float* __restrict__ b0, const float* __restrict__ w1,
+                                                          const float* __restrict__ b1, float base_period, int nfreq,
+                                                          const float* __restrict__ wc, const float* __restrict__ bc,
+                                                          int layers, int width, float* __restrict__ table) {
+  __shared__ float feat[128];
+  __shared__ float hid[32];
+  __shared__ float cond[16];
+  const int layer = blockIdx.x;
+  const int si = blockIdx.y;
+  const int tid = threadIdx.x;
+  const float z = logf(__ldg(sigma + si));
+  if (tid < nfreq) {
+    // common/model_utils.py:751-757: angular frequency 2 pi k / base_period, k = 1..K
+    const float ang = z * (6.283185307179586f * static_cast<float>(tid + 1) / base_period);
+    feat[tid] = cosf(ang);
+    feat[nfreq + tid] = sinf(ang);
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float a = __ldg(b0 + tid);
+    for (int i = 0; i < 2 * nfreq; ++i) a = fmaf(feat[i], __ldg(w0 + i * 32 + tid), a);
+    hid[tid] = gelu_tanh_exact(a);
+  }
+  __syncthreads();
+  if (tid < 16) {
+    float a = __ldg(b1 + tid);
+    for (int i = 0; i < 32; ++i) a = fmaf(hid[i], __ldg(w1 + i * 16 + tid), a);
+    cond[tid] = a;
+  }
+  __syncthreads();
+  const float* wl = wc + static_cast<int64_t>(layer) * 16 * 2 * width;
+  const float* bl = bc + static_cast<int64_t>(layer) * 2 * width;
+  float* dst = table + (static_cast<int64_t>(si) * layers + layer) * 2 * width;
+  for (int c = tid; c < 2 * width; c += blockDim.x) {
+    float a = __ldg(bl + c);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a = fmaf(cond[i], __ldg(wl + i * 2 * width + c), a);
+    dst[c] = c < width ? a + 1.0f : a;
+  }
+}
+
+// One block per output row n.
+__global__ void __launch_bounds__(128) fold_affine_kernel(const void* __restrict__ w, int dtype, int64_t ldw,
+                                                          const float* __restrict__ bias,
+                                                          const float* __restrict__ scale_offset, void* __restrict__ w_out,
+                                                          int64_t ldw_out, float* __restrict__ bias_out, int k) {
+  __shared__ float red[4];
+  const int n = blockIdx.x;
+  float dot = 0.0f;
+  for (int c = threadIdx.x; c < k; c += blockDim.x) {
+    float wv;
+    if (dtype == GC_BF16) wv = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(w)[n * ldw + c]);
+    else wv = reinterpret_cast<const float*>(w)[n * ldw + c];
+    const float o = wv * __ldg(scale_offset + c);
+    dot = fmaf(wv, __ldg(scale_offset + k + c), dot);
+    if (dtype == GC_BF16) reinterpret_cast<__nv_bfloat16*>(w_out)[n * ldw_out + c] = __float2bfloat16_rn(o);
+    else reinterpret_cast<float*>(w_out)[n * ldw_out + c] = o;
+  }
+  dot = warp_sum(dot);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) bias_out[n] = (bias != nullptr ? bias[n] : 0.0f) + red[0] + red[1] + red[2] + red[3];
+}
+
+__global__ void __launch_bounds__(256) dpm_update_kernel(const float* __restrict__ f, int64_t ldf,
+                                                         const float* __restrict__ x_cur, const float* __restrict__ x_base,
+                                                         int64_t ldx, const float* __restrict__ sched,
+                                                         float* __restrict__ x_out, void* __restrict__ xin_out,
+                                                         int xin_dtype, int64_t ld_xin, int64_t rows, int cols) {
+  const float c_out = __ldg(sched), c_skip = __ldg(sched + 1), a = __ldg(sched + 2), c_in_next = __ldg(sched + 3);
+  const int64_t total = rows * cols;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    const float d = c_out * __ldg(f + r * ldf + c) + c_skip * __ldg(x_cur + r * ldx + c);
+    const float xn = a * __ldg(x_base + r * ldx + c) + (1.0f - a) * d;
+    x_out[r * ldx + c] = xn;
+    if (xin_out != nullptr) {
+      const float xi = c_in_next * xn;
+      if (xin_dtype == GC_BF16) reinterpret_cast<__nv_bfloat16*>(xin_out)[r * ld_xin + c] = __float2bfloat16_rn(xi);
+      else reinterpret_cast<float*>(xin_out)[r * ld_xin + c] = xi;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_pad_kernel(const void* __restrict__ src, int src_dtype, int64_t ld_src,
+                                                       int cols_src, void* __restrict__ dst, int dst_dtype,
+                                                       int64_t ld_dst, int cols_dst, const float* __restrict__ scale_dev,
+                                                       int64_t rows) {
+  const float scale = scale_dev != nullptr ? __ldg(scale_dev) : 1.0f;
+  const int64_t total = rows * cols_dst;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols_dst;
+    const int c = static_cast<int>(i - r * cols_dst);
+    float v = 0.0f;
+    if (c < cols_src) {
+      if (src_dtype == GC_BF16) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[r * ld_src + c]);
+      else v = reinterpret_cast<const float*>(src)[r * ld_src + c];
+      v *= scale;
+    }
+    if (dst_dtype == GC_BF16) reinterpret_cast<__nv_bfloat16*>(dst)[r * ld_dst + c] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(dst)[r * ld_dst + c] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) ensemble_accumulate_kernel(const float* __restrict__ x, float* __restrict__ sum,
+                                                                  float* __restrict__ sumsq, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float v = __ldg(x + i);
+    sum[i] += v;
+    sumsq[i] = fmaf(v, v, sumsq[i]);
+  }
+}
+
+int sm_count() {
+  int dev = 0, n = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n > 0 ? n : 148;
+}
+
+unsigned grid_for(int64_t work_items, int per_block, int blocks_per_sm) {
+  const int64_t need = (work_items + per_block - 1) / per_block;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * blocks_per_sm;
+  return static_cast<unsigned>(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+bool dtype_ok(int d) { return d == GC_F32 || d == GC_BF16; }
+
+}  // namespace
+}  // namespace gc
+
+extern "C" {
+
+using namespace gc;
+
+int gc_ln_cond(void* stream, const void* x, int32_t x_dtype, int64_t ldx, const float* scale_offset,
+               int32_t do_layer_norm, const void* residual, int32_t res_dtype, int64_t ld_res, void* out,
+               int32_t out_dtype, int64_t ldo, int64_t rows, int32_t cols) {
+  GC_REQUIRE(x && out, "gc_ln_cond: null buffer");
+  GC_REQUIRE(cols == 128 || cols == 256 || cols == 512, "gc_ln_cond: cols=%d (supported: 128, 256, 512)", cols);
+  GC_REQUIRE(dtype_ok(x_dtype) && dtype_ok(out_dtype), "gc_ln_cond: bad dtype");
+  GC_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0 && aligned16(x) && aligned16(out), "gc_ln_cond: alignment");
+  if (residual) GC_REQUIRE(dtype_ok(res_dtype) && ld_res % 4 == 0 && aligned16(residual), "gc_ln_cond: residual alignment");
+  if (rows <= 0) return GC_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned grid = grid_for(rows, 8, 8);
+#define GC_LAUNCH_LN(NV)                                                                                        \
+  ln_cond_kernel<NV><<<grid, 256, 0, st>>>(x, x_dtype, ldx, scale_offset, do_layer_norm, residual, res_dtype, \
+                                            ld_res, out, out_dtype, ldo, rows)
+  if (cols == 128) GC_LAUNCH_LN(4);
+  else if (cols == 256) GC_LAUNCH_LN(8);
+  else GC_LAUNCH_LN(16);
+#undef GC_LAUNCH_LN
+  GC_CHECK_LAUNCH("ln_cond_kernel");
+  return GC_OK;
+}
+
+int gc_ln_cond_segment_sum(void* stream, const void* y, int32_t y_dtype, int64_t ldy, const float* scale_offset,
+                           int32_t do_layer_norm, const int32_t* row_ptr, const int32_t* edge_perm, void* out,
+                           int32_t out_dtype, int64_t ldo, int64_t num_segments, int32_t cols) {
+  GC_REQUIRE(y && out && row_ptr, "gc_ln_cond_segment_sum: null buffer");
+  GC_REQUIRE(cols == 128 || cols == 256 || cols == 512, "gc_ln_cond_segment_sum: cols=%d (supported: 128, 256, 512)", cols);
+  GC_REQUIRE(dtype_ok(y_dtype) && dtype_ok(out_dtype), "gc_ln_cond_segment_sum: bad dtype");
+  GC_REQUIRE(ldy % 4 == 0 && ldo % 4 == 0 && aligned16(y) && aligned16(out), "gc_ln_cond_segment_sum: alignment");
+  if (num_segments <= 0) return GC_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned grid = grid_for(num_segments, SEG_WARPS, 8);
+#define GC_LAUNCH_SEG(NV)                                                                                      \
+  ln_cond_segment_sum_kernel<NV><<<grid, SEG_WARPS * 32, 0, st>>>(y, y_dtype, ldy, scale_offset, do_layer_norm, \
+                                                                  row_ptr, edge_perm, out, out_dtype, ldo, num_segments)
+  if (cols == 128) GC_LAUNCH_SEG(4);
+  else if (cols == 256) GC_LAUNCH_SEG(8);
+  else GC_LAUNCH_SEG(16);
+#undef GC_LAUNCH_SEG
+  GC_CHECK_LAUNCH("ln_cond_segment_sum_kernel");
+  return GC_OK;
+}
+
+int gc_cond_tables(void* stream, const float* sigma, int32_t num_sigma, const float* w0, const float* b0,
+                   const float* w1, const float* b1, float base_period, int32_t num_frequencies, const float* wc,
+                   const float* bc, int32_t layers, int32_t width, float* table) {
+  GC_REQUIRE(sigma && w0 && b0 && w1 && b1 && wc && bc && table, "gc_cond_tables: null buffer");
+  GC_REQUIRE(num_frequencies >= 1 && num_frequencies <= 64, "gc_cond_tables: num_frequencies=%d", num_frequencies);
+  GC_REQUIRE(layers >= 1 && width >= 1 && num_sigma >= 1 && num_sigma <= 65535, "gc_cond_tables: bad sizes");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cond_tables_kernel<<<dim3(layers, num_sigma), 128, 0, st>>>(sigma, w0, b0, w1, b1, base_period, num_frequencies, wc,
+                                                              bc, layers, width, table);
+  GC_CHECK_LAUNCH("cond_tables_kernel");
+  return GC_OK;
+}
+
+int gc_fold_affine_into_linear(void* stream, const void* w, int32_t dtype, int64_t ldw, const float* bias,
+                               const float* scale_offset, void* w_out, int64_t ldw_out, float* bias_out, int32_t n,
+                               int32_t k) {
+  GC_REQUIRE(w && scale_offset && w_out && bias_out, "gc_fold_affine_into_linear: null buffer");
+  GC_REQUIRE(dtype_ok(dtype) && n > 0 && k > 0, "gc_fold_affine_into_linear: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  fold_affine_kernel<<<n, 128, 0, st>>>(w, dtype, ldw, bias, scale_offset, w_out, ldw_out, bias_out, k);
+  GC_CHECK_LAUNCH("fold_affine_kernel");
+  return GC_OK;
+}
+
+int gc_dpm_update(void* stream, const float* f, int64_t ldf, const float* x_cur, const float* x_base, int64_t ldx,
+                  const float* sched, float* x_out, void* xin_out, int32_t xin_dtype, int64_t ld_xin, int64_t rows,
+                  int32_t cols) {
+  GC_REQUIRE(f && x_cur && x_base && sched && x_out, "gc_dpm_update: null buffer");
+  GC_REQUIRE(cols > 0 && ldf >= cols && ldx >= cols, "gc_dpm_update: bad sizes");
+  if (xin_out) GC_REQUIRE(dtype_ok(xin_dtype) && ld_xin >= cols, "gc_dpm_update: bad xin");
+  if (rows <= 0) return GC_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dpm_update_kernel<<<grid_for(rows * cols, 256 * 4, 8), 256, 0, st>>>(f, ldf, x_cur, x_base, ldx, sched, x_out, xin_out,
+                                                                      xin_dtype, ld_xin, rows, cols);
+  GC_CHECK_LAUNCH("dpm_update_kernel");
+  return GC_OK;
+}
+
+int gc_cast_pad(void* stream, const void* src, int32_t src_dtype, int64_t ld_src, int32_t cols_src, void* dst,
+                int32_t dst_dtype, int64_t ld_dst, int32_t cols_dst, const float* scale_dev, int64_t rows) {
+  GC_REQUIRE(src && dst, "gc_cast_pad: null buffer");
+  GC_REQUIRE(dtype_ok(src_dtype) && dtype_ok(dst_dtype), "gc_cast_pad: bad dtype");
+  GC_REQUIRE(cols_src >= 0 && cols_dst > 0 && ld_src >= cols_src && ld_dst >= cols_dst, "gc_cast_pad: bad sizes");
+  if (rows <= 0) return GC_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cast_pad_kernel<<<grid_for(rows * cols_dst, 256 * 4, 8), 256, 0, st>>>(src, src_dtype, ld_src, cols_src, dst, dst_dtype,
+                                                                        ld_dst, cols_dst, scale_dev, rows);
+  GC_CHECK_LAUNCH("cast_pad_kernel");
+  return GC_OK;
+}
+
+int gc_ensemble_accumulate(void* stream, const float* x, float* sum, float* sumsq, int64_t n) {
+  GC_REQUIRE(x && sum && sumsq, "gc_ensemble_accumulate: null buffer");
+  if (n <= 0) return GC_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ensemble_accumulate_kernel<<<grid_for(n, 256 * 4, 8), 256, 0, st>>>(x, sum, sumsq, n);
+  GC_CHECK_LAUNCH("ensemble_accumulate_kernel");
+  return GC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,165 @@
+"""Torch-tensor front end of the C ABI (device memory and streams are torch's; the
+compute is the library's).  Every function enqueues on torch's current stream and
+returns immediately; outputs are caller-allocated unless stated.
+
+Reference operators these replace are cited in include/gencast_b200.h.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import GC_ACT_GELU_TANH, GC_ACT_NONE, GC_ACT_SWISH, GC_BF16, GC_F32, GemmArgs
+
+ACT = {None: GC_ACT_NONE, "none": GC_ACT_NONE, "swish": GC_ACT_SWISH, "gelu_tanh": GC_ACT_GELU_TANH}
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return GC_F32
+    if t.dtype == torch.bfloat16:
+        return GC_BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _row_major(t: torch.Tensor, what: str) -> int:
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{what}: expected a 2-D tensor with unit inner stride, got shape {tuple(t.shape)} "
+                         f"strides {t.stride()}")
+    if not t.is_cuda:
+        raise ValueError(f"{what}: tensor is not on a CUDA device (there is no CPU path)")
+    return t.stride(0)
+
+
+def gemm(segments: Sequence[Tuple[torch.Tensor, torch.Tensor]], out: torch.Tensor, *,
+         bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
+         addend: Optional[torch.Tensor] = None,
+         gathers: Sequence[Tuple[torch.Tensor, torch.Tensor]] = (),
+         residual: Optional[torch.Tensor] = None, alpha: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = act(alpha * sum_s A_s @ W_s^T + bias + addend + sum_j G_j[idx_j]) + residual.
+
+    segments: [(A_s [m, k_s], W_s [n, k_s])], all of one dtype (bf16 -> tcgen05, f32 -> FFMA).
+    """
+    lib = _lib.load()
+    args = GemmArgs()
+    m, n = out.shape
+    for s, (a, w) in enumerate(segments):
+        if a.dtype != w.dtype or a.dtype != segments[0][0].dtype:
+            raise TypeError("gemm: all operands must share one dtype")
+        if a.shape[0] != m or w.shape[0] != n or a.shape[1] != w.shape[1]:
+            raise ValueError(f"gemm: segment {s} shapes {tuple(a.shape)} x {tuple(w.shape)} do not match out {tuple(out.shape)}")
+        args.a[s] = a.data_ptr(); args.w[s] = w.data_ptr()
+        args.lda[s] = _row_major(a, "A"); args.ldw[s] = _row_major(w, "W")
+        args.k[s] = a.shape[1]
+    args.num_segments = len(segments)
+    args.m = m; args.n = n
+    args.dtype = _dt(segments[0][0])
+    args.bias = _p(bias)
+    args.alpha_dev = _p(alpha)
+    if addend is not None:
+        args.addend = addend.data_ptr(); args.ld_addend = _row_major(addend, "addend"); args.addend_dtype = _dt(addend)
+    for j, (src, idx) in enumerate(gathers):
+        if idx.dtype != torch.int32 or idx.numel() != m:
+            raise ValueError("gemm: gather index must be int32 [m]")
+        args.gather_src[j] = src.data_ptr(); args.gather_idx[j] = idx.data_ptr()
+        args.ld_gather[j] = _row_major(src, "gather source")
+        args.gather_dtype = _dt(src)
+        if j and _dt(src) != _dt(gathers[0][0]):
+            raise TypeError("gemm: gather sources must share one dtype")
+    args.act = ACT[act]
+    if residual is not None:
+        args.residual = residual.data_ptr(); args.ld_res = _row_major(residual, "residual"); args.res_dtype = _dt(residual)
+    args.out = out.data_ptr(); args.ldo = _row_major(out, "out"); args.out_dtype = _dt(out)
+    _lib.check(lib.gc_gemm(_stream(), ctypes.byref(args)), "gc_gemm")
+    return out
+
+
+def ln_cond(x: torch.Tensor, out: torch.Tensor, scale_offset: Optional[torch.Tensor], *,
+            layer_norm: bool = True, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    rows, cols = x.shape
+    _lib.check(lib.gc_ln_cond(_stream(), x.data_ptr(), _dt(x), _row_major(x, "x"), _p(scale_offset), int(layer_norm),
+                              _p(residual), _dt(residual) if residual is not None else 0,
+                              _row_major(residual, "residual") if residual is not None else 0,
+                              out.data_ptr(), _dt(out), _row_major(out, "out"), rows, cols), "gc_ln_cond")
+    return out
+
+
+def ln_cond_segment_sum(y: torch.Tensor, out: torch.Tensor, scale_offset: Optional[torch.Tensor],
+                        row_ptr: torch.Tensor, edge_perm: Optional[torch.Tensor], *, layer_norm: bool = True):
+    lib = _lib.load()
+    nseg, cols = out.shape
+    if row_ptr.dtype != torch.int32 or row_ptr.numel() != nseg + 1:
+        raise ValueError("row_ptr must be int32 [num_segments + 1]")
+    _lib.check(lib.gc_ln_cond_segment_sum(_stream(), y.data_ptr(), _dt(y), _row_major(y, "y"), _p(scale_offset),
+                                          int(layer_norm), row_ptr.data_ptr(), _p(edge_perm), out.data_ptr(), _dt(out),
+                                          _row_major(out, "out"), nseg, cols), "gc_ln_cond_segment_sum")
+    return out
+
+
+def khop_attention(qkv: torch.Tensor, out: torch.Tensor, nbr_ptr: torch.Tensor, nbr_idx: torch.Tensor,
+                   heads: int, head_dim: int, max_degree: int = 0) -> torch.Tensor:
+    lib = _lib.load()
+    if out.dtype != qkv.dtype:
+        raise TypeError("khop_attention: out must have the dtype of qkv")
+    _lib.check(lib.gc_khop_attention(_stream(), qkv.data_ptr(), _dt(qkv), _row_major(qkv, "qkv"), nbr_ptr.data_ptr(),
+                                     nbr_idx.data_ptr(), max_degree, out.data_ptr(), _row_major(out, "out"),
+                                     qkv.shape[0], heads, head_dim), "gc_khop_attention")
+    return out
+
+
+def cond_tables(sigma: torch.Tensor, w0, b0, w1, b1, base_period: float, num_frequencies: int,
+                wc: torch.Tensor, bc: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    layers, _, two_w = wc.shape
+    _lib.check(lib.gc_cond_tables(_stream(), sigma.data_ptr(), sigma.numel(), w0.data_ptr(), b0.data_ptr(),
+                                  w1.data_ptr(), b1.data_ptr(), float(base_period), num_frequencies, wc.data_ptr(),
+                                  bc.data_ptr(), layers, two_w // 2, table.data_ptr()), "gc_cond_tables")
+    return table
+
+
+def fold_affine_into_linear(w: torch.Tensor, bias: Optional[torch.Tensor], scale_offset: torch.Tensor,
+                            w_out: torch.Tensor, bias_out: torch.Tensor):
+    lib = _lib.load()
+    n, k = w.shape
+    _lib.check(lib.gc_fold_affine_into_linear(_stream(), w.data_ptr(), _dt(w), _row_major(w, "w"), _p(bias),
+                                              scale_offset.data_ptr(), w_out.data_ptr(), _row_major(w_out, "w_out"),
+                                              bias_out.data_ptr(), n, k), "gc_fold_affine_into_linear")
+    return w_out, bias_out
+
+
+def dpm_update(f: torch.Tensor, x_cur: torch.Tensor, x_base: torch.Tensor, sched: torch.Tensor,
+               x_out: torch.Tensor, xin_out: Optional[torch.Tensor], cols: int):
+    lib = _lib.load()
+    rows = x_cur.shape[0]
+    _lib.check(lib.gc_dpm_update(_stream(), f.data_ptr(), _row_major(f, "f"), x_cur.data_ptr(), x_base.data_ptr(),
+                                 _row_major(x_cur, "x"), sched.data_ptr(), x_out.data_ptr(), _p(xin_out),
+                                 _dt(xin_out) if xin_out is not None else 0,
+                                 _row_major(xin_out, "xin") if xin_out is not None else 0, rows, cols), "gc_dpm_update")
+
+
+def cast_pad(src: torch.Tensor, dst: torch.Tensor, cols_src: Optional[int] = None,
+             scale: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    rows = src.shape[0]
+    cs = src.shape[1] if cols_src is None else cols_src
+    _lib.check(lib.gc_cast_pad(_stream(), src.data_ptr(), _dt(src), _row_major(src, "src"), cs, dst.data_ptr(),
+                               _dt(dst), _row_major(dst, "dst"), dst.shape[1], _p(scale), rows), "gc_cast_pad")
+    return dst
+
+
+def ensemble_accumulate(x: torch.Tensor, total: torch.Tensor, total_sq: torch.Tensor):
+    lib = _lib.load()
+    _lib.check(lib.gc_ensemble_accumulate(_stream(), x.data_ptr(), total.data_ptr(), total_sq.data_ptr(), x.numel()),
+               "gc_ensemble_accumulate")

@@ -1,0 +1,211 @@
+/*
+ * gencast_b200 — C ABI of the B200 (sm_100a) GenCast denoiser / sampler kernels.
+ *
+ * The reference (fgiral000/gencast-flax-nnx) is pure Python/JAX: it has no FFI
+ * layer of its own.  Its hot path is made of the Python operators cited next to
+ * each entry point below; these entry points are what an XLA FFI custom call
+ * (jax.ffi.ffi_call) or any other host binding would bind in their place — see
+ * INTEGRATION.md for the jax.ffi stub and gencast_flax_nnx_b200/_lib.py for the
+ * ctypes binding used by this repo's own host code and tests.
+ *
+ * Conventions
+ *   - every launcher is enqueue-only on `stream` (a cudaStream_t passed as
+ *     void*): no allocation, no synchronisation, no default-stream work, no
+ *     global mutable state, so calls are re-entrant and CUDA-graph capturable;
+ *   - all buffers are caller-owned device pointers; row-major, leading
+ *     dimension (`ld*`) counted in elements;
+ *   - return value 0 = success; negative = error, message via gc_last_error()
+ *     (thread-local).  Nothing throws across the boundary;
+ *   - dtype codes: GC_F32 = 0 (float), GC_BF16 = 1 (__nv_bfloat16).
+ */
+#ifndef GENCAST_B200_H_
+#define GENCAST_B200_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define GC_API __attribute__((visibility("default")))
+#else
+#define GC_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GC_F32 0
+#define GC_BF16 1
+
+#define GC_ACT_NONE 0
+#define GC_ACT_SWISH 1      /* jax.nn.swish, common/deep_typed_graph_net.py:61-62 */
+#define GC_ACT_GELU_TANH 2  /* jax.nn.gelu(approximate=True), gencast/sparse_transformer.py:264 */
+
+#define GC_OK 0
+#define GC_ERR_INVALID_ARGUMENT (-1)
+#define GC_ERR_CUDA (-2)
+#define GC_ERR_UNSUPPORTED (-3)
+
+#define GC_MAX_SEGMENTS 3
+
+/* Library / device introspection. */
+GC_API const char* gc_last_error(void);
+GC_API int gc_abi_version(void);
+/* 1 if the current device can run the tcgen05 path (compute capability 10.x). */
+GC_API int gc_device_supports_tcgen05(void);
+
+/*
+ * Fused linear layer:  OUT = post( act( alpha * sum_s A_s . W_s^T + bias + addend
+ *                                       + gather0[idx0[row]] + gather1[idx1[row]] ) ) + residual
+ *
+ * Replaces flax.nnx.Linear inside MLP / MLPWithNormConditioning
+ * (common/mlp.py:152-203), the [e | s | r] concatenation + first edge-MLP
+ * layer of the interaction network (common/typed_graph_net.py:134-159,
+ * :301-305 — the concatenation becomes K-segments and row gathers of
+ * per-node partial products), the [n | agg] node update (:315-326), and the
+ * transformer projections with residual add (gencast/sparse_transformer.py:
+ * 252-290, :353, :520-524).
+ *
+ * A_s: [m, k[s]] (ld lda[s]);  W_s: [n, k[s]] i.e. the Linear kernel stored
+ * transposed, K contiguous (ld ldw[s]).  dtype selects the operand type and the
+ * engine: GC_BF16 -> tcgen05/TMEM/TMA tensor-core kernel (fp32 accumulate),
+ * GC_F32 -> fp32 FFMA kernel.  k[s] % 64 == 0, n % 128 == 0, pointers 16-byte
+ * aligned, ld % 8 == 0.
+ */
+typedef struct gc_gemm_args {
+  const void* a[GC_MAX_SEGMENTS];
+  const void* w[GC_MAX_SEGMENTS];
+  int64_t lda[GC_MAX_SEGMENTS];
+  int64_t ldw[GC_MAX_SEGMENTS];
+  int32_t k[GC_MAX_SEGMENTS];
+  int32_t num_segments;
+  int64_t m;
+  int32_t n;
+  int32_t dtype;            /* operand dtype of every A_s and W_s */
+  const float* bias;        /* [n] or NULL */
+  const float* alpha_dev;   /* device scalar or NULL (= 1) */
+  const void* addend;       /* [m, n] added before the activation, or NULL */
+  int64_t ld_addend;
+  int32_t addend_dtype;
+  int32_t gather_dtype;
+  const void* gather_src[2];     /* tables gathered by row index, added before the activation, or NULL */
+  const int32_t* gather_idx[2];  /* [m] row ids into gather_src[j] */
+  int64_t ld_gather[2];
+  int32_t act;              /* GC_ACT_* */
+  int32_t res_dtype;
+  const void* residual;     /* [m, n] added after the activation, or NULL */
+  int64_t ld_res;
+  void* out;                /* [m, n] */
+  int64_t ldo;
+  int32_t out_dtype;
+  int32_t reserved;
+} gc_gemm_args;
+
+GC_API int gc_gemm(void* stream, const gc_gemm_args* args);
+
+/*
+ * Row LayerNorm (no learned affine, eps 1e-6, var = E[x^2]-E[x]^2 >= 0) followed
+ * by the conditional affine  y * scale + offset  (+ residual).
+ * Replaces nnx.LayerNorm + LinearNormConditioning: common/mlp.py:59-65,
+ * :121-145; gencast/sparse_transformer.py:518-523, :630-633, and the residual
+ * adds of common/deep_typed_graph_net.py:569-581.
+ * scale_offset: [2*cols] float = (1 + s | o) for this call's noise level
+ * (produced by gc_cond_tables).  do_layer_norm = 0 applies the affine only.
+ */
+GC_API int gc_ln_cond(void* stream, const void* x, int32_t x_dtype, int64_t ldx,
+               const float* scale_offset, int32_t do_layer_norm,
+               const void* residual, int32_t res_dtype, int64_t ld_res,
+               void* out, int32_t out_dtype, int64_t ldo,
+               int64_t rows, int32_t cols);
+
+/*
+ * Deterministic receiver-sorted segment sum with LayerNorm + conditional affine
+ * applied to every edge row on the fly:
+ *   out[v] = sum_{j in [row_ptr[v], row_ptr[v+1])}  LN(y[edge_perm[j]]) * scale + offset
+ * Replaces the tail of the edge MLP (common/mlp.py:121-145) together with
+ * jraph.segment_sum (call sites common/typed_graph_net.py:173-182, f32
+ * aggregation of common/deep_typed_graph_net.py:396-404).  The sum runs in
+ * fp32 in a fixed order (no atomics) so results are bitwise reproducible.
+ * edge_perm may be NULL (edges already receiver-sorted: mesh2grid).
+ */
+GC_API int gc_ln_cond_segment_sum(void* stream, const void* y, int32_t y_dtype, int64_t ldy,
+                           const float* scale_offset, int32_t do_layer_norm,
+                           const int32_t* row_ptr, const int32_t* edge_perm,
+                           void* out, int32_t out_dtype, int64_t ldo,
+                           int64_t num_segments, int32_t cols);
+
+/*
+ * k-hop neighbourhood multi-head attention on the mesh (exact sparse pattern):
+ *   out[i, h] = softmax_j( q[i,h] . k[j,h] / sqrt(d) ) v[j,h],  j in neighbours(i)
+ * Replaces TriblockdiagMHA without its projections
+ * (gencast/sparse_transformer.py:323-351, softmax :100-125, mask :163-201): the
+ * tri-block mask evaluates to exactly this neighbour set, masked logits
+ * contribute exp(-1e30 - max) = 0.
+ * qkv: [nodes, 3*heads*head_dim] laid out (q | k | v); out: [nodes, heads*head_dim].
+ * nbr_ptr/nbr_idx: CSR of the k-hop pattern (self included).
+ */
+GC_API int gc_khop_attention(void* stream, const void* qkv, int32_t dtype, int64_t ld_qkv,
+                      const int32_t* nbr_ptr, const int32_t* nbr_idx, int32_t max_degree,
+                      void* out, int64_t ldo, int64_t nodes, int32_t heads, int32_t head_dim);
+
+/*
+ * Noise-level conditioning for a batch of noise levels, all layers at once:
+ *   cond      = Linear1(gelu_tanh(Linear0(fourier(log sigma))))     [16]
+ *   table[i, l] = (1 + s_l | o_l),  [s_l | o_l] = cond . Wc_l + bc_l   [2*width]
+ * Replaces FourierFeaturesMLP.__call__ (common/mlp.py:255-265,
+ * common/model_utils.py:728-757) and every LinearNormConditioning linear
+ * (common/mlp.py:59-64).  Weights fp32: w0 [2*num_freq, 32], b0 [32],
+ * w1 [32, 16], b1 [16], wc [layers, 16, 2*width], bc [layers, 2*width].
+ * table: [num_sigma, layers, 2*width] fp32.
+ */
+GC_API int gc_cond_tables(void* stream, const float* sigma, int32_t num_sigma,
+                   const float* w0, const float* b0, const float* w1, const float* b1,
+                   float base_period, int32_t num_frequencies,
+                   const float* wc, const float* bc, int32_t layers, int32_t width,
+                   float* table);
+
+/*
+ * Folds a conditional affine that sits in front of a Linear into that Linear:
+ *   w_out[n, k] = w[n, k] * scale[k];   bias_out[n] = bias[n] + sum_k offset[k] * w[n, k]
+ * so that Linear(x * scale + offset) == x . w_out^T + bias_out.  Used for the
+ * statically embedded edge latents, whose LayerNorm output is a constant and only
+ * the noise-level affine changes per call (common/mlp.py:62-65 feeding
+ * common/typed_graph_net.py:301-305).  w: [n, k] (dtype), bias fp32 or NULL.
+ */
+GC_API int gc_fold_affine_into_linear(void* stream, const void* w, int32_t dtype, int64_t ldw,
+                               const float* bias, const float* scale_offset,
+                               void* w_out, int64_t ldw_out, float* bias_out,
+                               int32_t n, int32_t k);
+
+/*
+ * Preconditioning + DPM-Solver++ 2S state update, elementwise:
+ *   D     = c_out * f + c_skip * x_cur
+ *   x_new = a * x_base + (1 - a) * D
+ *   x_out = x_new (fp32);   xin_out = c_in_next * x_new (operand dtype)
+ * Replaces Sampler._preconditioned_denoiser and the two update lines of body_fn
+ * (gencast/dpm_solver_plus_plus_2s.py:145-153, :198-205).  sched: device
+ * float[4] = (c_out, c_skip, a, c_in_next).  All arrays [rows, cols] with the
+ * given leading dimensions; xin_out may be NULL.
+ */
+GC_API int gc_dpm_update(void* stream, const float* f, int64_t ldf, const float* x_cur, const float* x_base,
+                  int64_t ldx, const float* sched, float* x_out, void* xin_out, int32_t xin_dtype,
+                  int64_t ld_xin, int64_t rows, int32_t cols);
+
+/*
+ * 2-D convert / pad / scale: dst[r, c] = c < cols_src ? scale * src[r, c] : 0.
+ * Layout glue of gencast/denoiser.py:794-806 (feature assembly) on device.
+ * scale_dev may be NULL (= 1).
+ */
+GC_API int gc_cast_pad(void* stream, const void* src, int32_t src_dtype, int64_t ld_src, int32_t cols_src,
+                void* dst, int32_t dst_dtype, int64_t ld_dst, int32_t cols_dst,
+                const float* scale_dev, int64_t rows);
+
+/*
+ * Ensemble statistics accumulation (no reference implementation exists; defined
+ * in DESIGN.md): sum[i] += x[i]; sumsq[i] += x[i]^2 over n elements.
+ */
+GC_API int gc_ensemble_accumulate(void* stream, const float* x, float* sum, float* sumsq, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* GENCAST_B200_H_ */

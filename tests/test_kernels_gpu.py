@@ -1,0 +1,222 @@
+"""Per-kernel parity on the GPU: every C-ABI launcher against a plain torch fp32
+restatement of the same arithmetic (the reference operators are cited in
+include/gencast_b200.h)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _swish(x):
+    return x * torch.sigmoid(x)
+
+
+def _gelu_tanh(x):
+    return 0.5 * x * (1 + torch.tanh(math.sqrt(2 / math.pi) * (x + 0.044715 * x ** 3)))
+
+
+def _ln(x, eps=1e-6):
+    mean = x.mean(-1, keepdim=True)
+    var = ((x * x).mean(-1, keepdim=True) - mean * mean).clamp_min(0)
+    return (x - mean) * torch.rsqrt(var + eps)
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("m,n,ks", [(300, 128, (64,)), (1000, 512, (128, 192)), (4099, 256, (256, 64, 128)),
+                                    (128, 2048, (512,)), (70000, 512, (512,))])
+def test_gemm_plain(cuda_device, dtype, m, n, ks):
+    from gencast_flax_nnx_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(m + n)
+    segs, ref = [], torch.zeros(m, n, dtype=torch.float64)
+    for k in ks:
+        a = torch.randn(m, k, generator=g).to(dtype)
+        w = (torch.randn(n, k, generator=g) / math.sqrt(sum(ks))).to(dtype)
+        ref += a.double() @ w.double().t()
+        segs.append((a.to(cuda_device), w.to(cuda_device)))
+    out = torch.empty(m, n, dtype=torch.float32, device=cuda_device)
+    ops.gemm(segs, out)
+    torch.cuda.synchronize()
+    assert _rel(out.cpu(), ref) < (2e-5 if dtype == torch.float32 else 1e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("act", [None, "swish", "gelu_tanh"])
+def test_gemm_fused_epilogue(cuda_device, dtype, act):
+    from gencast_flax_nnx_b200 import ops
+    m, n, k, ns, nr = 777, 256, 128, 200, 50
+    g = torch.Generator(device="cpu").manual_seed(5)
+    a = torch.randn(m, k, generator=g).to(dtype)
+    w = (torch.randn(n, k, generator=g) / math.sqrt(k)).to(dtype)
+    bias = torch.randn(n, generator=g)
+    addend = torch.randn(m, n, generator=g).to(dtype)
+    gs = torch.randn(ns, n, generator=g).to(dtype)
+    gr = torch.randn(nr, n, generator=g).to(dtype)
+    si = torch.randint(0, ns, (m,), generator=g, dtype=torch.int32)
+    ri = torch.randint(0, nr, (m,), generator=g, dtype=torch.int32)
+    res = torch.randn(m, n, generator=g)
+    alpha = torch.tensor([0.37])
+    pre = alpha.double() * (a.double() @ w.double().t()) + bias.double() + addend.double() + gs.double()[si.long()] + gr.double()[ri.long()]
+    fn = {None: lambda x: x, "swish": _swish, "gelu_tanh": _gelu_tanh}[act]
+    ref = fn(pre) + res.double()
+    d = cuda_device
+    for out_dtype, tol in ((torch.float32, 3e-5), (torch.bfloat16, 1e-2)):
+        out = torch.empty(m, n, dtype=out_dtype, device=d)
+        ops.gemm([(a.to(d), w.to(d))], out, bias=bias.to(d), act=act, addend=addend.to(d),
+                 gathers=[(gs.to(d), si.to(d)), (gr.to(d), ri.to(d))], residual=res.to(d), alpha=alpha.to(d))
+        torch.cuda.synchronize()
+        assert _rel(out.cpu(), ref) < tol
+
+
+@pytest.mark.parametrize("cols", [128, 256, 512])
+@pytest.mark.parametrize("in_dtype,out_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                                (torch.bfloat16, torch.float32)])
+def test_ln_cond(cuda_device, cols, in_dtype, out_dtype):
+    from gencast_flax_nnx_b200 import ops
+    rows = 1001
+    g = torch.Generator(device="cpu").manual_seed(cols)
+    x = (torch.randn(rows, cols, generator=g) * 3 + 1).to(in_dtype)
+    so = torch.cat([1 + 0.1 * torch.randn(cols, generator=g), torch.randn(cols, generator=g)])
+    res = torch.randn(rows, cols, generator=g)
+    d = cuda_device
+    out = torch.empty(rows, cols, dtype=out_dtype, device=d)
+    ops.ln_cond(x.to(d), out, so.to(d), residual=res.to(d))
+    ref = _ln(x.double()) * so[:cols].double() + so[cols:].double() + res.double()
+    assert _rel(out.cpu(), ref) < (1e-5 if out_dtype == torch.float32 else 1e-2)
+    out2 = torch.empty(rows, cols, dtype=out_dtype, device=d)
+    ops.ln_cond(x.to(d), out2, so.to(d), layer_norm=False)
+    ref2 = x.double() * so[:cols].double() + so[cols:].double()
+    assert _rel(out2.cpu(), ref2) < (1e-5 if out_dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("cols", [128, 256, 512])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_segment_sum(cuda_device, cols, dtype):
+    from gencast_flax_nnx_b200 import ops
+    from gencast_flax_nnx_b200.graph import csr_by_receiver
+    rng = np.random.default_rng(cols)
+    nseg, nedge = 500, 6000
+    recv = rng.integers(0, nseg, size=nedge)
+    recv[:900] = 7            # one heavy receiver (block-cooperative path)
+    recv[900:1100] = 123      # another in a different block
+    recv = recv[recv != 11]   # one empty segment
+    nedge = len(recv)
+    row_ptr, perm = csr_by_receiver(recv, nseg)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    y = torch.randn(nedge, cols, generator=g).to(dtype)
+    so = torch.cat([1 + 0.1 * torch.randn(cols, generator=g), torch.randn(cols, generator=g)])
+    d = cuda_device
+    out = torch.full((nseg, cols), float("nan"), dtype=torch.float32, device=d)
+    args = (y.to(d), out, so.to(d), torch.from_numpy(row_ptr).to(d), torch.from_numpy(perm).to(d))
+    ops.ln_cond_segment_sum(*args)
+    e = _ln(y.double()) * so[:cols].double() + so[cols:].double()
+    ref = torch.zeros(nseg, cols, dtype=torch.float64).index_add_(0, torch.from_numpy(recv).long(), e)
+    assert _rel(out.cpu(), ref) < 1e-5
+    assert torch.all(out[11] == 0)
+    # bitwise determinism
+    out_b = torch.empty_like(out)
+    ops.ln_cond_segment_sum(args[0], out_b, *args[2:])
+    assert torch.equal(out, out_b)
+    # already-sorted edges, no permutation, no LayerNorm (degree-3 mesh2grid shape)
+    y3 = torch.randn(nseg * 3, cols, generator=g).to(dtype)
+    rp3 = torch.arange(0, 3 * nseg + 1, 3, dtype=torch.int32)
+    out3 = torch.empty(nseg, cols, dtype=torch.float32, device=d)
+    ops.ln_cond_segment_sum(y3.to(d), out3, None, rp3.to(d), None, layer_norm=False)
+    assert _rel(out3.cpu(), y3.double().reshape(nseg, 3, cols).sum(1)) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("heads,head_dim", [(4, 32), (4, 64), (4, 128)])
+def test_khop_attention(cuda_device, dtype, heads, head_dim):
+    from gencast_flax_nnx_b200 import ops
+    rng = np.random.default_rng(head_dim)
+    n = 300
+    hd = heads * head_dim
+    g = torch.Generator(device="cpu").manual_seed(3)
+    qkv = torch.randn(n, 3 * hd, generator=g).to(dtype)
+    mask = rng.random((n, n)) < 0.2
+    mask[np.arange(n), np.arange(n)] = True
+    mask[5, :] = True            # a full row (> 32 * several chunks)
+    ptr = np.zeros(n + 1, np.int32); ptr[1:] = np.cumsum(mask.sum(1))
+    idx = np.nonzero(mask)[1].astype(np.int32)
+    d = cuda_device
+    out = torch.empty(n, hd, dtype=dtype, device=d)
+    ops.khop_attention(qkv.to(d), out, torch.from_numpy(ptr).to(d), torch.from_numpy(idx).to(d), heads, head_dim)
+    q, k, v = [t.double().reshape(n, heads, head_dim) for t in qkv.split(hd, dim=1)]
+    logits = torch.einsum("qhd,khd->hqk", q, k) / math.sqrt(head_dim)
+    logits = logits.masked_fill(~torch.from_numpy(mask)[None], float("-inf"))
+    ref = torch.einsum("hqk,khd->qhd", torch.softmax(logits, -1), v).reshape(n, hd)
+    assert _rel(out.cpu(), ref) < (1e-5 if dtype == torch.float32 else 1e-2)
+
+
+def test_cond_tables_and_fold(cuda_device):
+    from gencast_flax_nnx_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(9)
+    nfreq, layers, width = 32, 5, 256
+    sigma = torch.tensor([80.0, 1.0, 0.03, 1e-6, 7.5])
+    w0 = torch.randn(2 * nfreq, 32, generator=g) / 8; b0 = torch.randn(32, generator=g) * 0.1
+    w1 = torch.randn(32, 16, generator=g) / 5.6; b1 = torch.randn(16, generator=g) * 0.1
+    wc = torch.randn(layers, 16, 2 * width, generator=g) * 0.1; bc = torch.randn(layers, 2 * width, generator=g) * 0.1
+    d = cuda_device
+    table = torch.empty(len(sigma), layers, 2 * width, device=d)
+    ops.cond_tables(sigma.to(d), w0.to(d), b0.to(d), w1.to(d), b1.to(d), 16.0, nfreq, wc.to(d), bc.to(d), table)
+    z = torch.log(sigma.double())
+    ang = z[:, None] * (2 * math.pi * torch.arange(1, nfreq + 1).double() / 16.0)
+    f = torch.cat([torch.cos(ang), torch.sin(ang)], -1)
+    cond = _gelu_tanh(f @ w0.double() + b0.double()) @ w1.double() + b1.double()
+    ref = torch.einsum("sc,lcw->slw", cond, wc.double()) + bc.double()
+    ref[..., :width] += 1
+    assert _rel(table.cpu(), ref) < 2e-4       # fp32 sin/cos of |angle| up to ~170 rad
+
+    for dtype in (torch.float32, torch.bfloat16):
+        n, k = 256, 256
+        w = (torch.randn(n, k, generator=g) / 16).to(dtype)
+        bias = torch.randn(n, generator=g)
+        so = torch.cat([1 + 0.1 * torch.randn(k, generator=g), torch.randn(k, generator=g)])
+        w_out = torch.empty(n, k, dtype=dtype, device=d); b_out = torch.empty(n, device=d)
+        ops.fold_affine_into_linear(w.to(d), bias.to(d), so.to(d), w_out, b_out)
+        assert _rel(w_out.cpu(), w.double() * so[:k].double()) < (1e-6 if dtype == torch.float32 else 1e-2)
+        assert _rel(b_out.cpu(), bias.double() + w.double() @ so[k:].double()) < 1e-5
+
+
+def test_dpm_update_cast_pad_accumulate(cuda_device):
+    from gencast_flax_nnx_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(2)
+    rows, cols = 1000, 82
+    f = torch.randn(rows, 128, generator=g); x = torch.randn(rows, cols, generator=g); xb = torch.randn(rows, cols, generator=g)
+    sched = torch.tensor([0.7, 0.3, 0.25, 1.7])
+    d = cuda_device
+    for xin_dtype in (torch.float32, torch.bfloat16):
+        x_out = torch.empty(rows, cols, device=d)
+        xin = torch.zeros(rows, 128, dtype=xin_dtype, device=d)
+        ops.dpm_update(f.to(d), x.to(d), xb.to(d), sched.to(d), x_out, xin, cols)
+        den = 0.7 * f[:, :cols] + 0.3 * x
+        ref = 0.25 * xb + 0.75 * den
+        assert _rel(x_out.cpu(), ref) < 1e-6
+        assert _rel(xin.cpu()[:, :cols], 1.7 * ref) < (1e-6 if xin_dtype == torch.float32 else 1e-2)
+        assert torch.all(xin[:, cols:] == 0)
+    dst = torch.full((rows, 128), 5.0, dtype=torch.bfloat16, device=d)
+    ops.cast_pad(x.to(d), dst)
+    assert _rel(dst.cpu()[:, :cols], x) < 1e-2 and torch.all(dst[:, cols:] == 0)
+    tot = torch.zeros(rows, cols, device=d); tot2 = torch.zeros(rows, cols, device=d)
+    for _ in range(3):
+        ops.ensemble_accumulate(x.to(d), tot, tot2)
+    assert _rel(tot.cpu(), 3 * x) < 1e-6 and _rel(tot2.cpu(), 3 * x * x) < 1e-6
+
+
+def test_errors_are_reported(cuda_device):
+    from gencast_flax_nnx_b200 import ops, _lib
+    d = cuda_device
+    a = torch.zeros(10, 100, dtype=torch.bfloat16, device=d)     # k not a multiple of 64
+    w = torch.zeros(128, 100, dtype=torch.bfloat16, device=d)
+    out = torch.zeros(10, 128, device=d)
+    with pytest.raises(_lib.GencastKernelError):
+        ops.gemm([(a[:, :96], w[:, :96])], out)
+    with pytest.raises(ValueError):
+        ops.gemm([(a.cpu(), w.cpu())], out)
