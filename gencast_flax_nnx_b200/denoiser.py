@@ -1,0 +1,112 @@
+"""`denoiser.Denoiser` of the reference, on B200 kernels.
+
+Mirrors gencast/denoiser.py:142-202 (Denoiser) and :205-341 (DenoiserArchitecture):
+same constructor arguments, same call signature and error behaviour, same
+Dataset in / Dataset out contract.  The network itself runs in DenoiserEngine.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import stacking
+from .configs import DenoiserArchitectureConfig, NoiseEncoderConfig
+from .engine import ChannelLayout, DenoiserEngine
+from .graph import build_denoiser_graphs
+from .params import init_perturbed, init_reference_like, param_shapes
+from .xarray_lite import DataArray, Dataset
+
+
+class Denoiser:
+    """Wraps the GNN-transformer-GNN network with noise-level encoding.
+
+    Reference: gencast/denoiser.py:153-159 for the constructor (`rngs` seeds the
+    lazily created parameters, `gpu_mesh` is accepted and unused exactly as in the
+    reference drivers, training/train_helpers.py:143-150).  Extra keyword-only
+    arguments select what the reference leaves to JAX: `params` (a flat dict keyed
+    by the NNX attribute paths), `compute_dtype`
+    ('bf16' tensor-core path or 'f32' parity path) and `device`.
+    """
+
+    def __init__(self, noise_encoder_config: Optional[NoiseEncoderConfig],
+                 denoiser_architecture_config: DenoiserArchitectureConfig, rngs=None, gpu_mesh=None, *,
+                 params: Optional[Dict[str, np.ndarray]] = None, compute_dtype: str = "bf16",
+                 device=None, param_init: str = "reference"):
+        self._noise_cfg = noise_encoder_config or NoiseEncoderConfig()
+        self._arch = denoiser_architecture_config
+        self._rngs = rngs
+        self._params = params
+        self._compute_dtype = compute_dtype
+        self._device = device
+        self._param_init = param_init
+        self._engine: Optional[DenoiserEngine] = None
+        self._grid_key = None
+
+    # -- lazy construction, as in DenoiserArchitecture._maybe_init (denoiser.py:343-416)
+    def _maybe_init(self, inputs: Dataset, noisy_targets: Dataset, forcings: Optional[Dataset]) -> DenoiserEngine:
+        lat, lon = np.asarray(inputs.coords["lat"]), np.asarray(inputs.coords["lon"])
+        key = (lat.tobytes(), lon.tobytes())
+        if self._engine is not None:
+            if key != self._grid_key:
+                raise ValueError("Denoiser was initialised for a different lat/lon grid")
+            return self._engine
+        forc = forcings if forcings is not None else Dataset({}, inputs.coords)
+        sizes = dict(inputs.sizes)
+        sizes.setdefault("batch", 1)
+        layout = ChannelLayout(
+            num_input_channels=sum(c for _, c in stacking.channel_layout(inputs)),
+            forcing_vars=tuple(stacking.channel_layout(forc)),
+            target_vars=tuple(stacking.channel_layout(noisy_targets)))
+        st = self._arch.sparse_transformer_config
+        graphs = build_denoiser_graphs(lat, lon, self._arch.mesh_size, st.attention_k_hop,
+                                       self._arch.radius_query_fraction_edge_length)
+        if self._params is None:
+            shapes = param_shapes(self._arch, layout.num_data_channels, layout.num_targets, self._noise_cfg)
+            seed = 0
+            if self._rngs is not None:
+                seed = self._rngs.params()
+            init = init_reference_like if self._param_init == "reference" else init_perturbed
+            self._params = init(shapes, seed=seed)
+        self._engine = DenoiserEngine(graphs, self._arch, self._params, layout, self._noise_cfg,
+                                      compute_dtype=self._compute_dtype, device=self._device)
+        self._grid_key = key
+        return self._engine
+
+    @property
+    def engine(self) -> DenoiserEngine:
+        if self._engine is None:
+            raise RuntimeError("Denoiser is initialised lazily on its first call")
+        return self._engine
+
+    @property
+    def params(self) -> Dict[str, np.ndarray]:
+        return self._params
+
+    def stack_constants(self, inputs: Dataset, forcings: Optional[Dataset], sizes):
+        inp, _ = stacking.dataset_to_nodes(inputs, sizes)
+        forc = forcings if forcings is not None else Dataset({}, inputs.coords)
+        frc, _ = stacking.dataset_to_nodes(forc, sizes)
+        return inp, frc
+
+    def __call__(self, inputs: Dataset, noisy_targets: Dataset, noise_levels: DataArray,
+                 forcings: Optional[Dataset] = None, **kwargs) -> Dataset:
+        if tuple(noise_levels.dims) != ("batch",):
+            raise ValueError("noise_levels expected to be shape (batch,).")     # denoiser.py:188-189
+        engine = self._maybe_init(inputs, noisy_targets, forcings)
+        sizes = dict(noisy_targets.sizes)
+        sizes.setdefault("batch", 1)
+        batch = sizes["batch"]
+        if noise_levels.shape[0] != batch:
+            raise ValueError("noise_levels must have one entry per batch element")
+        inp, frc = self.stack_constants(inputs, forcings, sizes)
+        noisy, _ = stacking.dataset_to_nodes(noisy_targets, sizes)
+        out = np.empty((engine.G, batch, engine.n_out), np.float32)
+        with torch.cuda.device(engine.device):
+            for b in range(batch):
+                engine.set_constant_features(inp[:, b], frc[:, b])
+                engine.set_network_input(noisy[:, b])
+                f = engine.forward(engine.sigma_context(float(noise_levels.data[b])))
+                out[:, b] = f[:, :engine.n_out].cpu().numpy()
+        return stacking.nodes_to_dataset(out, noisy_targets)

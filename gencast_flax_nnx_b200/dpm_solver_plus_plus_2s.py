@@ -1,0 +1,78 @@
+"""`dpm_solver_plus_plus_2s.Sampler` of the reference, on B200 kernels.
+
+Mirrors gencast/dpm_solver_plus_plus_2s.py:21-177: same constructor arguments,
+`__call__(inputs, targets_template, forcings=None, rngs=None)` and errors.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import stacking
+from .engine import SamplerEngine, noise_schedule
+from .xarray_lite import Dataset
+
+
+class Sampler:
+    def __init__(self, denoiser, max_noise_level: float, min_noise_level: float, num_noise_levels: int,
+                 rho: float, stochastic_churn_rate: float, churn_min_noise_level: float,
+                 churn_max_noise_level: float, noise_level_inflation_factor: float, *,
+                 evaluate_discarded_call: bool = True, use_cuda_graph: bool = True):
+        self._noise_levels = noise_schedule(max_noise_level, min_noise_level, num_noise_levels, rho)
+        self._stochastic_churn = stochastic_churn_rate > 0
+        if self._stochastic_churn:
+            # The reference's loop calls utils.apply_stochastic_churn_arr, which does not exist
+            # (gencast/dpm_solver_plus_plus_2s.py:131 vs gencast/samplers_utils.py:434); both of its
+            # drivers pass 0.0 (training/train.py:167, training/evaluation.py:69).
+            raise NotImplementedError("stochastic churn is not runnable in the reference either; pass "
+                                      "stochastic_churn_rate=0.0")
+        self._churn = (churn_min_noise_level, churn_max_noise_level, noise_level_inflation_factor)
+        self._denoiser = denoiser
+        self.sigma_data = 1.0
+        self._evaluate_discarded_call = evaluate_discarded_call
+        self._use_graph = use_cuda_graph
+        self._engine: Optional[SamplerEngine] = None
+
+    @property
+    def noise_levels(self) -> np.ndarray:
+        return self._noise_levels
+
+    def sampler_engine(self) -> SamplerEngine:
+        if self._engine is None:
+            self._engine = SamplerEngine(self._denoiser.engine, self._noise_levels, self._evaluate_discarded_call)
+        return self._engine
+
+    def __call__(self, inputs: Dataset, targets_template: Dataset, forcings: Optional[Dataset] = None,
+                 rngs=None, *, init_noise: Optional[np.ndarray] = None) -> Dataset:
+        """One 12 h step.  `init_noise` ([G, batch, n_out], unit variance) overrides the generator.
+
+        The reference draws spherical-harmonic white noise (samplers_utils.py:333-346, dinosaur);
+        here the default is white noise in grid space drawn on the device from `rngs.noise()`.
+        Surface variables are carried once (the reference broadcasts them over 13 levels and
+        selects level 0, :59, :93-95 -- an equivalent state).
+        """
+        if rngs is None:
+            raise ValueError("Must pass rngs: nnx.Rngs(...) to Sampler")          # :54-55
+        key = rngs.noise()
+        den = self._denoiser
+        engine = den._maybe_init(inputs, targets_template, forcings)
+        sizes = dict(targets_template.sizes)
+        sizes.setdefault("batch", 1)
+        batch = sizes["batch"]
+        inp, frc = den.stack_constants(inputs, forcings, sizes)
+        se = self.sampler_engine()
+        out = np.empty((engine.G, batch, engine.n_out), np.float32)
+        with torch.cuda.device(engine.device):
+            gen = torch.Generator(device=engine.device)
+            gen.manual_seed(int(key) & 0x7FFFFFFFFFFFFFFF)
+            for b in range(batch):
+                engine.set_constant_features(inp[:, b], frc[:, b])
+                if init_noise is not None:
+                    noise = torch.as_tensor(np.ascontiguousarray(init_noise[:, b]), dtype=torch.float32)
+                else:
+                    noise = torch.randn(engine.G, engine.n_out, generator=gen, device=engine.device)
+                res = se.sample(noise, use_graph=self._use_graph)
+                out[:, b] = res.cpu().numpy()
+        return stacking.nodes_to_dataset(out, targets_template)

@@ -133,3 +133,48 @@ def mlp_prefixes():
         transformer=_TFM,
         noise_encoder=_ENC,
     )
+
+
+def init_reference_like(shapes: Dict[str, Tuple[int, ...]], seed: int = 0, num_layers: int = 16,
+                        attn_final_mult: float = 0.0, ffw_final_mult: float = 0.0) -> Dict[str, np.ndarray]:
+    """Same initial *distributions* as the reference (not the same draws: NNX's RNG is JAX threefry).
+
+    MLP kernels xavier-uniform, biases 0 (common/mlp.py:167-199); conditional linears
+    truncated-normal(1e-8) (common/mlp.py:43-46); q/k/v and the first FFW layer
+    variance_scaling(2/num_layers, fan_in, truncated normal) (gencast/sparse_transformer.py:256,275);
+    attention output projection and second FFW layer variance_scaling(mult/num_layers), mult = 0 by
+    default, i.e. zeros (gencast/denoiser.py:93-95, sparse_transformer.py:257,302); noise-level encoder
+    variance_scaling(2, fan_in, uniform) (common/mlp.py:225-228).
+    """
+    rng = np.random.default_rng(seed)
+
+    def trunc_normal(shape, std):
+        x = rng.standard_normal(shape)
+        bad = np.abs(x) > 2
+        while bad.any():
+            x[bad] = rng.standard_normal(int(bad.sum()))
+            bad = np.abs(x) > 2
+        return x * std / 0.87962566103423978   # jax's truncated-normal variance correction
+
+    out = {}
+    for name, shape in shapes.items():
+        if name.endswith("/bias"):
+            out[name] = np.zeros(shape, np.float32)
+            continue
+        fan_in, fan_out = shape
+        if "conditional_linear_layer" in name:
+            w = trunc_normal(shape, 1e-8)
+        elif "/noise_level_encoder/" in name:
+            lim = np.sqrt(3.0 * 2.0 / fan_in)
+            w = rng.uniform(-lim, lim, shape)
+        elif "/attn_module/final_linear/" in name:
+            w = trunc_normal(shape, np.sqrt(attn_final_mult / num_layers / fan_in)) if attn_final_mult > 0 else np.zeros(shape)
+        elif "/ffw_module/mlp/layers/2/" in name:
+            w = trunc_normal(shape, np.sqrt(ffw_final_mult / num_layers / fan_in)) if ffw_final_mult > 0 else np.zeros(shape)
+        elif "/attn_module/" in name or "/ffw_module/" in name:
+            w = trunc_normal(shape, np.sqrt(2.0 / num_layers / fan_in))
+        else:
+            lim = np.sqrt(6.0 / (fan_in + fan_out))
+            w = rng.uniform(-lim, lim, shape)
+        out[name] = w.astype(np.float32)
+    return out

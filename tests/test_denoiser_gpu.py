@@ -1,0 +1,96 @@
+"""Parity of the CUDA denoiser and sampler against the CPU oracle (fp64 restatement of the
+reference, oracle/gencast_oracle.py) on seeded inputs and perturbed weights.
+
+Tolerances (BASELINE.json north_star / BASELINE.md §4): fp32 path max relative error per
+variable <= 1e-3 for one denoiser call; bf16 path <= 2e-2 against the same oracle.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_case, oracle_forward, per_variable_error
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"f32": 1e-3, "bf16": 2e-2}
+
+
+def _engine(case, dtype):
+    from gencast_flax_nnx_b200.engine import DenoiserEngine
+    return DenoiserEngine(case.graphs, case.arch, case.params, case.layout, compute_dtype=dtype)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("name,sigmas", [("tiny", (80.0, 1.0, 0.03)), ("nano", (1.0,))])
+def test_single_forward_matches_oracle(cuda_device, name, sigmas, dtype):
+    case = make_case(name)
+    eng = _engine(case, dtype)
+    rng = np.random.default_rng(2)
+    eng.set_constant_features(case.inp_nodes[:, 0], case.frc_nodes[:, 0])
+    for sigma in sigmas:
+        x = rng.standard_normal((eng.G, eng.n_out)).astype(np.float32)
+        eng.set_network_input(x)
+        got = eng.forward(eng.sigma_context(sigma))[:, :eng.n_out].cpu().numpy()
+        ref = oracle_forward(case, x, sigma)
+        errs = per_variable_error(case, got, ref)
+        worst = max(errs.values())
+        print(f"{name} {dtype} sigma={sigma}: worst per-variable error {worst:.3e}")
+        assert worst <= TOL[dtype], errs
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_sampler_matches_oracle(cuda_device, dtype):
+    """Full DPM-Solver++ 2S loop on the tiny case with a 4-level schedule (7 network evaluations)."""
+    from gencast_flax_nnx_b200.engine import SamplerEngine, noise_schedule
+    from oracle import gencast_oracle as o
+    case = make_case("tiny")
+    eng = _engine(case, dtype)
+    sigmas = noise_schedule(80.0, 0.03, 4, 7.0)
+    np.testing.assert_allclose(sigmas, o.noise_schedule(80.0, 0.03, 4, 7.0))
+    eng.set_constant_features(case.inp_nodes[:, 0], case.frc_nodes[:, 0])
+    noise = np.random.default_rng(3).standard_normal((eng.G, eng.n_out)).astype(np.float32)
+    results = {}
+    for discard in (True, False):
+        se = SamplerEngine(eng, sigmas, evaluate_discarded_call=discard)
+        eager = se.sample(noise, use_graph=False).cpu().numpy().copy()
+        graphed = se.sample(noise, use_graph=True).cpu().numpy().copy()
+        again = se.sample(noise, use_graph=True).cpu().numpy().copy()
+        assert np.array_equal(eager, graphed) and np.array_equal(graphed, again)   # deterministic, graph == eager
+        results[discard] = eager
+    assert np.array_equal(results[True], results[False])       # the discarded call cannot change the result
+    dt = torch.float64
+    init = case.split_targets(torch.as_tensor(noise[:, None, :] * sigmas[0]).to(dt))
+    frc = {k: torch.as_tensor(v).to(dt) for k, v in case.frc_vars.items()}
+    ref = o.dpm_solver_2s(case.params, case.oracle_graph, case.oracle_arch, torch.as_tensor(case.inp_nodes).to(dt),
+                          frc, init, sigmas, dt)
+    ref = torch.cat([ref[n] for n, _ in case.target_vars], dim=-1)[:, 0].numpy()
+    errs = per_variable_error(case, results[True], ref)
+    print(f"sampler {dtype}: worst per-variable error {max(errs.values()):.3e}")
+    assert max(errs.values()) <= (2e-3 if dtype == "f32" else 5e-2), errs
+
+
+def test_public_api_round_trip(cuda_device):
+    """GenCast.full_sampling / Denoiser.__call__ through Datasets equal the engine on arrays."""
+    from gencast_flax_nnx_b200 import configs, gencast, stacking
+    from gencast_flax_nnx_b200.rngs import Rngs
+    from gencast_flax_nnx_b200.xarray_lite import DataArray
+    case = make_case("tiny")
+    res, arch = configs.named_config("tiny")
+    sc = configs.SamplerConfig(num_noise_levels=3, stochastic_churn_rate=0.0)
+    model = gencast.GenCast(configs.TASK, arch, sampler_config=sc, rngs=Rngs(0), params=case.params,
+                            compute_dtype="f32")
+    noisy = np.random.default_rng(5).standard_normal((case.graphs.num_grid_nodes, 1, 82)).astype(np.float32)
+    noisy_ds = stacking.nodes_to_dataset(noisy, case.targets)
+    out = model.denoiser(case.inputs, noisy_ds, DataArray(np.array([1.0], np.float32), ("batch",)), case.forcings)
+    got, _ = stacking.dataset_to_nodes(out, dict(case.targets.sizes))
+    ref = oracle_forward(case, noisy[:, 0], 1.0)
+    assert max(per_variable_error(case, got[:, 0], ref).values()) <= 1e-3
+    with pytest.raises(ValueError):
+        model.denoiser(case.inputs, noisy_ds, DataArray(np.ones((1, 1), np.float32), ("batch", "x")), case.forcings)
+    pred = model.full_sampling(case.inputs, case.targets, case.forcings)
+    assert set(pred.keys()) == set(case.targets.keys())
+    for k in pred.keys():
+        assert pred[k].dims == case.targets[k].dims and pred[k].shape == case.targets[k].shape
+        assert np.isfinite(pred[k].data).all()
+    with pytest.raises(ValueError):
+        model._sampler(case.inputs, case.targets, case.forcings, rngs=None)
