@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Benchmark of the GenCast sampling hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config nano|1deg|tiny] [--dtype bf16|f32]
+  python bench.py --impl reference ...      # the reference algorithm's CPU restatement (oracle/) on host cores
+
+One "step" = one 12 h forecast step of one ensemble member: the 20-level DPM-Solver++ 2S
+loop, 40 denoiser evaluations (the reference evaluates and discards the 40th; so do we).
+Members are independent: rank r runs member r (weak scaling, no collective on the data
+path); with N > 1 the per-step ensemble sum / sum-of-squares is all-reduced over NCCL.
+`value` = members x steps / max-over-ranks device time with inputs resident in HBM.
+`e2e` = the same through GenCast.full_sampling with host Datasets (H2D of the step's
+inputs from pinned memory and D2H of the prediction inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "12h_forecast_steps_per_sec"
+UNIT = "member-steps/s"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tensor_burst=p["bf16_tflops"], tensor_sustained=p["bf16_tflops_sustained"],
+                    source="measured")
+    except Exception:
+        return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_case(config: str, seed: int = 0):
+    from gencast_flax_nnx_b200 import configs, graph, params, stacking, synthetic
+    from gencast_flax_nnx_b200.engine import ChannelLayout
+    res, arch = configs.named_config(config)
+    lat, lon = graph.regular_grid(res)
+    inputs, targets, forcings = synthetic.make_example(lat, lon, batch=1, seed=seed)
+    sizes = dict(targets.sizes)
+    inp_nodes, _ = stacking.dataset_to_nodes(inputs, sizes)
+    frc_nodes, frc_layout = stacking.dataset_to_nodes(forcings, sizes)
+    layout = ChannelLayout(num_input_channels=inp_nodes.shape[-1], forcing_vars=tuple(frc_layout),
+                           target_vars=tuple(stacking.channel_layout(targets)))
+    shapes = params.param_shapes(arch, layout.num_data_channels, layout.num_targets)
+    p = params.init_perturbed(shapes, seed=1)     # random O(1/sqrt(fan_in)) weights
+    return dict(res=res, arch=arch, lat=lat, lon=lon, inputs=inputs, targets=targets, forcings=forcings,
+                inp_nodes=inp_nodes, frc_nodes=frc_nodes, frc_layout=frc_layout, layout=layout, params=p)
+
+
+def workload_name(config: str) -> str:
+    return {"nano": "nano-GenCast 2.5deg (73x144 grid, mesh 4, L=256, 16 layers, k-hop 8), one member per GPU, "
+                    "12 h step = 20-level DPM-Solver++ 2S",
+            "1deg": "GenCast 1deg (181x360 grid, mesh 5, L=512, 16 layers, k-hop 8), one member per GPU, "
+                    "12 h step = 20-level DPM-Solver++ 2S",
+            "tiny": "test-size GenCast 10deg (19x36 grid, mesh 2, L=128, 2 layers), 12 h step = 20-level DPM-Solver++ 2S",
+            }[config]
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm as written, restated in torch fp32 (oracle/), on host cores
+# ----------------------------------------------------------------------------------------------
+
+def cpu_solver_iteration_seconds(case, repeats: int, warmup: int = 0):
+    """Times one solver iteration (2 denoiser evaluations + updates) of the oracle on all host cores."""
+    import torch
+    from oracle import gencast_oracle as o
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = case["graphs_oracle"]
+    dt = torch.float32
+    G, n_out = case["inp_nodes"].shape[0], case["layout"].num_targets
+    rng = np.random.default_rng(7)
+    tv = sorted(case["layout"].target_vars)
+    x, i = {}, 0
+    noise = torch.as_tensor(rng.standard_normal((G, 1, n_out)).astype(np.float32)) * 80.0
+    for n, c in tv:
+        x[n] = noise[:, :, i:i + c]
+        i += c
+    frc, i = {}, 0
+    for n, c in case["frc_layout"]:
+        frc[n] = torch.as_tensor(case["frc_nodes"][:, :, i:i + c])
+        i += c
+    inp = torch.as_tensor(case["inp_nodes"])
+    st = case["arch"].sparse_transformer_config
+    arch = dict(num_layers=st.num_layers, num_heads=st.num_heads)
+    sig = [80.0, 60.0]
+    times = []
+    with torch.no_grad():
+        for r in range(warmup + repeats):
+            t0 = time.perf_counter()
+            o.dpm_solver_2s(case["params"], g, arch, inp, frc, x, sig, dt, num_steps=1)
+            if r >= warmup:
+                times.append(time.perf_counter() - t0)
+    return times
+
+
+def oracle_graph(case):
+    from gencast_flax_nnx_b200 import graph
+    st = case["arch"].sparse_transformer_config
+    g = graph.build_denoiser_graphs(case["lat"], case["lon"], case["arch"].mesh_size, st.attention_k_hop)
+    case["graphs"] = g
+    case["graphs_oracle"] = dict(g2m_grid_feat=g.g2m_grid_feat, g2m_mesh_feat=g.g2m_mesh_feat,
+                                 g2m_edge_feat=g.g2m_edge_feat, g2m_senders=g.g2m_senders,
+                                 g2m_receivers=g.g2m_receivers, m2g_senders=g.m2g_senders,
+                                 m2g_receivers=g.m2g_receivers, m2g_edge_feat=g.m2g_edge_feat, khop=g.khop)
+    return g
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    case = build_case(args.config)
+    oracle_graph(case)
+    iters_per_step = 20
+    times = cpu_solver_iteration_seconds(case, repeats=args.steps, warmup=min(args.warmup, 1))
+    t_iter = float(np.mean(times))
+    value = 1.0 / (t_iter * iters_per_step)
+    sample = ("each timed step = 1 of the 20 solver iterations (2 denoiser evaluations + updates) of the torch-fp32 "
+              "restatement of the reference algorithm (dense tri-block attention, [e|s|r] concat, scatter-add); "
+              "12 h step time = 20 x that")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_iter * iters_per_step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.config), "members": 1},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from gencast_flax_nnx_b200 import configs, gencast, ops
+    from gencast_flax_nnx_b200.engine import DenoiserEngine, SamplerEngine, noise_schedule
+    from gencast_flax_nnx_b200.rngs import Rngs
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    case = build_case(args.config)
+    graphs = oracle_graph(case)
+    eng = DenoiserEngine(graphs, case["arch"], case["params"], case["layout"], compute_dtype=args.dtype, device=dev)
+    sigmas = noise_schedule(80.0, 0.03, 20, 7.0)
+    se = SamplerEngine(eng, sigmas, evaluate_discarded_call=True)
+    eng.set_constant_features(case["inp_nodes"][:, 0], case["frc_nodes"][:, 0])
+    G, C = eng.G, eng.n_out
+    gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+    noises = [torch.randn(G, C, generator=gen, device=dev) for _ in range(max(args.steps, 1))]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    ens_sum = torch.zeros(G, C, device=dev); ens_sq = torch.zeros(G, C, device=dev)
+    red = torch.zeros(2, G, C, device=dev)
+
+    def one_step(noise):
+        out = se.sample(noise, use_graph=True)
+        if world > 1:
+            red[0].copy_(out); torch.mul(out, out, out=red[1])
+            dist.all_reduce(red)           # ensemble sum / sum of squares over members (mean, spread)
+        return out
+
+    for i in range(args.warmup):
+        one_step(noises[i % len(noises)])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)           # evict L2 between timed steps (not timed)
+            starts[i].record()
+            one_step(noises[i])
+            ends[i].record()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    dev_ms = sum(a.elapsed_time(b) for a, b in zip(starts, ends))
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * args.steps / (total_ms / 1e3)
+    clock_summary = clocks.summary()
+
+    # ---- e2e through the public API: host Datasets in, host Dataset out
+    sc = configs.SamplerConfig(stochastic_churn_rate=0.0)
+    model = gencast.GenCast(configs.TASK, case["arch"], sampler_config=sc, rngs=Rngs(rank), params=case["params"],
+                            compute_dtype=args.dtype, device=dev)
+    model.denoiser._engine = eng                                   # share the resident weights / graph tables
+    model.denoiser._grid_key = (np.asarray(case["inputs"].coords["lat"]).tobytes(),
+                                np.asarray(case["inputs"].coords["lon"]).tobytes())
+    model._sampler._engine = se
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        model.full_sampling(case["inputs"], case["targets"], case["forcings"])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pred = model.full_sampling(case["inputs"], case["targets"], case["forcings"])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps / float(t.item())
+    h2d = (case["layout"].num_input_channels + case["layout"].num_forcings) * G * 4
+    d2h = C * G * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline leg: per-kernel CUDA-event timing of one eager sampling step (rank 0)
+    peaks = _peaks()
+    rec = ops.Recorder()
+    se.sample(noises[0], use_graph=False)
+    torch.cuda.synchronize()
+    ops.set_recorder(rec)
+    se.sample(noises[0], use_graph=False)
+    ops.set_recorder(None)
+    agg = rec.summary()
+    tot_ms = sum(d["ms"] for d in agg.values())
+    kernels = {}
+    for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        avg_ms = d["ms"] / d["launches"]
+        k = {"launches": d["launches"], "avg_us": 1e3 * avg_ms, "share": d["ms"] / tot_ms}
+        if d["flops"] > 0:
+            k["tflops"] = d["flops"] / d["ms"] / 1e9
+        k["gbs"] = d["bytes"] / d["ms"] / 1e6
+        kernels[name] = k
+    dom = next(iter(kernels))
+    domk = kernels[dom]
+    tensor_bound = dom.startswith("gemm_bf16") or dom.startswith("khop_attention_tc")
+    if tensor_bound:
+        roof = {"kernel": dom, "bound": "tensor", "achieved": domk["tflops"], "peak": peaks["tensor_sustained"],
+                "unit": "TFLOP/s", "frac": domk["tflops"] / peaks["tensor_sustained"], "traffic": None}
+    else:
+        roof = {"kernel": dom, "bound": "hbm", "achieved": domk["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": domk["gbs"] / peaks["hbm"], "traffic": None}
+    roof["peak_source"] = peaks["source"] + (" (sustained bf16 GEMM)" if tensor_bound else " (copy bandwidth)")
+    roof["avg_launch_us"] = domk["avg_us"]
+    roof["share_of_step"] = domk["share"]
+
+    # ---- single denoiser evaluation latency (graph-free, events)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx = se.ctx[5]
+    for _ in range(3):
+        eng.forward(ctx)
+    a.record()
+    for _ in range(10):
+        eng.forward(ctx)
+    b.record()
+    torch.cuda.synchronize()
+    fwd_ms_eager = a.elapsed_time(b) / 10
+    fwd_ms_graph = total_ms / args.steps / se.num_network_evaluations
+
+    # ---- CPU baseline beside it (bounded sample; rank 0, N = 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        reps = 2 if args.config == "nano" else 1
+        times = cpu_solver_iteration_seconds(case, repeats=reps, warmup=1 if args.config != "1deg" else 0)
+        v = 1.0 / (float(np.mean(times)) * 20)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{reps} of the 20 solver iterations (2 denoiser evaluations each) of the torch-fp32 oracle "
+                         f"of the reference algorithm, all host threads; step time = 20 x mean iteration"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(args.config), "members": world,
+                       "denoiser_evaluations_per_step": se.num_network_evaluations,
+                       "weights": "random N(0, 1/fan_in) (reference init makes the transformer an identity)",
+                       "l2": "flushed between timed steps (256 MiB write, not timed)",
+                       "execution": "one CUDA graph per 12 h step",
+                       "collective": "nccl all_reduce of ensemble sum / sum-of-squares per step" if world > 1 else "none"},
+            "denoiser_fwd_ms": fwd_ms_graph, "denoiser_fwd_ms_eager_launch": fwd_ms_eager,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "GenCast.full_sampling(inputs, targets_template, forcings)"},
+            "gpu_launches": args.steps * se.launches_per_step,
+            "clocks": clock_summary, "roofline": roofline_clean(roof), "kernels": kernels}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline_clean(r):
+    return {k: (float(v) if isinstance(v, (np.floating, float)) else v) for k, v in r.items()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
+    ap.add_argument("--config", default="nano", choices=["tiny", "nano", "1deg"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

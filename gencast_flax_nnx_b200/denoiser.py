@@ -108,5 +108,5 @@ class Denoiser:
                 engine.set_constant_features(inp[:, b], frc[:, b])
                 engine.set_network_input(noisy[:, b])
                 f = engine.forward(engine.sigma_context(float(noise_levels.data[b])))
-                out[:, b] = f[:, :engine.n_out].cpu().numpy()
+                out[:, b] = engine.read_output(f)
         return stacking.nodes_to_dataset(out, noisy_targets)

@@ -70,9 +70,9 @@ class Sampler:
             for b in range(batch):
                 engine.set_constant_features(inp[:, b], frc[:, b])
                 if init_noise is not None:
-                    noise = torch.as_tensor(np.ascontiguousarray(init_noise[:, b]), dtype=torch.float32)
+                    noise = np.ascontiguousarray(init_noise[:, b], dtype=np.float32)
                 else:
                     noise = torch.randn(engine.G, engine.n_out, generator=gen, device=engine.device)
                 res = se.sample(noise, use_graph=self._use_graph)
-                out[:, b] = res.cpu().numpy()
+                out[:, b] = engine.read_output(res)
         return stacking.nodes_to_dataset(out, targets_template)

@@ -324,20 +324,51 @@ class DenoiserEngine:
         return ctx
 
     # ------------------------------------------------------------------ inputs
+    def _stage(self, name: str, cols: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(pinned host, device) fp32 staging pair of shape [G, cols], allocated once."""
+        st = self.__dict__.setdefault("_staging", {})
+        if name not in st:
+            st[name] = (torch.empty(self.G, cols, dtype=torch.float32, pin_memory=True),
+                        torch.empty(self.G, cols, dtype=torch.float32, device=self.device))
+        return st[name]
+
+    def _to_device_f32(self, name: str, parts: Sequence) -> torch.Tensor:
+        """Host arrays go through pinned memory (async H2D on the current stream); device tensors are used as is."""
+        cols = sum(int(np.prod(p.shape)) // self.G for p in parts)
+        if all(isinstance(p, torch.Tensor) and p.is_cuda for p in parts):
+            t = torch.cat([p.reshape(self.G, -1).to(torch.float32) for p in parts], dim=1)
+            return t.contiguous()
+        pin, dev = self._stage(name, cols)
+        c = 0
+        for p in parts:
+            a = p.detach().cpu().numpy() if isinstance(p, torch.Tensor) else np.asarray(p)
+            a = a.reshape(self.G, -1)
+            pin[:, c:c + a.shape[1]] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+            c += a.shape[1]
+        dev.copy_(pin, non_blocking=True)
+        return dev
+
     def set_constant_features(self, inputs_nodes, forcings_nodes) -> None:
         """Per-step constants: stacked inputs [G, C_in] and forcings [G, C_f] (host or device, fp32)."""
         ni, nf = self.layout.num_input_channels, self.layout.num_forcings
-        x = torch.as_tensor(inputs_nodes, dtype=torch.float32).reshape(self.G, ni)
-        f = torch.as_tensor(forcings_nodes, dtype=torch.float32).reshape(self.G, nf)
         with torch.cuda.device(self.device):
-            cat = torch.cat([x.to(self.device, non_blocking=True), f.to(self.device, non_blocking=True)], dim=1).contiguous()
+            cat = self._to_device_f32("const", [inputs_nodes, forcings_nodes])
+            if cat.shape[1] != ni + nf:
+                raise ValueError(f"expected {ni} input + {nf} forcing channels, got {cat.shape[1]}")
             ops.cast_pad(cat, self.a_const[:, 3:3 + ni + nf])
 
     def set_network_input(self, scaled_noisy_targets) -> None:
         """c_in * noisy targets, [G, n_out] fp32 (host or device)."""
-        x = torch.as_tensor(scaled_noisy_targets, dtype=torch.float32).reshape(self.G, self.n_out)
         with torch.cuda.device(self.device):
-            ops.cast_pad(x.to(self.device).contiguous(), self.xin[:, :self.n_out])
+            x = self._to_device_f32("xin", [scaled_noisy_targets])
+            ops.cast_pad(x, self.xin[:, :self.n_out])
+
+    def read_output(self, src: torch.Tensor) -> np.ndarray:
+        """Device [G, >= n_out] fp32 -> host [G, n_out] through pinned memory (blocking)."""
+        pin, _ = self._stage("out", self.n_out)
+        pin.copy_(src[:, :self.n_out], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return pin.numpy().copy()
 
     # ------------------------------------------------------------------ forward
     def _mlp_ln(self, segs, w1b, w2, b2, h, y, out, so, residual=None, gathers=(), act="swish"):
@@ -504,7 +535,7 @@ class SamplerEngine:
         e = self.engine
         with torch.cuda.device(e.device):
             if noise is not None:
-                self.noise.copy_(torch.as_tensor(noise, dtype=torch.float32).reshape(e.G, e.n_out), non_blocking=True)
+                self.noise.copy_(e._to_device_f32("noise", [noise]), non_blocking=True)
             if not use_graph:
                 self._enqueue()
                 return self.result

@@ -14,6 +14,65 @@ import torch
 from . import _lib
 from ._lib import GC_ACT_GELU_TANH, GC_ACT_NONE, GC_ACT_SWISH, GC_BF16, GC_F32, GemmArgs
 
+# Optional per-launch timing (bench.py's roofline leg): when a recorder is installed every
+# launcher is bracketed by CUDA events on the launching stream and reports its
+# algorithmic FLOPs / bytes.  Never active during graph capture or normal runs.
+_RECORDER = None
+
+
+def set_recorder(rec) -> None:
+    global _RECORDER
+    _RECORDER = rec
+
+
+class Recorder:
+    def __init__(self):
+        self.items = []      # (name, start_event, end_event, flops, bytes)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, a, b, fl, by in self.items:
+            d = agg.setdefault(name, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+            d["launches"] += 1; d["ms"] += a.elapsed_time(b); d["flops"] += fl; d["bytes"] += by
+        return agg
+
+
+def _recorded(name, cost):
+    def deco(fn):
+        def wrapper(*args, **kw):
+            rec = _RECORDER
+            if rec is None:
+                return fn(*args, **kw)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = fn(*args, **kw)
+            b.record()
+            fl, by = cost(*args, **kw)
+            rec.items.append((name(*args, **kw) if callable(name) else name, a, b, fl, by))
+            return out
+        wrapper.__doc__ = fn.__doc__
+        wrapper.__name__ = fn.__name__
+        return wrapper
+    return deco
+
+
+def _nbytes(*ts):
+    return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
+
+
+def _gemm_cost(segments, out, *, bias=None, act=None, addend=None, gathers=(), residual=None, alpha=None):
+    m, n = out.shape
+    flops = 2.0 * m * n * sum(a.shape[1] for a, _ in segments)
+    by = sum(_nbytes(a, w) for a, w in segments) + _nbytes(out, addend, residual)
+    by += sum(m * n * src.element_size() + 4.0 * m for src, _ in gathers)
+    return flops, by
+
+
+def _gemm_name(segments, out, **kw):
+    return "gemm_bf16_tcgen05" if segments[0][0].dtype == torch.bfloat16 else "gemm_f32_ffma"
+
+
 ACT = {None: GC_ACT_NONE, "none": GC_ACT_NONE, "swish": GC_ACT_SWISH, "gelu_tanh": GC_ACT_GELU_TANH}
 
 
@@ -42,6 +101,7 @@ def _row_major(t: torch.Tensor, what: str) -> int:
     return t.stride(0)
 
 
+@_recorded(_gemm_name, _gemm_cost)
 def gemm(segments: Sequence[Tuple[torch.Tensor, torch.Tensor]], out: torch.Tensor, *,
          bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
          addend: Optional[torch.Tensor] = None,
@@ -85,6 +145,7 @@ def gemm(segments: Sequence[Tuple[torch.Tensor, torch.Tensor]], out: torch.Tenso
     return out
 
 
+@_recorded("ln_cond", lambda x, out, so, **kw: (0.0, _nbytes(x, out, kw.get("residual"))))
 def ln_cond(x: torch.Tensor, out: torch.Tensor, scale_offset: Optional[torch.Tensor], *,
             layer_norm: bool = True, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.load()
@@ -96,6 +157,7 @@ def ln_cond(x: torch.Tensor, out: torch.Tensor, scale_offset: Optional[torch.Ten
     return out
 
 
+@_recorded("ln_cond_segment_sum", lambda y, out, so, rp, perm, **kw: (0.0, _nbytes(y, out, rp, perm)))
 def ln_cond_segment_sum(y: torch.Tensor, out: torch.Tensor, scale_offset: Optional[torch.Tensor],
                         row_ptr: torch.Tensor, edge_perm: Optional[torch.Tensor], *, layer_norm: bool = True):
     lib = _lib.load()
@@ -108,6 +170,7 @@ def ln_cond_segment_sum(y: torch.Tensor, out: torch.Tensor, scale_offset: Option
     return out
 
 
+@_recorded("khop_attention", lambda qkv, out, ptr, idx, heads, head_dim, *a: (4.0 * idx.numel() * heads * head_dim, _nbytes(qkv, out, ptr, idx)))
 def khop_attention(qkv: torch.Tensor, out: torch.Tensor, nbr_ptr: torch.Tensor, nbr_idx: torch.Tensor,
                    heads: int, head_dim: int, max_degree: int = 0) -> torch.Tensor:
     lib = _lib.load()
@@ -139,6 +202,7 @@ def fold_affine_into_linear(w: torch.Tensor, bias: Optional[torch.Tensor], scale
     return w_out, bias_out
 
 
+@_recorded("dpm_update", lambda f, x_cur, x_base, sched, x_out, xin_out, cols: (0.0, 4.0 * x_cur.shape[0] * cols * 4 + (0 if xin_out is None else x_cur.shape[0] * cols * xin_out.element_size())))
 def dpm_update(f: torch.Tensor, x_cur: torch.Tensor, x_base: torch.Tensor, sched: torch.Tensor,
                x_out: torch.Tensor, xin_out: Optional[torch.Tensor], cols: int):
     lib = _lib.load()
