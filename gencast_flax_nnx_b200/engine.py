@@ -40,7 +40,7 @@ import torch
 
 from . import ops
 from .configs import DenoiserArchitectureConfig, NoiseEncoderConfig
-from .graph import DenoiserGraphs, csr_by_receiver
+from .graph import DenoiserGraphs, csr_by_receiver, khop_tiles, patch_order
 from .params import COND_DIM, mlp_prefixes
 
 _DTYPES = {"bf16": torch.bfloat16, "f32": torch.float32}
@@ -110,7 +110,12 @@ class DenoiserEngine:
 
     def __init__(self, graphs: DenoiserGraphs, arch: DenoiserArchitectureConfig, params: Dict[str, np.ndarray],
                  layout: ChannelLayout, noise_cfg: NoiseEncoderConfig = NoiseEncoderConfig(),
-                 compute_dtype: str = "bf16", device: Optional[torch.device] = None):
+                 compute_dtype: str = "bf16", device: Optional[torch.device] = None,
+                 mesh_order: str = "patch", attention: str = "auto"):
+        """mesh_order: 'patch' relabels mesh nodes into compact 128-node patches (fewer attention
+        tiles), 'reference' keeps the reference's band ordering.  attention: 'auto' uses the
+        tensor-core tile kernel for bf16 with head_dim 64/128 and the CSR kernel otherwise;
+        'csr' forces the CSR kernel."""
         if not torch.cuda.is_available():
             raise RuntimeError("DenoiserEngine needs a CUDA device: there is no CPU path")
         ops._lib.load()
@@ -135,6 +140,8 @@ class DenoiserEngine:
         self.NO = _pad_to(self.n_out, 128)
         self._p = params
         self._pre = mlp_prefixes()
+        self.mesh_order = mesh_order
+        self.use_tc_attention = (attention == "auto" and compute_dtype == "bf16" and self.head_dim in (64, 128))
         self._sigma_cache: Dict[float, SigmaContext] = {}
         with torch.cuda.device(self.device):
             self._upload_graph()
@@ -178,11 +185,24 @@ class DenoiserEngine:
     def _upload_graph(self):
         g = self.graphs
         i32 = torch.int32
+        # Internal mesh relabelling: position i holds reference mesh node order[i].
+        if self.mesh_order == "patch":
+            order = patch_order(g.mesh.vertices, 128)
+        elif self.mesh_order == "reference":
+            order = np.arange(self.V)
+        else:
+            raise ValueError(f"mesh_order={self.mesh_order!r}")
+        inv = np.empty(self.V, np.int64)
+        inv[order] = np.arange(self.V)
+        self.mesh_perm = order
+        g2m_recv = inv[g.g2m_receivers]
+        m2g_send = inv[g.m2g_senders]
+        self._mesh_feat = g.g2m_mesh_feat[order]
         self.g2m_s = self._dev(g.g2m_senders.astype(np.int32))
-        self.g2m_r = self._dev(g.g2m_receivers.astype(np.int32))
-        rp, perm = csr_by_receiver(g.g2m_receivers, self.V)
+        self.g2m_r = self._dev(g2m_recv.astype(np.int32))
+        rp, perm = csr_by_receiver(g2m_recv, self.V)
         self.g2m_row_ptr, self.g2m_perm = self._dev(rp), self._dev(perm)
-        self.m2g_s = self._dev(g.m2g_senders.astype(np.int32))
+        self.m2g_s = self._dev(m2g_send.astype(np.int32))
         self.m2g_r = self._dev(g.m2g_receivers.astype(np.int32))
         # mesh2grid edges are emitted grid-major, three per grid node
         # (common/grid_mesh_connectivity.py:125-131): already receiver sorted.
@@ -192,11 +212,18 @@ class DenoiserEngine:
         else:
             self.m2g_row_ptr = torch.arange(0, 3 * self.G + 1, 3, dtype=i32, device=self.device)
             self.m2g_perm = None
-        khop = g.khop.tocsr()
+        khop = g.khop.tocsr()[order][:, order].tocsr()
         khop.sort_indices()
-        self.nbr_ptr = self._dev(khop.indptr.astype(np.int32))
-        self.nbr_idx = self._dev(khop.indices.astype(np.int32))
+        self.khop_nnz = int(khop.nnz)
         self.max_degree = int(np.diff(khop.indptr).max())
+        if self.use_tc_attention:
+            tp, tk, tm = khop_tiles(khop, 128)
+            self.tile_ptr, self.tile_kv = self._dev(tp), self._dev(tk)
+            self.tile_mask = self._dev(tm.view(np.int32)).view(torch.int32)
+            self.num_attention_tiles = int(len(tk))
+        else:
+            self.nbr_ptr = self._dev(khop.indptr.astype(np.int32))
+            self.nbr_idx = self._dev(khop.indices.astype(np.int32))
 
     def _upload_weights(self):
         p, pre, L = self._p, self._pre, self.L
@@ -299,7 +326,7 @@ class DenoiserEngine:
         self.g2m_e_ln = self._static_embed(pre["g2m_edge_embed"], g.g2m_edge_feat, slice(0, 4))
         self.m2g_e_ln = self._static_embed(pre["m2g_edge_embed"], g.m2g_edge_feat, slice(0, 4))
         # mesh nodes: [structural | zeros] (gencast/denoiser.py:640-657) -> only the first 3 kernel rows matter
-        self.m0_ln = self._static_embed(pre["g2m_mesh_embed"], g.g2m_mesh_feat, slice(0, 3))
+        self.m0_ln = self._static_embed(pre["g2m_mesh_embed"], self._mesh_feat, slice(0, 3))
         # structural part of the constant grid operand
         self.a_const[:, :3] = self._dev(g.g2m_grid_feat, self.cd)
 
@@ -423,7 +450,11 @@ class DenoiserEngine:
         return self.f_out
 
     def _attention(self):
-        ops.khop_attention(self.t_qkv, self.t_o, self.nbr_ptr, self.nbr_idx, self.H, self.head_dim, self.max_degree)
+        if self.use_tc_attention:
+            ops.khop_attention_tiles(self.t_qkv, self.t_o, self.tile_ptr, self.tile_kv, self.tile_mask, self.H,
+                                     self.head_dim, self.khop_nnz)
+        else:
+            ops.khop_attention(self.t_qkv, self.t_o, self.nbr_ptr, self.nbr_idx, self.H, self.head_dim, self.max_degree)
 
     LAUNCHES_PER_FORWARD_FIXED = 15 + 1 + 10   # encoder + final norm + decoder
 

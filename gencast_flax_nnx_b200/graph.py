@@ -357,6 +357,59 @@ def mask_block_size(mask: sparse.spmatrix) -> int:
     return int(max(lower, upper))
 
 
+def khop_tiles(khop: sparse.spmatrix, tile: int = 128):
+    """Block-sparse form of the k-hop pattern for the tensor-core attention kernel.
+
+    Returns (tile_ptr[nq+1] i32, tile_kv[nt] i32, tile_mask[nt, tile, tile//32] u32): for each
+    query tile the non-empty key tiles in ascending order and one bit mask per pair (bit j%32 of
+    word j//32 of row r = key kv*tile + j is a k-hop neighbour of query qt*tile + r).
+    """
+    coo = khop.tocoo()
+    n = khop.shape[0]
+    nq = -(-n // tile)
+    qt, kt = coo.row // tile, coo.col // tile
+    key = qt.astype(np.int64) * nq + kt
+    uniq, inv = np.unique(key, return_inverse=True)
+    tile_q, tile_kv = (uniq // nq).astype(np.int32), (uniq % nq).astype(np.int32)
+    tile_ptr = np.zeros(nq + 1, np.int32)
+    np.cumsum(np.bincount(tile_q, minlength=nq), out=tile_ptr[1:])
+    bits = np.zeros((len(uniq), tile, tile), dtype=bool)
+    bits[inv, coo.row % tile, coo.col % tile] = True
+    mask = np.packbits(bits, axis=-1, bitorder="little").view(np.uint32).reshape(len(uniq), tile, tile // 32)
+    return tile_ptr, tile_kv, np.ascontiguousarray(mask)
+
+
+def patch_order(xyz: np.ndarray, leaf: int = 128) -> np.ndarray:
+    """Permutation that groups mesh nodes into spatially compact patches of `leaf` nodes.
+
+    Recursive bisection along the principal axis with left halves sized in multiples of `leaf`,
+    so every aligned block of `leaf` consecutive nodes is one patch.  Attention is permutation
+    equivariant and mesh latents never leave the denoiser, so the engine is free to relabel mesh
+    nodes; compact patches put the k-hop neighbourhoods of a query tile into fewer key tiles than
+    the band ordering the reference needs for its tri-block mask (gencast/denoiser.py:849-867).
+    new position i holds old node order[i].
+    """
+    xyz = np.asarray(xyz, np.float64)
+    out = []
+
+    def rec(ids):
+        n = len(ids)
+        if n <= leaf:
+            out.append(ids)
+            return
+        c = xyz[ids] - xyz[ids].mean(0)
+        _, _, vt = np.linalg.svd(c, full_matrices=False)
+        order = np.argsort(c @ vt[0], kind="stable")
+        nl = ((n // 2 + leaf - 1) // leaf) * leaf
+        if nl >= n:
+            nl = n - leaf
+        rec(ids[order[:nl]])
+        rec(ids[order[nl:]])
+
+    rec(np.arange(len(xyz)))
+    return np.concatenate(out)
+
+
 # --------------------------------------------------------------------------
 # CSR by receiver
 # --------------------------------------------------------------------------

@@ -182,6 +182,21 @@ def khop_attention(qkv: torch.Tensor, out: torch.Tensor, nbr_ptr: torch.Tensor, 
     return out
 
 
+@_recorded("khop_attention_tc", lambda qkv, out, tp, tk, tm, heads, head_dim, nnz=0: (4.0 * nnz * heads * head_dim, _nbytes(qkv, out, tm)))
+def khop_attention_tiles(qkv: torch.Tensor, out: torch.Tensor, tile_ptr: torch.Tensor, tile_kv: torch.Tensor,
+                         tile_mask: torch.Tensor, heads: int, head_dim: int, nnz: int = 0) -> torch.Tensor:
+    """Tensor-core k-hop attention over a block-sparse tile list (bf16).  `nnz` (pattern size) is only
+    used by the timing recorder to report algorithmic FLOPs."""
+    lib = _lib.load()
+    if qkv.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
+        raise TypeError("khop_attention_tiles: bf16 only")
+    _lib.check(lib.gc_khop_attention_tiles(_stream(), qkv.data_ptr(), _row_major(qkv, "qkv"), tile_ptr.data_ptr(),
+                                           tile_kv.data_ptr(), tile_mask.data_ptr(), out.data_ptr(),
+                                           _row_major(out, "out"), qkv.shape[0], heads, head_dim),
+               "gc_khop_attention_tiles")
+    return out
+
+
 def cond_tables(sigma: torch.Tensor, w0, b0, w1, b1, base_period: float, num_frequencies: int,
                 wc: torch.Tensor, bc: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()

@@ -148,6 +148,19 @@ GC_API int gc_khop_attention(void* stream, const void* qkv, int32_t dtype, int64
                       void* out, int64_t ldo, int64_t nodes, int32_t heads, int32_t head_dim);
 
 /*
+ * The same attention on tcgen05 tensor cores (bf16 only), driven by a block-sparse
+ * tile list instead of a CSR: for query tile t (128 consecutive nodes) the pairs
+ * tile_ptr[t] .. tile_ptr[t+1]-1 name the 128-key tiles tile_kv[] that contain at
+ * least one neighbour, and tile_mask holds one 128 x 128 bit mask per pair
+ * ([pair][row][4] uint32, bit (j % 32) of word (j / 32) = key tile_kv * 128 + j is a
+ * neighbour of query t * 128 + row).  Same reference operator as gc_khop_attention.
+ * head_dim 64 or 128.
+ */
+GC_API int gc_khop_attention_tiles(void* stream, const void* qkv, int64_t ld_qkv, const int32_t* tile_ptr,
+                                   const int32_t* tile_kv, const uint32_t* tile_mask, void* out, int64_t ldo,
+                                   int64_t nodes, int32_t heads, int32_t head_dim);
+
+/*
  * Noise-level conditioning for a batch of noise levels, all layers at once:
  *   cond      = Linear1(gelu_tanh(Linear0(fourier(log sigma))))     [16]
  *   table[i, l] = (1 + s_l | o_l),  [s_l | o_l] = cond . Wc_l + bc_l   [2*width]

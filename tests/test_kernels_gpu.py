@@ -155,6 +155,35 @@ def test_khop_attention(cuda_device, dtype, heads, head_dim):
     assert _rel(out.cpu(), ref) < (1e-5 if dtype == torch.float32 else 1e-2)
 
 
+@pytest.mark.parametrize("heads,head_dim", [(4, 64), (2, 128), (4, 128)])
+@pytest.mark.parametrize("n,density", [(300, 0.2), (1000, 0.05), (128, 1.0)])
+def test_khop_attention_tensor_core(cuda_device, heads, head_dim, n, density):
+    """Block-sparse tcgen05 attention against dense masked softmax attention in fp64."""
+    from scipy import sparse
+    from gencast_flax_nnx_b200 import ops
+    from gencast_flax_nnx_b200.graph import khop_tiles
+    rng = np.random.default_rng(head_dim + n)
+    hd = heads * head_dim
+    g = torch.Generator(device="cpu").manual_seed(4)
+    qkv = (torch.randn(n, 3 * hd, generator=g) * 1.5).to(torch.bfloat16)
+    mask = rng.random((n, n)) < density
+    if n == 1000:
+        mask[:, 300:700] = False         # empty key tiles for some query tiles (tile skipping)
+        mask[400:, :200] = False
+    mask[np.arange(n), np.arange(n)] = True
+    tp, tk, tm = khop_tiles(sparse.csr_matrix(mask))
+    d = cuda_device
+    out = torch.full((n, hd), float("nan"), dtype=torch.bfloat16, device=d)
+    ops.khop_attention_tiles(qkv.to(d), out, torch.from_numpy(tp).to(d), torch.from_numpy(tk).to(d),
+                             torch.from_numpy(tm.view(np.int32)).to(d), heads, head_dim)
+    torch.cuda.synchronize()
+    q, k, v = [t.double().reshape(n, heads, head_dim) for t in qkv.split(hd, dim=1)]
+    logits = torch.einsum("qhd,khd->hqk", q, k) / math.sqrt(head_dim)
+    logits = logits.masked_fill(~torch.from_numpy(mask)[None], float("-inf"))
+    ref = torch.einsum("hqk,khd->qhd", torch.softmax(logits, -1), v).reshape(n, hd)
+    assert _rel(out.cpu(), ref) < 1.5e-2
+
+
 def test_cond_tables_and_fold(cuda_device):
     from gencast_flax_nnx_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(9)
