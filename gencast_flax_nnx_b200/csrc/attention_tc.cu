@@ -184,29 +184,38 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
     const int q = warp & 3;
     const int r = q * 32 + lane;                       // row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    float m = -INFINITY;
     int g = 0;
+    // Each thread walks its row in four 32-column steps; the tcgen05.ld of the next step is in
+    // flight while the current one is reduced, and reductions use four independent accumulators
+    // (one warp per SM sub-partition: there is no other warp to hide a serial dependency chain).
+    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     for (int t = 0; t < T; ++t, ++g) {                 // pass 1: masked row maximum
       const int b = g & 1;
       const uint4 mk = __ldg(p.tile_mask + static_cast<int64_t>(t_beg + t) * TQ + r);
       const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
       mbar_wait(s_full(b), (g >> 1) & 1);
       tc_fence_after();
+      const uint32_t s_addr = tmem_s0 + b * 128 + lane_addr;
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(s_addr, v);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_s0 + b * 128 + lane_addr + c * 32, v);
+        float f[32];
         tc_wait_ld();
 #pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        if (c < 3) tmem_ld_32x32b_x32(s_addr + (c + 1) * 32, v);
+#pragma unroll
         for (int i = 0; i < 32; ++i)
-          if ((mw[c] >> i) & 1u) m = fmaxf(m, __uint_as_float(v[i]));
+          mx[i & 3] = fmaxf(mx[i & 3], ((mw[c] >> i) & 1u) ? f[i] : -INFINITY);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free(b));
     }
+    const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
     const float m_scaled = (m == -INFINITY) ? 0.0f : m * p.scale_log2e;
-    float l = 0.0f;
+    float ls[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     for (int t = 0; t < T; ++t, ++g) {                 // pass 2: P = exp2(S * c - max * c), row sums
       const int b = g & 1;
       const int pb = t % C::NPBUF;
@@ -214,22 +223,27 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
       const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
       mbar_wait(s_full(b), (g >> 1) & 1);
       tc_fence_after();
+      const uint32_t s_addr = tmem_s0 + b * 128 + lane_addr;
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(s_addr, v);
       if (t >= C::NPBUF) mbar_wait(p_empty(pb), ((t / C::NPBUF) - 1) & 1);
       const uint32_t p_row = p_smem + pb * C::P_BYTES + r * 128;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_s0 + b * 128 + lane_addr + c * 32, v);
+        float f[32];
         tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        if (c < 3) tmem_ld_32x32b_x32(s_addr + (c + 1) * 32, v);
         uint32_t packed[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = ((mw[c] >> i) & 1u) ? exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2e, -m_scaled)) : 0.0f;
-          const float p1 = ((mw[c] >> (i + 1)) & 1u) ? exp2f(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, -m_scaled)) : 0.0f;
+          const float p0 = ((mw[c] >> i) & 1u) ? exp2f(fmaf(f[i], p.scale_log2e, -m_scaled)) : 0.0f;
+          const float p1 = ((mw[c] >> (i + 1)) & 1u) ? exp2f(fmaf(f[i + 1], p.scale_log2e, -m_scaled)) : 0.0f;
           const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
           // the row sum uses the same rounded values the tensor core will multiply
           const float2 hr = __bfloat1622float2(h);
-          l += hr.x + hr.y;
+          ls[(i >> 1) & 3] += hr.x + hr.y;
           packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
         }
         // keys 32c .. 32c+31 -> 64-key chunk (c >> 1), 16-byte units (c & 1) * 4 + u, swizzled by row
@@ -250,6 +264,7 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
         mbar_arrive(p_full(pb));
       }
     }
+    const float l = (ls[0] + ls[1]) + (ls[2] + ls[3]);
     // epilogue: O / l -> bf16 -> global
     mbar_wait(o_full, 0);
     tc_fence_after();

@@ -44,9 +44,27 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   return 0.5f * x * (1.0f + tanhf(u));
 }
 
+// One MUFU op; |error| ~ 2^-11, far below bf16 resolution: used by the bf16 paths only.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float swish_fast(float x) {
+  // x * sigmoid(x), sigmoid(x) = 0.5 + 0.5 tanh(x / 2)
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(h), h);
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(u), h);
+}
+
+template <bool FAST>
 __device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == GC_ACT_SWISH) return swish_f(x);
-  if (act == GC_ACT_GELU_TANH) return gelu_tanh_f(x);
+  if (act == GC_ACT_SWISH) return FAST ? swish_fast(x) : swish_f(x);
+  if (act == GC_ACT_GELU_TANH) return FAST ? gelu_tanh_fast(x) : gelu_tanh_f(x);
   return x;
 }
 
@@ -145,18 +163,22 @@ struct EpilogueParams {
 };
 
 // v[NV]: accumulators of row `row`, columns [col0, col0+NV).  alpha is preloaded.
-template <int NV>
+// bias_ptr points at the NV bias values of these columns (global or shared memory) or is null.
+// FAST selects the MUFU-based activations (bf16 paths).
+template <int NV, bool FAST>
 __device__ __forceinline__ void epilogue_row_segment(const EpilogueParams& p, float alpha, int64_t row, int col0,
-                                                     float (&v)[NV]) {
+                                                     float (&v)[NV], const float* bias_ptr) {
   float t[NV];
   if (p.alpha_dev != nullptr) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] *= alpha;
   }
-  if (p.bias != nullptr) {
-    load_as_float<NV>(p.bias, GC_F32, col0, t);
+  if (bias_ptr != nullptr) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] += t[i];
+    for (int i = 0; i < NV / 4; ++i) {
+      const float4 b = reinterpret_cast<const float4*>(bias_ptr)[i];
+      v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    }
   }
   if (p.addend != nullptr) {
     load_as_float<NV>(p.addend, p.addend_dtype, row * p.ld_addend + col0, t);
@@ -175,9 +197,12 @@ __device__ __forceinline__ void epilogue_row_segment(const EpilogueParams& p, fl
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] += t[i];
   }
-  if (p.act != GC_ACT_NONE) {
+  if (p.act == GC_ACT_SWISH) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = apply_act(v[i], p.act);
+    for (int i = 0; i < NV; ++i) v[i] = apply_act<FAST>(v[i], GC_ACT_SWISH);
+  } else if (p.act == GC_ACT_GELU_TANH) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = apply_act<FAST>(v[i], GC_ACT_GELU_TANH);
   }
   if (p.residual != nullptr) {
     load_as_float<NV>(p.residual, p.res_dtype, row * p.ld_res + col0, t);

@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(256, 2) gemm_f32_ffma_kernel(const FfmaArgs g,
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float v[4] = {acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]};
-      epilogue_row_segment<4>(ep, alpha, row, col0 + h * 64 + tx * 4, v);
+      epilogue_row_segment<4, false>(ep, alpha, row, col0 + h * 64 + tx * 4, v,
+                                     ep.bias != nullptr ? ep.bias + col0 + h * 64 + tx * 4 : nullptr);
     }
   }
 }

@@ -23,16 +23,23 @@ namespace gc {
 namespace {
 
 constexpr int BM = 128;
-constexpr int BN = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 3;
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int B_STAGE_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/;
-constexpr uint32_t TMEM_COLS = 128;
+
+// BN = 128 is the throughput shape; BN = 64 doubles the CTA count for the small
+// mesh-side problems (a few thousand rows) that would otherwise leave most SMs idle.
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = BN == 128 ? 3 : 4;
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 128;
+  static constexpr int SMEM_BYTES = BIAS_OFFSET + BN * 4 + 1024 /*alignment slack*/;
+  static constexpr uint32_t TMEM_COLS = BN;
+};
 
 struct GemmMaps {
   CUtensorMap a[GC_MAX_SEGMENTS];
@@ -45,14 +52,19 @@ struct GemmShape {
   int n_tiles;
 };
 
+template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shape, const EpilogueParams ep) {
   using namespace sm100;
+  using C = GemmCfg<BN>;
+  constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + STAGES * A_STAGE_BYTES;
-  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bars = smem_base + C::BAR_OFFSET;
+  float* bias_s = reinterpret_cast<float*>(smem_gen + C::BIAS_OFFSET);
   // barrier block: full[STAGES] | empty[STAGES] | tmem_full | tmem_ptr
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
@@ -77,8 +89,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmShape 
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
     tmem_relinquish();
+  }
+  if (warp >= 2) {
+    // bias tile -> shared memory while the main loop runs (read back as broadcasts)
+    const int t = threadIdx.x - 64;
+    if (t < BN) bias_s[t] = ep.bias != nullptr ? __ldg(ep.bias + n_blk * BN + t) : 0.0f;
   }
   tc_fence_before();
   __syncthreads();
@@ -93,9 +110,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmShape 
       for (int s = 0; s < shape.num_segments; ++s) {
         for (int kb = 0; kb < shape.kblocks[s]; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
           tma_load_2d(smem_a + stage * A_STAGE_BYTES, &maps.a[s], full_bar(stage), kb * BK, m_blk * BM);
-          tma_load_2d(smem_b + stage * B_STAGE_BYTES, &maps.w[s], full_bar(stage), kb * BK, n_blk * BN);
+          tma_load_2d(smem_b + stage * C::B_STAGE_BYTES, &maps.w[s], full_bar(stage), kb * BK, n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -111,7 +128,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmShape 
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint64_t da = desc_kmajor_sw128(smem_a + stage * A_STAGE_BYTES);
-          const uint64_t db = desc_kmajor_sw128(smem_b + stage * B_STAGE_BYTES);
+          const uint64_t db = desc_kmajor_sw128(smem_b + stage * C::B_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 16 bf16 = 32 bytes inside the 128-byte swizzle span: +2 in the (>>4) address field
@@ -125,29 +142,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmShape 
       umma_commit(tmem_full_bar);
     }
   } else {
-    // Epilogue: TMEM lane quarter is fixed by warp id modulo 4.
+    // Epilogue: TMEM lane quarter is fixed by warp id modulo 4.  32 columns per step, the next
+    // step's tcgen05.ld is in flight while the current one is processed.
     const int q = warp & 3;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
     const int64_t row = static_cast<int64_t>(m_blk) * BM + q * 32 + lane;
     const float alpha = ep.alpha_dev != nullptr ? __ldg(ep.alpha_dev) : 1.0f;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float* bias_ptr = ep.bias != nullptr ? bias_s : nullptr;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(taddr, r);
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(taddr + c, r);
+    for (int c = 0; c < BN; c += 32) {
+      float v[32];
       tc_wait_ld();
-      if (row < ep.m) {
-        float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-        epilogue_row_segment<16>(ep, alpha, row, n_blk * BN + c, v);
-      }
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+      if (c + 32 < BN) tmem_ld_32x32b_x32(taddr + c + 32, r);
+      if (row < ep.m) epilogue_row_segment<32, true>(ep, alpha, row, n_blk * BN + c, v, bias_ptr ? bias_ptr + c : nullptr);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -189,7 +207,9 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return GC_OK;
 }
 
-int launch_gemm_tcgen05(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
+template <int BN>
+int launch_cfg(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
+  using C = GemmCfg<BN>;
   GemmMaps maps;
   GemmShape shape;
   shape.num_segments = a.num_segments;
@@ -206,21 +226,24 @@ int launch_gemm_tcgen05(cudaStream_t stream, const gc_gemm_args& a, const Epilog
     maps.a[s] = maps.a[0];
     maps.w[s] = maps.w[0];
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel)");
-    attr_set = true;
-  }
+  cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel)");
   const int64_t m_tiles = (a.m + BM - 1) / BM;
   const int64_t grid = m_tiles * shape.n_tiles;
   if (grid > 0x7fffffffLL) {
     set_error("gc_gemm: too many tiles (%lld)", (long long)grid);
     return GC_ERR_INVALID_ARGUMENT;
   }
-  gemm_bf16_tcgen05_kernel<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, stream>>>(maps, shape, ep);
+  gemm_bf16_tcgen05_kernel<BN><<<(unsigned)grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(maps, shape, ep);
   GC_CHECK_LAUNCH("gemm_bf16_tcgen05_kernel");
   return GC_OK;
+}
+
+int launch_gemm_tcgen05(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
+  // Fewer than ~2 CTAs per SM with 128-wide tiles: halve the tile width to spread the work.
+  const int64_t tiles128 = ((a.m + BM - 1) / BM) * (a.n / 128);
+  if (tiles128 < 2 * 148) return launch_cfg<64>(stream, a, ep);
+  return launch_cfg<128>(stream, a, ep);
 }
 
 }  // namespace gc
