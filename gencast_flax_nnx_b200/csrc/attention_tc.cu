@@ -14,8 +14,9 @@
 // the reference's where(mask, logits, -1e30) + softmax evaluates to
 // (gencast/sparse_transformer.py:100-125, :340-347).
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
-// warps 2-5 softmax / epilogue (thread <-> query row, TMEM lane quarter = warp % 4).
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
+// warps 2-9 softmax / epilogue: two warps per TMEM lane quarter (warp % 4), each owning
+// one 64-key half of every S tile, so each SM sub-partition has two warps to interleave.
 // TMEM: S double buffer (2 x 128 columns) + O (d columns).
 #include "common.cuh"
 #include "sm100.cuh"
@@ -26,7 +27,7 @@ namespace {
 
 constexpr int TQ = 128;          // queries per tile
 constexpr int TK = 128;          // keys per tile
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;   // TMA warp, MMA warp, 8 softmax warps
 
 template <int D>
 struct AttCfg {
@@ -36,7 +37,7 @@ struct AttCfg {
   static constexpr int P_BYTES = TQ * TK * 2;            // 32 KB, two 64-key chunks
   static constexpr int NPBUF = D == 64 ? 2 : 1;
   static constexpr int NSLOT = D == 64 ? 6 : 4;
-  static constexpr int SMEM = Q_BYTES + NSLOT * SLOT_BYTES + NPBUF * P_BYTES + 1024 + 256;
+  static constexpr int SMEM = Q_BYTES + NSLOT * SLOT_BYTES + NPBUF * P_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*exchange*/;
 };
 
 struct AttParams {
@@ -86,8 +87,8 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
     mbar_init(q_full, 1);
     for (int s = 0; s < C::NSLOT; ++s) { mbar_init(slot_full(s), 1); mbar_init(slot_empty(s), 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(s_full(b), 1); mbar_init(s_free(b), 4);
-      mbar_init(p_full(b), 4); mbar_init(p_empty(b), 1);
+      mbar_init(s_full(b), 1); mbar_init(s_free(b), 8);
+      mbar_init(p_full(b), 8); mbar_init(p_empty(b), 1);
     }
     mbar_init(o_full, 1);
     fence_mbar_init();
@@ -182,75 +183,81 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
   } else {
     // ---------------- softmax + epilogue warps
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;                  // which 64-key half of each S tile this warp owns
     const int r = q * 32 + lane;                       // row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    float* xch = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + 8 * 32);   // [2][128] exchange
     int g = 0;
-    // Each thread walks its row in four 32-column steps; the tcgen05.ld of the next step is in
-    // flight while the current one is reduced, and reductions use four independent accumulators
-    // (one warp per SM sub-partition: there is no other warp to hide a serial dependency chain).
+    // Each thread walks its half row in two 32-column steps; the tcgen05.ld of the next step is in
+    // flight while the current one is reduced, and reductions use independent accumulators.
     float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     for (int t = 0; t < T; ++t, ++g) {                 // pass 1: masked row maximum
       const int b = g & 1;
-      const uint4 mk = __ldg(p.tile_mask + static_cast<int64_t>(t_beg + t) * TQ + r);
-      const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+      const uint2 mk = __ldg(reinterpret_cast<const uint2*>(p.tile_mask + static_cast<int64_t>(t_beg + t) * TQ + r) + half);
+      const uint32_t mw[2] = {mk.x, mk.y};
       mbar_wait(s_full(b), (g >> 1) & 1);
       tc_fence_after();
-      const uint32_t s_addr = tmem_s0 + b * 128 + lane_addr;
+      const uint32_t s_addr = tmem_s0 + b * 128 + half * 64 + lane_addr;
       uint32_t v[32];
       tmem_ld_32x32b_x32(s_addr, v);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float f[32];
         tc_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        if (c < 3) tmem_ld_32x32b_x32(s_addr + (c + 1) * 32, v);
+        if (c < 1) tmem_ld_32x32b_x32(s_addr + 32, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          mx[i & 3] = fmaxf(mx[i & 3], ((mw[c] >> i) & 1u) ? f[i] : -INFINITY);
+          mx[i & 3] = fmaxf(mx[i & 3], (mw[c] & (1u << i)) ? f[i] : -INFINITY);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free(b));
     }
-    const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+    float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+    // combine the two halves of each row (named barrier 1 over the 256 softmax threads)
+    xch[half * 128 + r] = m;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    m = fmaxf(m, xch[(half ^ 1) * 128 + r]);
     const float m_scaled = (m == -INFINITY) ? 0.0f : m * p.scale_log2e;
     float ls[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     for (int t = 0; t < T; ++t, ++g) {                 // pass 2: P = exp2(S * c - max * c), row sums
       const int b = g & 1;
       const int pb = t % C::NPBUF;
-      const uint4 mk = __ldg(p.tile_mask + static_cast<int64_t>(t_beg + t) * TQ + r);
-      const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+      const uint2 mk = __ldg(reinterpret_cast<const uint2*>(p.tile_mask + static_cast<int64_t>(t_beg + t) * TQ + r) + half);
+      const uint32_t mw[2] = {mk.x, mk.y};
       mbar_wait(s_full(b), (g >> 1) & 1);
       tc_fence_after();
-      const uint32_t s_addr = tmem_s0 + b * 128 + lane_addr;
+      const uint32_t s_addr = tmem_s0 + b * 128 + half * 64 + lane_addr;
       uint32_t v[32];
       tmem_ld_32x32b_x32(s_addr, v);
       if (t >= C::NPBUF) mbar_wait(p_empty(pb), ((t / C::NPBUF) - 1) & 1);
-      const uint32_t p_row = p_smem + pb * C::P_BYTES + r * 128;
+      // this warp's keys are the 64-key operand chunk `half` of P
+      const uint32_t chunk_base = p_smem + pb * C::P_BYTES + half * (TQ * 128) + r * 128;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float f[32];
         tc_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        if (c < 3) tmem_ld_32x32b_x32(s_addr + (c + 1) * 32, v);
+        if (c < 1) tmem_ld_32x32b_x32(s_addr + 32, v);
         uint32_t packed[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = ((mw[c] >> i) & 1u) ? exp2f(fmaf(f[i], p.scale_log2e, -m_scaled)) : 0.0f;
-          const float p1 = ((mw[c] >> (i + 1)) & 1u) ? exp2f(fmaf(f[i + 1], p.scale_log2e, -m_scaled)) : 0.0f;
+          float e0, e1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(f[i], p.scale_log2e, -m_scaled)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(f[i + 1], p.scale_log2e, -m_scaled)));
+          const float p0 = (mw[c] & (1u << i)) ? e0 : 0.0f;
+          const float p1 = (mw[c] & (1u << (i + 1))) ? e1 : 0.0f;
+          ls[(i >> 1) & 3] += p0 + p1;
           const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-          // the row sum uses the same rounded values the tensor core will multiply
-          const float2 hr = __bfloat1622float2(h);
-          ls[(i >> 1) & 3] += hr.x + hr.y;
           packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
         }
-        // keys 32c .. 32c+31 -> 64-key chunk (c >> 1), 16-byte units (c & 1) * 4 + u, swizzled by row
-        const uint32_t chunk_base = p_row + (c >> 1) * (TQ * 128);
+        // keys 32c .. 32c+31 of the chunk -> 16-byte units c * 4 + u, swizzled by row
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const uint32_t unit = static_cast<uint32_t>((c & 1) * 4 + u) ^ static_cast<uint32_t>(r & 7);
+          const uint32_t unit = static_cast<uint32_t>(c * 4 + u) ^ static_cast<uint32_t>(r & 7);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(chunk_base + unit * 16), "r"(packed[4 * u]),
                        "r"(packed[4 * u + 1]), "r"(packed[4 * u + 2]), "r"(packed[4 * u + 3])
                        : "memory");
@@ -264,14 +271,18 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
         mbar_arrive(p_full(pb));
       }
     }
-    const float l = (ls[0] + ls[1]) + (ls[2] + ls[3]);
-    // epilogue: O / l -> bf16 -> global
+    float l = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+    asm volatile("bar.sync 1, 256;" ::: "memory");     // everyone has read the pass-1 exchange
+    xch[half * 128 + r] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += xch[(half ^ 1) * 128 + r];
+    // epilogue: O / l -> bf16 -> global; each warp stores its half of the head's channels
     mbar_wait(o_full, 0);
     tc_fence_after();
     const float inv_l = l > 0.0f ? 1.0f / l : 0.0f;
     const int64_t row = static_cast<int64_t>(qt) * TQ + r;
 #pragma unroll
-    for (int c = 0; c < D; c += 32) {
+    for (int c = half * (D / 2); c < (half + 1) * (D / 2); c += 32) {
       uint32_t v[32];
       tmem_ld_32x32b_x32(tmem_o + lane_addr + c, v);
       tc_wait_ld();

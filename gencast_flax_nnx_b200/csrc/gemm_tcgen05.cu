@@ -30,13 +30,13 @@ constexpr int NUM_THREADS = 192;
 
 // BN = 128 is the throughput shape; BN = 64 doubles the CTA count for the small
 // mesh-side problems (a few thousand rows) that would otherwise leave most SMs idle.
-template <int BN>
+template <int BN, int STAGES_>
 struct GemmCfg {
-  static constexpr int STAGES = BN == 128 ? 3 : 4;
+  static constexpr int STAGES = STAGES_;
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int BIAS_OFFSET = BAR_OFFSET + 128;
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;   // barrier block: up to 2 * 8 + 2 words of 8 bytes
   static constexpr int SMEM_BYTES = BIAS_OFFSET + BN * 4 + 1024 /*alignment slack*/;
   static constexpr uint32_t TMEM_COLS = BN;
 };
@@ -52,11 +52,11 @@ struct GemmShape {
   int n_tiles;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+template <int BN, int NSTAGES>
+__global__ void __launch_bounds__(NUM_THREADS, NSTAGES > 4 ? 1 : 2)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shape, const EpilogueParams ep) {
   using namespace sm100;
-  using C = GemmCfg<BN>;
+  using C = GemmCfg<BN, NSTAGES>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -207,9 +207,9 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return GC_OK;
 }
 
-template <int BN>
+template <int BN, int NSTAGES>
 int launch_cfg(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
-  using C = GemmCfg<BN>;
+  using C = GemmCfg<BN, NSTAGES>;
   GemmMaps maps;
   GemmShape shape;
   shape.num_segments = a.num_segments;
@@ -226,7 +226,7 @@ int launch_cfg(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams&
     maps.a[s] = maps.a[0];
     maps.w[s] = maps.w[0];
   }
-  cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, NSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel)");
   const int64_t m_tiles = (a.m + BM - 1) / BM;
   const int64_t grid = m_tiles * shape.n_tiles;
@@ -234,7 +234,7 @@ int launch_cfg(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams&
     set_error("gc_gemm: too many tiles (%lld)", (long long)grid);
     return GC_ERR_INVALID_ARGUMENT;
   }
-  gemm_bf16_tcgen05_kernel<BN><<<(unsigned)grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(maps, shape, ep);
+  gemm_bf16_tcgen05_kernel<BN, NSTAGES><<<(unsigned)grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(maps, shape, ep);
   GC_CHECK_LAUNCH("gemm_bf16_tcgen05_kernel");
   return GC_OK;
 }
@@ -242,8 +242,11 @@ int launch_cfg(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams&
 int launch_gemm_tcgen05(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
   // Fewer than ~2 CTAs per SM with 128-wide tiles: halve the tile width to spread the work.
   const int64_t tiles128 = ((a.m + BM - 1) / BM) * (a.n / 128);
-  if (tiles128 < 2 * 148) return launch_cfg<64>(stream, a, ep);
-  return launch_cfg<128>(stream, a, ep);
+  if (tiles128 >= 2 * 148) return launch_cfg<128, 3>(stream, a, ep);
+  // One CTA per SM at most: a deep ring (8 x 24 KB in flight) keeps the per-SM L2 link busy
+  // through the long serial K loops of the skinny mesh-side GEMMs.
+  if (2 * tiles128 <= 148) return launch_cfg<64, 8>(stream, a, ep);
+  return launch_cfg<64, 4>(stream, a, ep);
 }
 
 }  // namespace gc
