@@ -217,14 +217,16 @@ def run_gpu(args):
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
     noises = [torch.randn(G, C, generator=gen, device=dev) for _ in range(max(args.steps, 1))]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    ens_sum = torch.zeros(G, C, device=dev); ens_sq = torch.zeros(G, C, device=dev)
-    red = torch.zeros(2, G, C, device=dev)
+    from gencast_flax_nnx_b200.parallel import EnsembleStatistics
+    stats = EnsembleStatistics((G, C), dev)
 
     def one_step(noise):
         out = se.sample(noise, use_graph=True)
         if world > 1:
-            red[0].copy_(out); torch.mul(out, out, out=red[1])
-            dist.all_reduce(red)           # ensemble sum / sum of squares over members (mean, spread)
+            # ensemble mean / spread over the members of all ranks: local accumulate kernel + one NCCL all-reduce
+            stats.reset()
+            stats.add(out)
+            stats.finalize(total_members=world)
         return out
 
     for i in range(args.warmup):

@@ -58,6 +58,7 @@ SIGNATURES = {
     "gc_abi_version": (c_int32, []),
     "gc_device_supports_tcgen05": (c_int32, []),
     "gc_gemm": (c_int32, [c_void_p, POINTER(GemmArgs)]),
+    "gc_sizeof_gemm_args": (c_int32, []),
     "gc_ln_cond": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_int32, c_void_p, c_int32, c_int64,
                              c_void_p, c_int32, c_int64, c_int64, c_int32]),
     "gc_ln_cond_segment_sum": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_int32, c_void_p, c_void_p,
@@ -98,6 +99,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)     # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
+    if lib.gc_sizeof_gemm_args() != ctypes.sizeof(GemmArgs):
+        raise GencastKernelError("struct gc_gemm_args layout mismatch between the library and the ctypes binding")
     _lib = lib
     return lib
 

@@ -28,6 +28,8 @@ const char* gc_last_error(void) { return gc::g_err; }
 
 int gc_abi_version(void) { return 1; }
 
+int gc_sizeof_gemm_args(void) { return static_cast<int>(sizeof(gc_gemm_args)); }
+
 int gc_device_supports_tcgen05(void) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;

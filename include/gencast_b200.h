@@ -101,6 +101,8 @@ typedef struct gc_gemm_args {
 } gc_gemm_args;
 
 GC_API int gc_gemm(void* stream, const gc_gemm_args* args);
+/* sizeof(gc_gemm_args) as compiled into the library, for binding-side layout checks. */
+GC_API int gc_sizeof_gemm_args(void);
 
 /*
  * Row LayerNorm (no learned affine, eps 1e-6, var = E[x^2]-E[x]^2 >= 0) followed
