@@ -1,5 +1,6 @@
 // C-ABI plumbing: error reporting, introspection and the gc_gemm front end.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -13,6 +14,14 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const bool on = []() {
+    const char* v = getenv("GENCAST_PDL");
+    return !(v != nullptr && v[0] == '0');
+  }();
+  return on;
 }
 
 int cuda_fail(cudaError_t e, const char* what) {

@@ -22,6 +22,8 @@ __global__ void __launch_bounds__(128) khop_attention_csr_kernel(const void* __r
                                                                  int heads) {
   constexpr int DPL = D / 32;
   __shared__ __align__(16) float q_s[4][D];
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t hd = static_cast<int64_t>(heads) * D;
@@ -126,9 +128,9 @@ int launch_khop_attention_csr(cudaStream_t st, const void* qkv, int dtype, int64
   const int64_t need = (nodes * heads + 3) / 4;
   const int64_t cap = static_cast<int64_t>(sms) * 16;
   const unsigned grid = static_cast<unsigned>(need < cap ? need : cap);
-  if (head_dim == 32) khop_attention_csr_kernel<32><<<grid, 128, 0, st>>>(qkv, dtype, ld_qkv, nbr_ptr, nbr_idx, out, ldo, nodes, heads);
-  else if (head_dim == 64) khop_attention_csr_kernel<64><<<grid, 128, 0, st>>>(qkv, dtype, ld_qkv, nbr_ptr, nbr_idx, out, ldo, nodes, heads);
-  else if (head_dim == 128) khop_attention_csr_kernel<128><<<grid, 128, 0, st>>>(qkv, dtype, ld_qkv, nbr_ptr, nbr_idx, out, ldo, nodes, heads);
+  if (head_dim == 32) GC_CHECK_CUDA(launch_kernel(khop_attention_csr_kernel<32>, dim3(grid), dim3(128), 0, st, qkv, dtype, ld_qkv, nbr_ptr, nbr_idx, out, ldo, nodes, heads), "khop_attention_csr_kernel");
+  else if (head_dim == 64) GC_CHECK_CUDA(launch_kernel(khop_attention_csr_kernel<64>, dim3(grid), dim3(128), 0, st, qkv, dtype, ld_qkv, nbr_ptr, nbr_idx, out, ldo, nodes, heads), "khop_attention_csr_kernel");
+  else if (head_dim == 128) GC_CHECK_CUDA(launch_kernel(khop_attention_csr_kernel<128>, dim3(grid), dim3(128), 0, st, qkv, dtype, ld_qkv, nbr_ptr, nbr_idx, out, ldo, nodes, heads), "khop_attention_csr_kernel");
   else {
     set_error("gc_khop_attention: head_dim=%d (supported: 32, 64, 128)", head_dim);
     return GC_ERR_UNSUPPORTED;

@@ -79,8 +79,6 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
   const int lane = threadIdx.x & 31;
   const int head = blockIdx.x % p.heads;
   const int qt = blockIdx.x / p.heads;
-  const int t_beg = __ldg(p.tile_ptr + qt);
-  const int T = __ldg(p.tile_ptr + qt + 1) - t_beg;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&qkv_map);
@@ -102,6 +100,10 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  pdl_launch_dependents();
+  pdl_wait();                                    // everything below may read what a predecessor wrote
+  const int t_beg = __ldg(p.tile_ptr + qt);
+  const int T = __ldg(p.tile_ptr + qt + 1) - t_beg;
   const uint32_t tmem_s0 = tmem_base;            // S buffers at columns 0 and 128
   const uint32_t tmem_o = tmem_base + 256;       // O at columns 256 .. 256 + D
 
@@ -112,6 +114,7 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer: loads in exactly the order the MMA warp consumes them
+      pdl_wait();
       mbar_arrive_expect_tx(q_full, C::Q_BYTES);
       for (int c = 0; c < C::CHUNKS; ++c) tma_load_2d(q_smem + c * (TQ * 128), &qkv_map, q_full, q_col + 64 * c, qt * TQ);
       int slot = 0;
@@ -187,6 +190,7 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
     const int r = q * 32 + lane;                       // row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     float* xch = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + 8 * 32);   // [2][128] exchange
+    pdl_wait();
     int g = 0;
     // Each thread walks its half row in two 32-column steps; the tcgen05.ld of the next step is in
     // flight while the current one is reduced, and reductions use independent accumulators.
@@ -310,8 +314,8 @@ int launch_tc(cudaStream_t st, const CUtensorMap& map, const AttParams& p, int n
   using C = AttCfg<D>;
   cudaError_t e = cudaFuncSetAttribute(khop_attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(khop_attention_tc_kernel)");
-  khop_attention_tc_kernel<D><<<num_q_tiles * p.heads, ATT_THREADS, C::SMEM, st>>>(map, p);
-  GC_CHECK_LAUNCH("khop_attention_tc_kernel");
+  GC_CHECK_CUDA(launch_kernel(khop_attention_tc_kernel<D>, dim3(num_q_tiles * p.heads), dim3(ATT_THREADS), (size_t)C::SMEM, st,
+                              map, p), "khop_attention_tc_kernel");
   return GC_OK;
 }
 

@@ -30,12 +30,49 @@ int cuda_fail(cudaError_t e, const char* what);
     if (_e != cudaSuccess) return ::gc::cuda_fail(_e, what);       \
   } while (0)
 
+// ---------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel is launched with the
+// programmatic-stream-serialization attribute, signals its dependents at entry and
+// waits for its predecessor (griddepcontrol.wait) right before its first access to
+// memory a previous kernel may have written or may still be reading.  The next
+// kernel's launch latency, block scheduling and prologue (barrier init, TMEM
+// allocation, descriptor prefetch, weight-side loads) overlap the current
+// kernel's tail.  GENCAST_PDL=0 disables the attribute (the device-side
+// instructions are then no-ops).
+// ---------------------------------------------------------------------------
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+#define GC_CHECK_CUDA(expr, what)                                  \
+  do {                                                             \
+    cudaError_t _e = (expr);                                       \
+    if (_e != cudaSuccess) return ::gc::cuda_fail(_e, what);       \
+  } while (0)
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t dtype_size(int dt) { return dt == GC_BF16 ? 2 : 4; }
 
 // ---------------------------------------------------------------------------
 // Device helpers
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float swish_f(float x) { return x / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {

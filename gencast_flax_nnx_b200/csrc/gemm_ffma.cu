@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(256, 2) gemm_f32_ffma_kernel(const FfmaArgs g,
   __shared__ __align__(16) float As[2][FBK][FBM + FPAD];
   __shared__ __align__(16) float Bs[2][FBK][FBN + FPAD];
 
+  pdl_launch_dependents();
+  pdl_wait();
   const int tid = threadIdx.x;
   const int n_blk = blockIdx.x % g.n_tiles;
   const int m_blk = blockIdx.x / g.n_tiles;
@@ -134,8 +136,8 @@ int launch_gemm_ffma(cudaStream_t stream, const gc_gemm_args& a, const EpilogueP
     set_error("gc_gemm: too many tiles (%lld)", (long long)grid);
     return GC_ERR_INVALID_ARGUMENT;
   }
-  gemm_f32_ffma_kernel<<<(unsigned)grid, 256, 0, stream>>>(g, ep);
-  GC_CHECK_LAUNCH("gemm_f32_ffma_kernel");
+  GC_CHECK_CUDA(launch_kernel(gemm_f32_ffma_kernel, dim3((unsigned)grid), dim3(256), 0, stream, g, ep),
+                "gemm_f32_ffma_kernel");
   return GC_OK;
 }
 

@@ -92,19 +92,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmShape 
     tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
     tmem_relinquish();
   }
-  if (warp >= 2) {
-    // bias tile -> shared memory while the main loop runs (read back as broadcasts)
-    const int t = threadIdx.x - 64;
-    if (t < BN) bias_s[t] = ep.bias != nullptr ? __ldg(ep.bias + n_blk * BN + t) : 0.0f;
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
   if (warp == 0) {
     if (lane == 0) {
+      pdl_wait();            // first touch of operands a predecessor may have produced
       int stage = 0;
       uint32_t phase = 0;
       for (int s = 0; s < shape.num_segments; ++s) {
@@ -146,9 +143,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmShape 
     // step's tcgen05.ld is in flight while the current one is processed.
     const int q = warp & 3;
     const int64_t row = static_cast<int64_t>(m_blk) * BM + q * 32 + lane;
-    const float alpha = ep.alpha_dev != nullptr ? __ldg(ep.alpha_dev) : 1.0f;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float* bias_ptr = ep.bias != nullptr ? bias_s : nullptr;
+    pdl_wait();
+    {
+      // bias tile -> shared memory while the main loop runs (read back as broadcasts)
+      const int t = threadIdx.x - 64;
+      if (t < BN) bias_s[t] = ep.bias != nullptr ? __ldg(ep.bias + n_blk * BN + t) : 0.0f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    const float alpha = ep.alpha_dev != nullptr ? __ldg(ep.alpha_dev) : 1.0f;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     uint32_t r[32];
@@ -166,6 +170,153 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmShape 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent variant for problems with at least ~2 tiles per SM: one CTA per SM walks tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ...  The accumulator is double buffered in TMEM (2 x 128
+// columns), so the tensor core starts tile i+1 while eight epilogue warps (two per TMEM lane
+// quarter, half the columns each) drain tile i; the TMA producer runs ahead through a 6-stage
+// 192 KB operand ring across tile boundaries.
+// ---------------------------------------------------------------------------------------------
+constexpr int PBN = 128;
+constexpr int PSTAGES = 6;
+constexpr int P_B_STAGE_BYTES = PBN * BK * 2;
+constexpr int P_STAGE_BYTES = A_STAGE_BYTES + P_B_STAGE_BYTES;
+constexpr int P_BAR_OFFSET = PSTAGES * P_STAGE_BYTES;
+constexpr int P_SMEM_BYTES = P_BAR_OFFSET + 256 + 1024;
+constexpr int P_THREADS = 320;
+
+__global__ void __launch_bounds__(P_THREADS, 1)
+gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shape, const EpilogueParams ep,
+                                    const int num_tiles) {
+  using namespace sm100;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + PSTAGES * A_STAGE_BYTES;
+  const uint32_t bars = smem_base + P_BAR_OFFSET;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (PSTAGES + s); };
+  auto acc_full = [&](int b) { return bars + 8u * (2 * PSTAGES + b); };
+  auto acc_empty = [&](int b) { return bars + 8u * (2 * PSTAGES + 2 + b); };
+  const uint32_t tmem_ptr_smem = bars + 8u * (2 * PSTAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < shape.num_segments; ++s) {
+      prefetch_tensormap(&maps.a[s]);
+      prefetch_tensormap(&maps.w[s]);
+    }
+    for (int s = 0; s < PSTAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, 2 * PBN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_launch_dependents();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      pdl_wait();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % shape.n_tiles, m_blk = tile / shape.n_tiles;
+        for (int s = 0; s < shape.num_segments; ++s) {
+          for (int kb = 0; kb < shape.kblocks[s]; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_arrive_expect_tx(full_bar(stage), P_STAGE_BYTES);
+            tma_load_2d(smem_a + stage * A_STAGE_BYTES, &maps.a[s], full_bar(stage), kb * BK, m_blk * BM);
+            tma_load_2d(smem_b + stage * P_B_STAGE_BYTES, &maps.w[s], full_bar(stage), kb * BK, n_blk * PBN);
+            if (++stage == PSTAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16_f32(BM, PBN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const int b = lt & 1;
+        mbar_wait(acc_empty(b), ((lt >> 1) & 1) ^ 1u);      // epilogue has drained this accumulator buffer
+        tc_fence_after();
+        uint32_t accumulate = 0;
+        for (int s = 0; s < shape.num_segments; ++s) {
+          for (int kb = 0; kb < shape.kblocks[s]; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint64_t da = desc_kmajor_sw128(smem_a + stage * A_STAGE_BYTES);
+            const uint64_t db = desc_kmajor_sw128(smem_b + stage * P_B_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              umma_f16(tmem_base + b * PBN, da + 2u * k, db + 2u * k, idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(empty_bar(stage));
+            if (++stage == PSTAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+        umma_commit(acc_full(b));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    pdl_wait();
+    const float alpha = ep.alpha_dev != nullptr ? __ldg(ep.alpha_dev) : 1.0f;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int n_blk = tile % shape.n_tiles, m_blk = tile / shape.n_tiles;
+      const int b = lt & 1;
+      const int64_t row = static_cast<int64_t>(m_blk) * BM + q * 32 + lane;
+      const int col_base = n_blk * PBN + half * (PBN / 2);
+      const uint32_t taddr = tmem_base + b * PBN + half * (PBN / 2) + lane_addr;
+      mbar_wait(acc_full(b), (lt >> 1) & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr, r);
+#pragma unroll
+      for (int c = 0; c < PBN / 2; c += 32) {
+        float v[32];
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (c + 32 < PBN / 2) {
+          tmem_ld_32x32b_x32(taddr + c + 32, r);
+        } else {
+          // last read of this buffer is in registers: hand it back to the MMA warp before the math
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(b));
+        }
+        if (row < ep.m)
+          epilogue_row_segment<32, true>(ep, alpha, row, col_base + c, v, ep.bias != nullptr ? ep.bias + col_base + c : nullptr);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * PBN);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -234,15 +385,47 @@ int launch_cfg(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams&
     set_error("gc_gemm: too many tiles (%lld)", (long long)grid);
     return GC_ERR_INVALID_ARGUMENT;
   }
-  gemm_bf16_tcgen05_kernel<BN, NSTAGES><<<(unsigned)grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(maps, shape, ep);
-  GC_CHECK_LAUNCH("gemm_bf16_tcgen05_kernel");
+  GC_CHECK_CUDA(launch_kernel(gemm_bf16_tcgen05_kernel<BN, NSTAGES>, dim3((unsigned)grid), dim3(NUM_THREADS),
+                              (size_t)C::SMEM_BYTES, stream, maps, shape, ep), "gemm_bf16_tcgen05_kernel");
+  return GC_OK;
+}
+
+int launch_persistent(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
+  GemmMaps maps;
+  GemmShape shape;
+  shape.num_segments = a.num_segments;
+  shape.n_tiles = a.n / PBN;
+  for (int s = 0; s < GC_MAX_SEGMENTS; ++s) shape.kblocks[s] = 0;
+  for (int s = 0; s < a.num_segments; ++s) {
+    shape.kblocks[s] = a.k[s] / BK;
+    int rc = make_tmap_bf16_2d(&maps.a[s], a.a[s], (uint64_t)a.m, (uint64_t)a.k[s], (uint64_t)a.lda[s], BK, BM);
+    if (rc != GC_OK) return rc;
+    rc = make_tmap_bf16_2d(&maps.w[s], a.w[s], (uint64_t)a.n, (uint64_t)a.k[s], (uint64_t)a.ldw[s], BK, PBN);
+    if (rc != GC_OK) return rc;
+  }
+  for (int s = a.num_segments; s < GC_MAX_SEGMENTS; ++s) {
+    maps.a[s] = maps.a[0];
+    maps.w[s] = maps.w[0];
+  }
+  GC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     P_SMEM_BYTES), "cudaFuncSetAttribute(gemm_bf16_tcgen05_persistent_kernel)");
+  const int64_t num_tiles = ((a.m + BM - 1) / BM) * shape.n_tiles;
+  if (num_tiles > 0x7fffffffLL) {
+    set_error("gc_gemm: too many tiles (%lld)", (long long)num_tiles);
+    return GC_ERR_INVALID_ARGUMENT;
+  }
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)(num_tiles < sms ? num_tiles : sms);
+  GC_CHECK_CUDA(launch_kernel(gemm_bf16_tcgen05_persistent_kernel, dim3(grid), dim3(P_THREADS), (size_t)P_SMEM_BYTES, stream,
+                              maps, shape, ep, (int)num_tiles), "gemm_bf16_tcgen05_persistent_kernel");
   return GC_OK;
 }
 
 int launch_gemm_tcgen05(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
   // Fewer than ~2 CTAs per SM with 128-wide tiles: halve the tile width to spread the work.
   const int64_t tiles128 = ((a.m + BM - 1) / BM) * (a.n / 128);
-  if (tiles128 >= 2 * 148) return launch_cfg<128, 3>(stream, a, ep);
+  if (tiles128 >= 2 * 148) return launch_persistent(stream, a, ep);
   // One CTA per SM at most: a deep ring (8 x 24 KB in flight) keeps the per-SM L2 link busy
   // through the long serial K loops of the skinny mesh-side GEMMs.
   if (2 * tiles128 <= 148) return launch_cfg<64, 8>(stream, a, ep);

@@ -57,9 +57,11 @@ __global__ void __launch_bounds__(256) ln_cond_kernel(const void* __restrict__ x
                                                       void* __restrict__ out, int out_dtype, int64_t ldo,
                                                       int64_t rows) {
   constexpr int cols = NV * 32;
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  pdl_wait();
   float sc[NV], of[NV];
   if (scale_offset != nullptr) {
     load_row<NV>(scale_offset, GC_F32, 0, lane, sc);
@@ -90,8 +92,14 @@ __global__ void __launch_bounds__(256) ln_cond_kernel(const void* __restrict__ x
 // hundreds to thousands of grid edges and would otherwise
 // be a serial tail.  Summation order is a pure function of (row_ptr, edge_perm),
 // so results are bitwise reproducible.
+//
+// The kernel is latency bound unless many rows are in flight: edges are taken in
+// batches of SEG_UNROLL whose (index ->) row loads are all issued before the first
+// LayerNorm reduction, and the scale / offset vectors live in shared memory to keep
+// the register budget for those in-flight rows.
 constexpr int SEG_WARPS = 8;
 constexpr int HEAVY = 96;
+constexpr int SEG_UNROLL = 4;
 
 template <int NV>
 __global__ void __launch_bounds__(SEG_WARPS * 32) ln_cond_segment_sum_kernel(
@@ -99,29 +107,45 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) ln_cond_segment_sum_kernel(
     const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ edge_perm, void* __restrict__ out,
     int out_dtype, int64_t ldo, int64_t num_segments) {
   constexpr int cols = NV * 32;
-  __shared__ float partial[SEG_WARPS][cols];
+  __shared__ __align__(16) float partial[SEG_WARPS][cols];
+  __shared__ __align__(16) float so_s[2 * cols];
   __shared__ int heavy_seg[SEG_WARPS];
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  float sc[NV], of[NV];
-  if (scale_offset != nullptr) {
-    load_row<NV>(scale_offset, GC_F32, 0, lane, sc);
-    load_row<NV>(scale_offset, GC_F32, cols, lane, of);
-  } else {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) { sc[i] = 1.0f; of[i] = 0.0f; }
-  }
+  pdl_wait();
+  for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x)
+    so_s[c] = scale_offset != nullptr ? __ldg(scale_offset + c) : (c < cols ? 1.0f : 0.0f);
+  __syncthreads();
 
   auto accumulate_range = [&](int beg, int end, float (&acc)[NV]) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
-    for (int j = beg; j < end; ++j) {
-      const int64_t e = edge_perm != nullptr ? __ldg(edge_perm + j) : j;
-      float v[NV];
-      load_row<NV>(y, y_dtype, e * ldy, lane, v);
-      if (do_ln) layer_norm_inplace<NV>(v, cols);
+    for (int j0 = beg; j0 < end; j0 += SEG_UNROLL) {
+      int64_t e[SEG_UNROLL];
 #pragma unroll
-      for (int i = 0; i < NV; ++i) acc[i] += fmaf(v[i], sc[i], of[i]);
+      for (int u = 0; u < SEG_UNROLL; ++u) {
+        const int j = min(j0 + u, end - 1);
+        e[u] = edge_perm != nullptr ? __ldg(edge_perm + j) : j;
+      }
+      float v[SEG_UNROLL][NV];
+#pragma unroll
+      for (int u = 0; u < SEG_UNROLL; ++u) load_row<NV>(y, y_dtype, e[u] * ldy, lane, v[u]);
+#pragma unroll
+      for (int u = 0; u < SEG_UNROLL; ++u) {
+        if (j0 + u < end) {                    // warp-uniform
+          if (do_ln) layer_norm_inplace<NV>(v[u], cols);
+#pragma unroll
+          for (int jj = 0; jj < NV / 4; ++jj) {
+            const float4 sc = *reinterpret_cast<const float4*>(&so_s[(jj * 32 + lane) * 4]);
+            const float4 of = *reinterpret_cast<const float4*>(&so_s[cols + (jj * 32 + lane) * 4]);
+            acc[jj * 4 + 0] += fmaf(v[u][jj * 4 + 0], sc.x, of.x);
+            acc[jj * 4 + 1] += fmaf(v[u][jj * 4 + 1], sc.y, of.y);
+            acc[jj * 4 + 2] += fmaf(v[u][jj * 4 + 2], sc.z, of.z);
+            acc[jj * 4 + 3] += fmaf(v[u][jj * 4 + 3], sc.w, of.w);
+          }
+        }
+      }
     }
   };
 
@@ -186,6 +210,8 @@ __global__ void __launch_bounds__(128) cond_tables_kernel(const float* __restric
   __shared__ float feat[128];
   __shared__ float hid[32];
   __shared__ float cond[16];
+  pdl_launch_dependents();
+  pdl_wait();
   const int layer = blockIdx.x;
   const int si = blockIdx.y;
   const int tid = threadIdx.x;
@@ -226,6 +252,8 @@ __global__ void __launch_bounds__(128) fold_affine_kernel(const void* __restrict
                                                           const float* __restrict__ scale_offset, void* __restrict__ w_out,
                                                           int64_t ldw_out, float* __restrict__ bias_out, int k) {
   __shared__ float red[4];
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.x;
   float dot = 0.0f;
   for (int c = threadIdx.x; c < k; c += blockDim.x) {
@@ -248,6 +276,8 @@ __global__ void __launch_bounds__(256) dpm_update_kernel(const float* __restrict
                                                          int64_t ldx, const float* __restrict__ sched,
                                                          float* __restrict__ x_out, void* __restrict__ xin_out,
                                                          int xin_dtype, int64_t ld_xin, int64_t rows, int cols) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float c_out = __ldg(sched), c_skip = __ldg(sched + 1), a = __ldg(sched + 2), c_in_next = __ldg(sched + 3);
   const int64_t total = rows * cols;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -269,6 +299,8 @@ __global__ void __launch_bounds__(256) cast_pad_kernel(const void* __restrict__ 
                                                        int cols_src, void* __restrict__ dst, int dst_dtype,
                                                        int64_t ld_dst, int cols_dst, const float* __restrict__ scale_dev,
                                                        int64_t rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float scale = scale_dev != nullptr ? __ldg(scale_dev) : 1.0f;
   const int64_t total = rows * cols_dst;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -288,6 +320,8 @@ __global__ void __launch_bounds__(256) cast_pad_kernel(const void* __restrict__ 
 
 __global__ void __launch_bounds__(256) ensemble_accumulate_kernel(const float* __restrict__ x, float* __restrict__ sum,
                                                                   float* __restrict__ sumsq, int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float v = __ldg(x + i);
@@ -329,8 +363,9 @@ int gc_ln_cond(void* stream, const void* x, int32_t x_dtype, int64_t ldx, const 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const unsigned grid = grid_for(rows, 8, 8);
 #define GC_LAUNCH_LN(NV)                                                                                        \
-  ln_cond_kernel<NV><<<grid, 256, 0, st>>>(x, x_dtype, ldx, scale_offset, do_layer_norm, residual, res_dtype, \
-                                            ld_res, out, out_dtype, ldo, rows)
+  GC_CHECK_CUDA(launch_kernel(ln_cond_kernel<NV>, dim3(grid), dim3(256), 0, st, x, x_dtype, ldx, scale_offset,    \
+                              do_layer_norm, residual, res_dtype, ld_res, out, out_dtype, ldo, rows),           \
+                "ln_cond_kernel")
   if (cols == 128) GC_LAUNCH_LN(4);
   else if (cols == 256) GC_LAUNCH_LN(8);
   else GC_LAUNCH_LN(16);
@@ -350,8 +385,9 @@ int gc_ln_cond_segment_sum(void* stream, const void* y, int32_t y_dtype, int64_t
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const unsigned grid = grid_for(num_segments, SEG_WARPS, 8);
 #define GC_LAUNCH_SEG(NV)                                                                                      \
-  ln_cond_segment_sum_kernel<NV><<<grid, SEG_WARPS * 32, 0, st>>>(y, y_dtype, ldy, scale_offset, do_layer_norm, \
-                                                                  row_ptr, edge_perm, out, out_dtype, ldo, num_segments)
+  GC_CHECK_CUDA(launch_kernel(ln_cond_segment_sum_kernel<NV>, dim3(grid), dim3(SEG_WARPS * 32), 0, st, y, y_dtype, ldy, \
+                              scale_offset, do_layer_norm, row_ptr, edge_perm, out, out_dtype, ldo, num_segments),      \
+                "ln_cond_segment_sum_kernel")
   if (cols == 128) GC_LAUNCH_SEG(4);
   else if (cols == 256) GC_LAUNCH_SEG(8);
   else GC_LAUNCH_SEG(16);
@@ -367,8 +403,8 @@ int gc_cond_tables(void* stream, const float* sigma, int32_t num_sigma, const fl
   GC_REQUIRE(num_frequencies >= 1 && num_frequencies <= 64, "gc_cond_tables: num_frequencies=%d", num_frequencies);
   GC_REQUIRE(layers >= 1 && width >= 1 && num_sigma >= 1 && num_sigma <= 65535, "gc_cond_tables: bad sizes");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cond_tables_kernel<<<dim3(layers, num_sigma), 128, 0, st>>>(sigma, w0, b0, w1, b1, base_period, num_frequencies, wc,
-                                                              bc, layers, width, table);
+  GC_CHECK_CUDA(launch_kernel(cond_tables_kernel, dim3(layers, num_sigma), dim3(128), 0, st, sigma, w0, b0, w1, b1,
+                              base_period, num_frequencies, wc, bc, layers, width, table), "cond_tables_kernel");
   GC_CHECK_LAUNCH("cond_tables_kernel");
   return GC_OK;
 }
@@ -379,7 +415,8 @@ int gc_fold_affine_into_linear(void* stream, const void* w, int32_t dtype, int64
   GC_REQUIRE(w && scale_offset && w_out && bias_out, "gc_fold_affine_into_linear: null buffer");
   GC_REQUIRE(dtype_ok(dtype) && n > 0 && k > 0, "gc_fold_affine_into_linear: bad arguments");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  fold_affine_kernel<<<n, 128, 0, st>>>(w, dtype, ldw, bias, scale_offset, w_out, ldw_out, bias_out, k);
+  GC_CHECK_CUDA(launch_kernel(fold_affine_kernel, dim3(n), dim3(128), 0, st, w, dtype, ldw, bias, scale_offset, w_out,
+                              ldw_out, bias_out, k), "fold_affine_kernel");
   GC_CHECK_LAUNCH("fold_affine_kernel");
   return GC_OK;
 }
@@ -392,8 +429,8 @@ int gc_dpm_update(void* stream, const float* f, int64_t ldf, const float* x_cur,
   if (xin_out) GC_REQUIRE(dtype_ok(xin_dtype) && ld_xin >= cols, "gc_dpm_update: bad xin");
   if (rows <= 0) return GC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  dpm_update_kernel<<<grid_for(rows * cols, 256 * 4, 8), 256, 0, st>>>(f, ldf, x_cur, x_base, ldx, sched, x_out, xin_out,
-                                                                      xin_dtype, ld_xin, rows, cols);
+  GC_CHECK_CUDA(launch_kernel(dpm_update_kernel, dim3(grid_for(rows * cols, 256 * 4, 8)), dim3(256), 0, st, f, ldf, x_cur,
+                              x_base, ldx, sched, x_out, xin_out, xin_dtype, ld_xin, rows, cols), "dpm_update_kernel");
   GC_CHECK_LAUNCH("dpm_update_kernel");
   return GC_OK;
 }
@@ -405,8 +442,8 @@ int gc_cast_pad(void* stream, const void* src, int32_t src_dtype, int64_t ld_src
   GC_REQUIRE(cols_src >= 0 && cols_dst > 0 && ld_src >= cols_src && ld_dst >= cols_dst, "gc_cast_pad: bad sizes");
   if (rows <= 0) return GC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cast_pad_kernel<<<grid_for(rows * cols_dst, 256 * 4, 8), 256, 0, st>>>(src, src_dtype, ld_src, cols_src, dst, dst_dtype,
-                                                                        ld_dst, cols_dst, scale_dev, rows);
+  GC_CHECK_CUDA(launch_kernel(cast_pad_kernel, dim3(grid_for(rows * cols_dst, 256 * 4, 8)), dim3(256), 0, st, src, src_dtype,
+                              ld_src, cols_src, dst, dst_dtype, ld_dst, cols_dst, scale_dev, rows), "cast_pad_kernel");
   GC_CHECK_LAUNCH("cast_pad_kernel");
   return GC_OK;
 }
@@ -415,7 +452,8 @@ int gc_ensemble_accumulate(void* stream, const float* x, float* sum, float* sums
   GC_REQUIRE(x && sum && sumsq, "gc_ensemble_accumulate: null buffer");
   if (n <= 0) return GC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  ensemble_accumulate_kernel<<<grid_for(n, 256 * 4, 8), 256, 0, st>>>(x, sum, sumsq, n);
+  GC_CHECK_CUDA(launch_kernel(ensemble_accumulate_kernel, dim3(grid_for(n, 256 * 4, 8)), dim3(256), 0, st, x, sum, sumsq, n),
+                "ensemble_accumulate_kernel");
   GC_CHECK_LAUNCH("ensemble_accumulate_kernel");
   return GC_OK;
 }
