@@ -174,28 +174,39 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmShape 
 
 // ---------------------------------------------------------------------------------------------
 // Persistent variant for problems with at least ~2 tiles per SM: one CTA per SM walks tiles
-// blockIdx.x, blockIdx.x + gridDim.x, ...  The accumulator is double buffered in TMEM (2 x 128
-// columns), so the tensor core starts tile i+1 while eight epilogue warps (two per TMEM lane
-// quarter, half the columns each) drain tile i; the TMA producer runs ahead through a 6-stage
-// 192 KB operand ring across tile boundaries.
+// blockIdx.x, blockIdx.x + gridDim.x, ...  The accumulator is double buffered in TMEM, so the
+// tensor core starts tile i+1 while eight epilogue warps (two per TMEM lane quarter, half the
+// columns each) drain tile i; the TMA producer runs ahead through the operand ring across tile
+// boundaries.  128 x 128 tiles are bound by the L2 -> SM operand feed (64 FLOP per byte staged,
+// ~6.3 KB/clk chip-wide => ~1/3 of the tensor peak), so the tile is 128 x 256 whenever N allows
+// it (87 FLOP/B): TMEM then holds exactly two 256-column accumulators.
 // ---------------------------------------------------------------------------------------------
-constexpr int PBN = 128;
-constexpr int PSTAGES = 6;
-constexpr int P_B_STAGE_BYTES = PBN * BK * 2;
-constexpr int P_STAGE_BYTES = A_STAGE_BYTES + P_B_STAGE_BYTES;
-constexpr int P_BAR_OFFSET = PSTAGES * P_STAGE_BYTES;
-constexpr int P_SMEM_BYTES = P_BAR_OFFSET + 256 + 1024;
+template <int PBN>
+struct PersistCfg {
+  static constexpr int STAGES = PBN == 256 ? 4 : 6;
+  static constexpr int B_STAGE_BYTES = PBN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;
+  static constexpr int SMEM_BYTES = BIAS_OFFSET + 2 * PBN * 4 + 1024;
+};
 constexpr int P_THREADS = 320;
 
+template <int PBN>
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shape, const EpilogueParams ep,
                                     const int num_tiles) {
   using namespace sm100;
+  using C = PersistCfg<PBN>;
+  constexpr int PSTAGES = C::STAGES;
+  constexpr int HALF = PBN / 2;                 // columns per epilogue warp
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + PSTAGES * A_STAGE_BYTES;
-  const uint32_t bars = smem_base + P_BAR_OFFSET;
+  const uint32_t bars = smem_base + C::BAR_OFFSET;
+  float* bias_s = reinterpret_cast<float*>(smem_gen + C::BIAS_OFFSET);      // [2][PBN]
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (PSTAGES + s); };
   auto acc_full = [&](int b) { return bars + 8u * (2 * PSTAGES + b); };
@@ -241,9 +252,13 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const
         for (int s = 0; s < shape.num_segments; ++s) {
           for (int kb = 0; kb < shape.kblocks[s]; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_arrive_expect_tx(full_bar(stage), P_STAGE_BYTES);
+            mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
             tma_load_2d(smem_a + stage * A_STAGE_BYTES, &maps.a[s], full_bar(stage), kb * BK, m_blk * BM);
-            tma_load_2d(smem_b + stage * P_B_STAGE_BYTES, &maps.w[s], full_bar(stage), kb * BK, n_blk * PBN);
+            // W box is 128 rows: two boxes for a 256-wide tile
+#pragma unroll
+            for (int h = 0; h < PBN / 128; ++h)
+              tma_load_2d(smem_b + stage * C::B_STAGE_BYTES + h * (128 * BK * 2), &maps.w[s], full_bar(stage), kb * BK,
+                          n_blk * PBN + h * 128);
             if (++stage == PSTAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -265,7 +280,7 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             const uint64_t da = desc_kmajor_sw128(smem_a + stage * A_STAGE_BYTES);
-            const uint64_t db = desc_kmajor_sw128(smem_b + stage * P_B_STAGE_BYTES);
+            const uint64_t db = desc_kmajor_sw128(smem_b + stage * C::B_STAGE_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               umma_f16(tmem_base + b * PBN, da + 2u * k, db + 2u * k, idesc, accumulate);
@@ -281,6 +296,7 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const
   } else {
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;             // 0..255 within the epilogue group
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     pdl_wait();
     const float alpha = ep.alpha_dev != nullptr ? __ldg(ep.alpha_dev) : 1.0f;
@@ -288,20 +304,24 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int n_blk = tile % shape.n_tiles, m_blk = tile / shape.n_tiles;
       const int b = lt & 1;
+      // this tile's bias slice -> shared memory while the tensor core is still busy with it
+      if (et < PBN) bias_s[b * PBN + et] = ep.bias != nullptr ? __ldg(ep.bias + n_blk * PBN + et) : 0.0f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float* bias_ptr = ep.bias != nullptr ? bias_s + b * PBN + half * HALF : nullptr;
       const int64_t row = static_cast<int64_t>(m_blk) * BM + q * 32 + lane;
-      const int col_base = n_blk * PBN + half * (PBN / 2);
-      const uint32_t taddr = tmem_base + b * PBN + half * (PBN / 2) + lane_addr;
+      const int col_base = n_blk * PBN + half * HALF;
+      const uint32_t taddr = tmem_base + b * PBN + half * HALF + lane_addr;
       mbar_wait(acc_full(b), (lt >> 1) & 1);
       tc_fence_after();
       uint32_t r[32];
       tmem_ld_32x32b_x32(taddr, r);
 #pragma unroll
-      for (int c = 0; c < PBN / 2; c += 32) {
+      for (int c = 0; c < HALF; c += 32) {
         float v[32];
         tc_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (c + 32 < PBN / 2) {
+        if (c + 32 < HALF) {
           tmem_ld_32x32b_x32(taddr + c + 32, r);
         } else {
           // last read of this buffer is in registers: hand it back to the MMA warp before the math
@@ -309,8 +329,7 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty(b));
         }
-        if (row < ep.m)
-          epilogue_row_segment<32, true>(ep, alpha, row, col_base + c, v, ep.bias != nullptr ? ep.bias + col_base + c : nullptr);
+        if (row < ep.m) epilogue_row_segment<32, true>(ep, alpha, row, col_base + c, v, bias_ptr ? bias_ptr + c : nullptr);
       }
     }
   }
@@ -390,7 +409,9 @@ int launch_cfg(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams&
   return GC_OK;
 }
 
+template <int PBN>
 int launch_persistent(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
+  using C = PersistCfg<PBN>;
   GemmMaps maps;
   GemmShape shape;
   shape.num_segments = a.num_segments;
@@ -400,15 +421,15 @@ int launch_persistent(cudaStream_t stream, const gc_gemm_args& a, const Epilogue
     shape.kblocks[s] = a.k[s] / BK;
     int rc = make_tmap_bf16_2d(&maps.a[s], a.a[s], (uint64_t)a.m, (uint64_t)a.k[s], (uint64_t)a.lda[s], BK, BM);
     if (rc != GC_OK) return rc;
-    rc = make_tmap_bf16_2d(&maps.w[s], a.w[s], (uint64_t)a.n, (uint64_t)a.k[s], (uint64_t)a.ldw[s], BK, PBN);
+    rc = make_tmap_bf16_2d(&maps.w[s], a.w[s], (uint64_t)a.n, (uint64_t)a.k[s], (uint64_t)a.ldw[s], BK, 128);
     if (rc != GC_OK) return rc;
   }
   for (int s = a.num_segments; s < GC_MAX_SEGMENTS; ++s) {
     maps.a[s] = maps.a[0];
     maps.w[s] = maps.w[0];
   }
-  GC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     P_SMEM_BYTES), "cudaFuncSetAttribute(gemm_bf16_tcgen05_persistent_kernel)");
+  GC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_persistent_kernel<PBN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C::SMEM_BYTES), "cudaFuncSetAttribute(gemm_bf16_tcgen05_persistent_kernel)");
   const int64_t num_tiles = ((a.m + BM - 1) / BM) * shape.n_tiles;
   if (num_tiles > 0x7fffffffLL) {
     set_error("gc_gemm: too many tiles (%lld)", (long long)num_tiles);
@@ -417,15 +438,19 @@ int launch_persistent(cudaStream_t stream, const gc_gemm_args& a, const Epilogue
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)(num_tiles < sms ? num_tiles : sms);
-  GC_CHECK_CUDA(launch_kernel(gemm_bf16_tcgen05_persistent_kernel, dim3(grid), dim3(P_THREADS), (size_t)P_SMEM_BYTES, stream,
-                              maps, shape, ep, (int)num_tiles), "gemm_bf16_tcgen05_persistent_kernel");
+  GC_CHECK_CUDA(launch_kernel(gemm_bf16_tcgen05_persistent_kernel<PBN>, dim3(grid), dim3(P_THREADS), (size_t)C::SMEM_BYTES,
+                              stream, maps, shape, ep, (int)num_tiles), "gemm_bf16_tcgen05_persistent_kernel");
   return GC_OK;
 }
 
 int launch_gemm_tcgen05(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
   // Fewer than ~2 CTAs per SM with 128-wide tiles: halve the tile width to spread the work.
   const int64_t tiles128 = ((a.m + BM - 1) / BM) * (a.n / 128);
-  if (tiles128 >= 2 * 148) return launch_persistent(stream, a, ep);
+  if (tiles128 >= 2 * 148) {
+    // 256-wide tiles when N allows it and there are still >= 2 tiles per SM
+    if (a.n % 256 == 0 && tiles128 >= 4 * 148) return launch_persistent<256>(stream, a, ep);
+    return launch_persistent<128>(stream, a, ep);
+  }
   // One CTA per SM at most: a deep ring (8 x 24 KB in flight) keeps the per-SM L2 link busy
   // through the long serial K loops of the skinny mesh-side GEMMs.
   if (2 * tiles128 <= 148) return launch_cfg<64, 8>(stream, a, ep);
