@@ -8,20 +8,31 @@
 //     P = exp2(S - max)  softmax warps read S from TMEM, apply the bit mask, write bf16 P
 //                        to shared memory in the K-major swizzled operand layout
 //     O += P V           tcgen05.mma  M=128 N=d K=128      (V consumed MN-major, no transpose)
-// Softmax is exact and two-pass: pass 1 sweeps the key tiles for the masked row maximum
-// (S only), pass 2 recomputes S, exponentiates against the final maximum and accumulates
-// O in TMEM, so O is never rescaled.  Masked logits contribute exactly 0, which is what
-// the reference's where(mask, logits, -1e30) + softmax evaluates to
-// (gencast/sparse_transformer.py:100-125, :340-347).
+// Softmax is exact, single pass and online: every row keeps a running offset m and sum l;
+// a tile's masked maximum only replaces m when it exceeds it by more than 2^8 (then l and
+// the row of O in TMEM are rescaled by the softmax warps themselves, which is rare after
+// the first tile), otherwise exponentials are taken against the stale offset, which is
+// exact after the final division by l.  The kernel is bound by the L2 -> SM operand feed
+// (K and V tiles are re-read by every query tile that lists them), so K is staged once
+// per tile, not twice.  Masked logits contribute exactly 0, which is what the reference's
+// where(mask, logits, -1e30) + softmax evaluates to (gencast/sparse_transformer.py:100-125,
+// :340-347).
 //
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
-// warps 2-9 softmax / epilogue: two warps per TMEM lane quarter (warp % 4), each owning
-// one 64-key half of every S tile, so each SM sub-partition has two warps to interleave.
-// TMEM: S double buffer (2 x 128 columns) + O (d columns).
+// warps 2-9 softmax / epilogue in two groups of four (one warp per TMEM lane quarter each):
+// group g owns the key tiles t = g, g+2, ... with its own S buffer, P buffer, O accumulator
+// and (m, l) state, so the two groups are independent online-softmax streams that are merged
+// once at the end (O = (a0 O_0 + a1 O_1) / (a0 l_0 + a1 l_1), a_g = 2^(m_g - m)); no per-tile
+// exchange between warps is needed and each SM sub-partition has two warps to interleave.
+// 32 x 32 sub-blocks of a tile whose mask bits are all zero (about half of them with the
+// hierarchical patch ordering of the mesh) skip the exponentials altogether.
+// TMEM: S_0, S_1 (2 x 128 columns) + O_0, O_1 (2 x d columns).
 #include "common.cuh"
 #include "sm100.cuh"
 
 namespace gc {
+
+long long* g_attention_trace = nullptr;
 
 namespace {
 
@@ -35,9 +46,9 @@ struct AttCfg {
   static constexpr int SLOT_BYTES = TK * D * 2;          // one K or V tile
   static constexpr int Q_BYTES = TQ * D * 2;
   static constexpr int P_BYTES = TQ * TK * 2;            // 32 KB, two 64-key chunks
-  static constexpr int NPBUF = D == 64 ? 2 : 1;
-  static constexpr int NSLOT = D == 64 ? 6 : 4;
-  static constexpr int SMEM = Q_BYTES + NSLOT * SLOT_BYTES + NPBUF * P_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*exchange*/;
+  static constexpr int NPBUF = 2;
+  static constexpr int NSLOT = D == 64 ? 6 : 3;   // K / V tile ring
+  static constexpr int SMEM = Q_BYTES + NSLOT * SLOT_BYTES + NPBUF * P_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 3072 /*exchange*/;
 };
 
 struct AttParams {
@@ -50,7 +61,15 @@ struct AttParams {
   int heads;
   int hd;                     // heads * head_dim = column offset of K inside a qkv row (V at 2 * hd)
   float scale_log2e;          // head_dim^-0.5 * log2(e)
+  long long* trace;           // debug: per-role clock stamps of CTA 0 (null in normal use)
 };
+
+// Debug timeline: CTA 0 records clock64() at pipeline events into trace[role * 512 + index].
+#define GC_TRACE(role, index)                                                         \
+  do {                                                                                \
+    if (p.trace != nullptr && blockIdx.x == 0 && (index) < 512) p.trace[(role) * 512 + (index)] = clock64(); \
+  } while (0)
+
 
 template <int D>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -85,8 +104,8 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
     mbar_init(q_full, 1);
     for (int s = 0; s < C::NSLOT; ++s) { mbar_init(slot_full(s), 1); mbar_init(slot_empty(s), 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(s_full(b), 1); mbar_init(s_free(b), 8);
-      mbar_init(p_full(b), 8); mbar_init(p_empty(b), 1);
+      mbar_init(s_full(b), 1); mbar_init(s_free(b), 4);
+      mbar_init(p_full(b), 4); mbar_init(p_empty(b), 1);
     }
     mbar_init(o_full, 1);
     fence_mbar_init();
@@ -119,15 +138,16 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
       for (int c = 0; c < C::CHUNKS; ++c) tma_load_2d(q_smem + c * (TQ * 128), &qkv_map, q_full, q_col + 64 * c, qt * TQ);
       int slot = 0;
       uint32_t phase = 0;
+      int tma_ev = 0;
       auto load_tile = [&](int col, int kv) {
         mbar_wait(slot_empty(slot), phase ^ 1u);
+        GC_TRACE(0, tma_ev); ++tma_ev;
         mbar_arrive_expect_tx(slot_full(slot), C::SLOT_BYTES);
         for (int c = 0; c < C::CHUNKS; ++c)
           tma_load_2d(slot_smem + slot * C::SLOT_BYTES + c * (TK * 128), &qkv_map, slot_full(slot), col + 64 * c, kv * TK);
         if (++slot == C::NSLOT) { slot = 0; phase ^= 1u; }
       };
-      for (int t = 0; t < T; ++t) load_tile(k_col, __ldg(p.tile_kv + t_beg + t));          // pass 1: K_0 .. K_{T-1}
-      // pass 2 consumption order: K_0, K_1, V_0, K_2, V_1, ..., K_{T-1}, V_{T-2}, V_{T-1}
+      // consumption order: K_0, K_1, V_0, K_2, V_1, ..., K_{T-1}, V_{T-2}, V_{T-1}
       for (int t = 0; t < T; ++t) {
         if (t == 0) load_tile(k_col, __ldg(p.tile_kv + t_beg));
         if (t + 1 < T) load_tile(k_col, __ldg(p.tile_kv + t_beg + t + 1));
@@ -142,10 +162,13 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
       int slot = 0;
       uint32_t slot_phase = 0;
       int g = 0;     // S iterations issued so far (buffer g & 1, use count g >> 1)
+      int mma_ev = 0;
       auto issue_s = [&]() {
         const int b = g & 1;
         mbar_wait(slot_full(slot), slot_phase);
+        GC_TRACE(1, 2 * mma_ev);
         mbar_wait(s_free(b), ((g >> 1) & 1) ^ 1u);
+        GC_TRACE(1, 2 * mma_ev + 1); ++mma_ev;
         tc_fence_after();
         const uint32_t k_base = slot_smem + slot * C::SLOT_BYTES;
 #pragma unroll
@@ -159,13 +182,14 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
         ++g;
       };
       mbar_wait(q_full, 0);
-      for (int t = 0; t < T; ++t) issue_s();                       // pass 1
-      for (int t = 0; t < T; ++t) {                                // pass 2
+      for (int t = 0; t < T; ++t) {
         if (t == 0) issue_s();
         if (t + 1 < T) issue_s();
         const int pb = t % C::NPBUF;
         mbar_wait(slot_full(slot), slot_phase);
+        GC_TRACE(2, 2 * t);
         mbar_wait(p_full(pb), (t / C::NPBUF) & 1);
+        GC_TRACE(2, 2 * t + 1);
         tc_fence_after();
         const uint32_t v_base = slot_smem + slot * C::SLOT_BYTES;
         const uint32_t p_base = p_smem + pb * C::P_BYTES;
@@ -175,7 +199,7 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
           // 16 key rows of 128 B start at j * 2048; 64-wide d chunks are TK * 128 bytes apart.
           const uint64_t da = desc_kmajor_sw128(p_base + (j >> 2) * (TQ * 128) + (j & 3) * 32);
           const uint64_t db = desc_mnmajor_sw128(v_base + j * 2048, TK * 128, 1024);
-          umma_f16(tmem_o, da, db, idesc_o, (t > 0 || j > 0) ? 1u : 0u);
+          umma_f16(tmem_o + (t & 1) * D, da, db, idesc_o, (t > 1 || j > 0) ? 1u : 0u);
         }
         umma_commit(slot_empty(slot));
         umma_commit(p_empty(pb));
@@ -186,82 +210,102 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
   } else {
     // ---------------- softmax + epilogue warps
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;                  // which 64-key half of each S tile this warp owns
+    const int grp = (warp - 2) >> 2;                   // softmax group = parity of the key tiles it owns
     const int r = q * 32 + lane;                       // row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    float* xch = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + 8 * 32);   // [2][128] exchange
-    pdl_wait();
-    int g = 0;
-    // Each thread walks its half row in two 32-column steps; the tcgen05.ld of the next step is in
-    // flight while the current one is reduced, and reductions use independent accumulators.
-    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    for (int t = 0; t < T; ++t, ++g) {                 // pass 1: masked row maximum
-      const int b = g & 1;
-      const uint2 mk = __ldg(reinterpret_cast<const uint2*>(p.tile_mask + static_cast<int64_t>(t_beg + t) * TQ + r) + half);
-      const uint32_t mw[2] = {mk.x, mk.y};
-      mbar_wait(s_full(b), (g >> 1) & 1);
-      tc_fence_after();
-      const uint32_t s_addr = tmem_s0 + b * 128 + half * 64 + lane_addr;
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(s_addr, v);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float f[32];
-        tc_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        if (c < 1) tmem_ld_32x32b_x32(s_addr + 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          mx[i & 3] = fmaxf(mx[i & 3], (mw[c] & (1u << i)) ? f[i] : -INFINITY);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_free(b));
-    }
-    float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-    // combine the two halves of each row (named barrier 1 over the 256 softmax threads)
-    xch[half * 128 + r] = m;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    m = fmaxf(m, xch[(half ^ 1) * 128 + r]);
-    const float m_scaled = (m == -INFINITY) ? 0.0f : m * p.scale_log2e;
+    float* xch = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + 8 * 32);   // [2 groups][m, l][128]
+    const float c2 = p.scale_log2e;
+    const uint32_t s_addr = tmem_s0 + grp * 128 + lane_addr;
+    const uint32_t o_addr = tmem_o + grp * D + lane_addr;
+    const uint32_t p_row = p_smem + grp * C::P_BYTES + r * 128;
+    float m = -INFINITY;                               // running offset (raw logit units)
     float ls[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    for (int t = 0; t < T; ++t, ++g) {                 // pass 2: P = exp2(S * c - max * c), row sums
-      const int b = g & 1;
-      const int pb = t % C::NPBUF;
-      const uint2 mk = __ldg(reinterpret_cast<const uint2*>(p.tile_mask + static_cast<int64_t>(t_beg + t) * TQ + r) + half);
-      const uint32_t mw[2] = {mk.x, mk.y};
-      mbar_wait(s_full(b), (g >> 1) & 1);
+    for (int t = grp; t < T; t += 2) {
+      const int use = t >> 1;                          // how many times this group's buffers were used before
+      const uint4 mk = __ldg(p.tile_mask + static_cast<int64_t>(t_beg + t) * TQ + r);
+      const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+      // 32 x 32 sub-blocks without any neighbour are skipped (warp-uniform)
+      bool live[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) live[c] = __any_sync(0xffffffffu, mw[c] != 0u);
+      if (threadIdx.x == 64) GC_TRACE(3, 2 * t);
+      mbar_wait(s_full(grp), use & 1);
+      if (threadIdx.x == 64) GC_TRACE(3, 2 * t + 1);
       tc_fence_after();
-      const uint32_t s_addr = tmem_s0 + b * 128 + half * 64 + lane_addr;
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(s_addr, v);
-      if (t >= C::NPBUF) mbar_wait(p_empty(pb), ((t / C::NPBUF) - 1) & 1);
-      // this warp's keys are the 64-key operand chunk `half` of P
-      const uint32_t chunk_base = p_smem + pb * C::P_BYTES + half * (TQ * 128) + r * 128;
+      // (a) masked maximum of the row over this tile
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float f[32];
-        tc_wait_ld();
+      for (int c = 0; c < 4; ++c) {
+        if (live[c]) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(s_addr + c * 32, v);
+          tc_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        if (c < 1) tmem_ld_32x32b_x32(s_addr + 32, v);
-        uint32_t packed[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float e0, e1;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(f[i], p.scale_log2e, -m_scaled)));
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(f[i + 1], p.scale_log2e, -m_scaled)));
-          const float p0 = (mw[c] & (1u << i)) ? e0 : 0.0f;
-          const float p1 = (mw[c] & (1u << (i + 1))) ? e1 : 0.0f;
-          ls[(i >> 1) & 3] += p0 + p1;
-          const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-          packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+          for (int i = 0; i < 32; ++i)
+            mx[i & 3] = fmaxf(mx[i & 3], (mw[c] & (1u << i)) ? __uint_as_float(v[i]) : -INFINITY);
         }
-        // keys 32c .. 32c+31 of the chunk -> 16-byte units c * 4 + u, swizzled by row
+      }
+      const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      const float m_new = fmaxf(m, mt);
+      // the P buffer is free and O_grp is at rest once PV(t-2) has completed
+      if (use > 0) {
+        mbar_wait(p_empty(grp), (use - 1) & 1);
+        tc_fence_after();
+      }
+      if (threadIdx.x == 64) GC_TRACE(4, t);
+      if (use == 0) {
+        m = m_new;                                     // nothing accumulated yet
+      } else {
+        // raise the offset only when the stale one would let exponentials grow past 2^8
+        const bool need = m_new * c2 > m * c2 + 8.0f;      // false when m_new == m (incl. both -inf)
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? exp2f(m * c2 - m_new * c2) : 1.0f;   // m = -inf -> 0
+          if (need) {
+            m = m_new;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ls[i] *= alpha;
+          }
+#pragma unroll
+          for (int c = 0; c < D; c += 32) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(o_addr + c, o);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(o_addr + c, o);
+          }
+          tc_wait_st();
+        }
+      }
+      const float offset = (m == -INFINITY) ? 0.0f : m * c2;
+      // (b) P = exp2(S c - offset) on the live sub-blocks, zeros elsewhere -> swizzled K-major operand
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t packed[16];
+        if (live[c]) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(s_addr + c * 32, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float e0, e1;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(v[i]), c2, -offset)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(v[i + 1]), c2, -offset)));
+            const float p0 = (mw[c] & (1u << i)) ? e0 : 0.0f;
+            const float p1 = (mw[c] & (1u << (i + 1))) ? e1 : 0.0f;
+            ls[(i >> 1) & 3] += p0 + p1;
+            const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+            packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) packed[i] = 0u;
+        }
+        // keys 32c .. 32c+31 -> 64-key chunk (c >> 1), 16-byte units (c & 1) * 4 + u, swizzled by row
+        const uint32_t chunk_base = p_row + (c >> 1) * (TQ * 128);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const uint32_t unit = static_cast<uint32_t>(c * 4 + u) ^ static_cast<uint32_t>(r & 7);
+          const uint32_t unit = static_cast<uint32_t>((c & 1) * 4 + u) ^ static_cast<uint32_t>(r & 7);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(chunk_base + unit * 16), "r"(packed[4 * u]),
                        "r"(packed[4 * u + 1]), "r"(packed[4 * u + 2]), "r"(packed[4 * u + 3])
                        : "memory");
@@ -271,24 +315,34 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
       fence_proxy_async_smem();       // generic-proxy stores of P -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(s_free(b));
-        mbar_arrive(p_full(pb));
+        mbar_arrive(s_free(grp));
+        mbar_arrive(p_full(grp));
       }
     }
-    float l = (ls[0] + ls[1]) + (ls[2] + ls[3]);
-    asm volatile("bar.sync 1, 256;" ::: "memory");     // everyone has read the pass-1 exchange
-    xch[half * 128 + r] = l;
+    // ---- merge the two streams: every thread publishes (m, l) of its row
+    const float l_own = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+    xch[grp * 256 + r] = m;
+    xch[grp * 256 + 128 + r] = l_own;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    l += xch[(half ^ 1) * 128 + r];
-    // epilogue: O / l -> bf16 -> global; each warp stores its half of the head's channels
+    const float m0 = xch[r], l0 = xch[128 + r], m1 = xch[256 + r], l1 = xch[256 + 128 + r];
+    const float mm = fmaxf(m0, m1);
+    const float a0 = (m0 == -INFINITY) ? 0.0f : exp2f((m0 - mm) * c2);
+    const float a1 = (m1 == -INFINITY) ? 0.0f : exp2f((m1 - mm) * c2);
+    const float l = l0 * a0 + l1 * a1;
+    const bool two = T > 1;                            // O_1 is only defined when group 1 had a tile
+    // epilogue: group g stores channel half g of the head
+    if (threadIdx.x == 64) GC_TRACE(5, 0);
     mbar_wait(o_full, 0);
+    if (threadIdx.x == 64) GC_TRACE(5, 1);
     tc_fence_after();
     const float inv_l = l > 0.0f ? 1.0f / l : 0.0f;
+    const float w0 = a0 * inv_l, w1 = a1 * inv_l;
     const int64_t row = static_cast<int64_t>(qt) * TQ + r;
 #pragma unroll
-    for (int c = half * (D / 2); c < (half + 1) * (D / 2); c += 32) {
-      uint32_t v[32];
+    for (int c = grp * (D / 2); c < (grp + 1) * (D / 2); c += 32) {
+      uint32_t v[32], u[32];
       tmem_ld_32x32b_x32(tmem_o + lane_addr + c, v);
+      if (two) tmem_ld_32x32b_x32(tmem_o + D + lane_addr + c, u);
       tc_wait_ld();
       if (row < p.nodes && T > 0) {
         __nv_bfloat16* dst = p.out + row * p.ldo + head * D + c;
@@ -297,8 +351,14 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
           uint4 o;
           __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            h[j] = __floats2bfloat162_rn(__uint_as_float(v[i + 2 * j]) * inv_l, __uint_as_float(v[i + 2 * j + 1]) * inv_l);
+          for (int j = 0; j < 4; ++j) {
+            float x0 = __uint_as_float(v[i + 2 * j]) * w0, x1 = __uint_as_float(v[i + 2 * j + 1]) * w0;
+            if (two) {
+              x0 = fmaf(__uint_as_float(u[i + 2 * j]), w1, x0);
+              x1 = fmaf(__uint_as_float(u[i + 2 * j + 1]), w1, x1);
+            }
+            h[j] = __floats2bfloat162_rn(x0, x1);
+          }
           *reinterpret_cast<uint4*>(dst + i) = o;
         }
       }
@@ -322,6 +382,11 @@ int launch_tc(cudaStream_t st, const CUtensorMap& map, const AttParams& p, int n
 }  // namespace
 }  // namespace gc
 
+// Debug hook (not part of the public header): clock-stamp buffer of at least 8 * 512 int64.
+extern "C" __attribute__((visibility("default"))) void gc_debug_set_attention_trace(void* ptr) {
+  gc::g_attention_trace = reinterpret_cast<long long*>(ptr);
+}
+
 extern "C" int gc_khop_attention_tiles(void* stream, const void* qkv, int64_t ld_qkv, const int32_t* tile_ptr,
                                        const int32_t* tile_kv, const uint32_t* tile_mask, void* out, int64_t ldo,
                                        int64_t nodes, int32_t heads, int32_t head_dim) {
@@ -341,6 +406,7 @@ extern "C" int gc_khop_attention_tiles(void* stream, const void* qkv, int64_t ld
   p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ldo = ldo; p.nodes = (int)nodes; p.heads = heads;
   p.hd = heads * head_dim;
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)head_dim);
+  p.trace = g_attention_trace;
   const int num_q_tiles = (int)((nodes + 127) / 128);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (head_dim == 64) return launch_tc<64>(st, map, p, num_q_tiles);

@@ -379,14 +379,17 @@ def khop_tiles(khop: sparse.spmatrix, tile: int = 128):
     return tile_ptr, tile_kv, np.ascontiguousarray(mask)
 
 
-def patch_order(xyz: np.ndarray, leaf: int = 128) -> np.ndarray:
-    """Permutation that groups mesh nodes into spatially compact patches of `leaf` nodes.
+def patch_order(xyz: np.ndarray, leaf: int = 128, sub_leaf: int = 32) -> np.ndarray:
+    """Permutation that groups mesh nodes into spatially compact patches of `leaf` nodes, each of
+    which is itself ordered into compact sub-patches of `sub_leaf` nodes.
 
-    Recursive bisection along the principal axis with left halves sized in multiples of `leaf`,
-    so every aligned block of `leaf` consecutive nodes is one patch.  Attention is permutation
-    equivariant and mesh latents never leave the denoiser, so the engine is free to relabel mesh
-    nodes; compact patches put the k-hop neighbourhoods of a query tile into fewer key tiles than
-    the band ordering the reference needs for its tri-block mask (gencast/denoiser.py:849-867).
+    Recursive bisection along the principal axis with left halves sized in multiples of `leaf`
+    (then `sub_leaf`), so every aligned block of `leaf` (`sub_leaf`) consecutive nodes is one
+    patch.  Attention is permutation equivariant and mesh latents never leave the denoiser, so the
+    engine is free to relabel mesh nodes; compact patches put the k-hop neighbourhoods of a query
+    tile into fewer key tiles than the band ordering the reference needs for its tri-block mask
+    (gencast/denoiser.py:849-867), and compact sub-patches leave about half of the 32 x 32
+    sub-blocks of those tiles empty, which the attention kernel skips.
     new position i holds old node order[i].
     """
     xyz = np.asarray(xyz, np.float64)
@@ -394,15 +397,16 @@ def patch_order(xyz: np.ndarray, leaf: int = 128) -> np.ndarray:
 
     def rec(ids):
         n = len(ids)
-        if n <= leaf:
+        if n <= sub_leaf:
             out.append(ids)
             return
+        step = leaf if n > leaf else sub_leaf
         c = xyz[ids] - xyz[ids].mean(0)
         _, _, vt = np.linalg.svd(c, full_matrices=False)
         order = np.argsort(c @ vt[0], kind="stable")
-        nl = ((n // 2 + leaf - 1) // leaf) * leaf
+        nl = ((n // 2 + step - 1) // step) * step
         if nl >= n:
-            nl = n - leaf
+            nl = n - step
         rec(ids[order[:nl]])
         rec(ids[order[nl:]])
 

@@ -156,8 +156,8 @@ def test_khop_attention(cuda_device, dtype, heads, head_dim):
 
 
 @pytest.mark.parametrize("heads,head_dim", [(4, 64), (2, 128), (4, 128)])
-@pytest.mark.parametrize("n,density", [(300, 0.2), (1000, 0.05), (128, 1.0)])
-def test_khop_attention_tensor_core(cuda_device, heads, head_dim, n, density):
+@pytest.mark.parametrize("n,density,qk_scale", [(300, 0.2, 1.5), (1000, 0.05, 1.5), (128, 1.0, 1.5), (1000, 0.3, 5.0)])
+def test_khop_attention_tensor_core(cuda_device, heads, head_dim, n, density, qk_scale):
     """Block-sparse tcgen05 attention against dense masked softmax attention in fp64."""
     from scipy import sparse
     from gencast_flax_nnx_b200 import ops
@@ -165,9 +165,14 @@ def test_khop_attention_tensor_core(cuda_device, heads, head_dim, n, density):
     rng = np.random.default_rng(head_dim + n)
     hd = heads * head_dim
     g = torch.Generator(device="cpu").manual_seed(4)
-    qkv = (torch.randn(n, 3 * hd, generator=g) * 1.5).to(torch.bfloat16)
+    # qk_scale 5 gives logits of order +-50: row maxima jump between key tiles, which exercises the
+    # online-softmax offset update and the rescaling of O in tensor memory
+    qkv = torch.randn(n, 3 * hd, generator=g)
+    qkv[:, :2 * hd] *= qk_scale
+    qkv[:, 2 * hd:] *= 1.5
+    qkv = qkv.to(torch.bfloat16)
     mask = rng.random((n, n)) < density
-    if n == 1000:
+    if n == 1000 and density < 0.1:
         mask[:, 300:700] = False         # empty key tiles for some query tiles (tile skipping)
         mask[400:, :200] = False
     mask[np.arange(n), np.arange(n)] = True
