@@ -147,10 +147,10 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
           tma_load_2d(slot_smem + slot * C::SLOT_BYTES + c * (TK * 128), &qkv_map, slot_full(slot), col + 64 * c, kv * TK);
         if (++slot == C::NSLOT) { slot = 0; phase ^= 1u; }
       };
-      // consumption order: K_0, K_1, V_0, K_2, V_1, ..., K_{T-1}, V_{T-2}, V_{T-1}
+      // consumption order: K_0, K_1, then per tile t: K_{t+2}, V_t
+      for (int t = 0; t < 2 && t < T; ++t) load_tile(k_col, __ldg(p.tile_kv + t_beg + t));
       for (int t = 0; t < T; ++t) {
-        if (t == 0) load_tile(k_col, __ldg(p.tile_kv + t_beg));
-        if (t + 1 < T) load_tile(k_col, __ldg(p.tile_kv + t_beg + t + 1));
+        if (t + 2 < T) load_tile(k_col, __ldg(p.tile_kv + t_beg + t + 2));
         load_tile(v_col, __ldg(p.tile_kv + t_beg + t));
       }
     }
@@ -182,9 +182,11 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
         ++g;
       };
       mbar_wait(q_full, 0);
+      // S runs two tiles ahead of PV: the softmax group releases its S buffer as soon as its last
+      // read is in registers, so S(t+2) is formed under the tail of softmax(t)
+      for (int t = 0; t < 2 && t < T; ++t) issue_s();
       for (int t = 0; t < T; ++t) {
-        if (t == 0) issue_s();
-        if (t + 1 < T) issue_s();
+        if (t + 2 < T) issue_s();
         const int pb = t % C::NPBUF;
         mbar_wait(slot_full(slot), slot_phase);
         GC_TRACE(2, 2 * t);
@@ -232,17 +234,24 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
       mbar_wait(s_full(grp), use & 1);
       if (threadIdx.x == 64) GC_TRACE(3, 2 * t + 1);
       tc_fence_after();
-      // (a) masked maximum of the row over this tile
+      // (a) masked maximum of the row over this tile; the tcgen05.ld of the next sub-block is in
+      // flight while the current one is reduced
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      {
+        uint32_t nx[32];
+        tmem_ld_32x32b_x32(s_addr, nx);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (live[c]) {
+        for (int c = 0; c < 4; ++c) {
           uint32_t v[32];
-          tmem_ld_32x32b_x32(s_addr + c * 32, v);
           tc_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            mx[i & 3] = fmaxf(mx[i & 3], (mw[c] & (1u << i)) ? __uint_as_float(v[i]) : -INFINITY);
+          for (int i = 0; i < 32; ++i) v[i] = nx[i];
+          if (c < 3) tmem_ld_32x32b_x32(s_addr + (c + 1) * 32, nx);
+          if (live[c]) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              mx[i & 3] = fmaxf(mx[i & 3], (mw[c] & (1u << i)) ? __uint_as_float(v[i]) : -INFINITY);
+          }
         }
       }
       const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
@@ -279,45 +288,55 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
       }
       const float offset = (m == -INFINITY) ? 0.0f : m * c2;
       // (b) P = exp2(S c - offset) on the live sub-blocks, zeros elsewhere -> swizzled K-major operand
+      {
+        uint32_t nx[32];
+        tmem_ld_32x32b_x32(s_addr, nx);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t packed[16];
-        if (live[c]) {
+        for (int c = 0; c < 4; ++c) {
           uint32_t v[32];
-          tmem_ld_32x32b_x32(s_addr + c * 32, v);
           tc_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float e0, e1;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(v[i]), c2, -offset)));
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(v[i + 1]), c2, -offset)));
-            const float p0 = (mw[c] & (1u << i)) ? e0 : 0.0f;
-            const float p1 = (mw[c] & (1u << (i + 1))) ? e1 : 0.0f;
-            ls[(i >> 1) & 3] += p0 + p1;
-            const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-            packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+          for (int i = 0; i < 32; ++i) v[i] = nx[i];
+          if (c < 3) {
+            tmem_ld_32x32b_x32(s_addr + (c + 1) * 32, nx);
+          } else {
+            // last read of S is in registers: hand the buffer back before the remaining arithmetic
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free(grp));
           }
-        } else {
+          uint32_t packed[16];
+          if (live[c]) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) packed[i] = 0u;
-        }
-        // keys 32c .. 32c+31 -> 64-key chunk (c >> 1), 16-byte units (c & 1) * 4 + u, swizzled by row
-        const uint32_t chunk_base = p_row + (c >> 1) * (TQ * 128);
+            for (int i = 0; i < 32; i += 2) {
+              float e0, e1;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(v[i]), c2, -offset)));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(v[i + 1]), c2, -offset)));
+              const float p0 = (mw[c] & (1u << i)) ? e0 : 0.0f;
+              const float p1 = (mw[c] & (1u << (i + 1))) ? e1 : 0.0f;
+              ls[(i >> 1) & 3] += p0 + p1;
+              const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+              packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+          } else {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t unit = static_cast<uint32_t>((c & 1) * 4 + u) ^ static_cast<uint32_t>(r & 7);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(chunk_base + unit * 16), "r"(packed[4 * u]),
-                       "r"(packed[4 * u + 1]), "r"(packed[4 * u + 2]), "r"(packed[4 * u + 3])
-                       : "memory");
+            for (int i = 0; i < 16; ++i) packed[i] = 0u;
+          }
+          // keys 32c .. 32c+31 -> 64-key chunk (c >> 1), 16-byte units (c & 1) * 4 + u, swizzled by row
+          const uint32_t chunk_base = p_row + (c >> 1) * (TQ * 128);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t unit = static_cast<uint32_t>((c & 1) * 4 + u) ^ static_cast<uint32_t>(r & 7);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(chunk_base + unit * 16), "r"(packed[4 * u]),
+                         "r"(packed[4 * u + 1]), "r"(packed[4 * u + 2]), "r"(packed[4 * u + 3])
+                         : "memory");
+          }
         }
       }
       tc_fence_before();
       fence_proxy_async_smem();       // generic-proxy stores of P -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(s_free(grp));
-        mbar_arrive(p_full(grp));
-      }
+      if (lane == 0) mbar_arrive(p_full(grp));
     }
     // ---- merge the two streams: every thread publishes (m, l) of its row
     const float l_own = (ls[0] + ls[1]) + (ls[2] + ls[3]);

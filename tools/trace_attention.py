@@ -36,9 +36,9 @@ T = int(tp[1] - tp[0])
 t0 = t[t > 0].min()
 rel = lambda x: (x - t0) if x > 0 else -1
 print(f"{name}: CTA 0 has T={T} key tiles; times in cycles since first event")
-print("TMA issue (after slot free):", [rel(x) for x in t[0][: 3 * T]])
-print("MMA S  (K ready, S buffer free):", [(rel(t[1][2 * i]), rel(t[1][2 * i + 1])) for i in range(2 * T)])
+print("TMA issue (after slot free):", [rel(x) for x in t[0][: 2 * T]])
+print("MMA S  (K ready, S buffer free):", [(rel(t[1][2 * i]), rel(t[1][2 * i + 1])) for i in range(T)])
 print("MMA PV (V ready, P ready):", [(rel(t[2][2 * i]), rel(t[2][2 * i + 1])) for i in range(T)])
-print("softmax w2 (wait S start, S arrived):", [(rel(t[3][2 * i]), rel(t[3][2 * i + 1])) for i in range(2 * T)])
-print("softmax w2 pass2 P buffer free:", [rel(t[4][T + i]) for i in range(T)])
+print("softmax warp 2 (group 0; wait S start, S arrived, P buffer free) per even tile:",
+      [(rel(t[3][2 * i]), rel(t[3][2 * i + 1]), rel(t[4][i])) for i in range(0, T, 2)])
 print("epilogue wait O (start, arrived):", rel(t[5][0]), rel(t[5][1]))
