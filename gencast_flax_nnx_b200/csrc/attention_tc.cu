@@ -222,9 +222,12 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
     const uint32_t p_row = p_smem + grp * C::P_BYTES + r * 128;
     float m = -INFINITY;                               // running offset (raw logit units)
     float ls[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    uint4 mk_next = make_uint4(0u, 0u, 0u, 0u);
+    if (grp < T) mk_next = __ldg(p.tile_mask + static_cast<int64_t>(t_beg + grp) * TQ + r);
     for (int t = grp; t < T; t += 2) {
       const int use = t >> 1;                          // how many times this group's buffers were used before
-      const uint4 mk = __ldg(p.tile_mask + static_cast<int64_t>(t_beg + t) * TQ + r);
+      const uint4 mk = mk_next;                        // mask rows are fetched one tile ahead
+      if (t + 2 < T) mk_next = __ldg(p.tile_mask + static_cast<int64_t>(t_beg + t + 2) * TQ + r);
       const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
       // 32 x 32 sub-blocks without any neighbour are skipped (warp-uniform)
       bool live[4];
@@ -266,9 +269,12 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
         m = m_new;                                     // nothing accumulated yet
       } else {
         // raise the offset only when the stale one would let exponentials grow past 2^8
-        const bool need = m_new * c2 > m * c2 + 8.0f;      // false when m_new == m (incl. both -inf)
+        // (a row that has not met a neighbour yet, m = -inf, has l = 0 and a zero row of O: it just
+        // adopts the new offset)
+        if (m == -INFINITY) m = m_new;
+        const bool need = m_new * c2 > m * c2 + 8.0f;      // false when m_new == m
         if (__any_sync(0xffffffffu, need)) {
-          const float alpha = need ? exp2f(m * c2 - m_new * c2) : 1.0f;   // m = -inf -> 0
+          const float alpha = need ? exp2f(m * c2 - m_new * c2) : 1.0f;
           if (need) {
             m = m_new;
 #pragma unroll
