@@ -75,6 +75,7 @@ template <int D>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttParams p) {
   using namespace sm100;
+  pdl_launch_dependents();     // let the next kernel's launch and prologue overlap this one
   using C = AttCfg<D>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -119,7 +120,6 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
-  pdl_launch_dependents();
   pdl_wait();                                    // everything below may read what a predecessor wrote
   const int t_beg = __ldg(p.tile_ptr + qt);
   const int T = __ldg(p.tile_ptr + qt + 1) - t_beg;

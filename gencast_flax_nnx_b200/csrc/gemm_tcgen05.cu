@@ -56,6 +56,7 @@ template <int BN, int NSTAGES>
 __global__ void __launch_bounds__(NUM_THREADS, NSTAGES > 4 ? 1 : 2)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shape, const EpilogueParams ep) {
   using namespace sm100;
+  pdl_launch_dependents();     // let the next kernel's launch and prologue overlap this one
   using C = GemmCfg<BN, NSTAGES>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -95,7 +96,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmShape 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_launch_dependents();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shape, const EpilogueParams ep,
                                     const int num_tiles) {
   using namespace sm100;
+  pdl_launch_dependents();     // let the next kernel's launch and prologue overlap this one
   using C = PersistCfg<PBN>;
   constexpr int PSTAGES = C::STAGES;
   constexpr int HALF = PBN / 2;                 // columns per epilogue warp
@@ -238,7 +239,6 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_launch_dependents();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 

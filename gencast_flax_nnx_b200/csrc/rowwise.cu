@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) ln_cond_kernel(const void* __restrict__ x
 // LayerNorm reduction, and the scale / offset vectors live in shared memory to keep
 // the register budget for those in-flight rows.
 constexpr int SEG_WARPS = 8;
-constexpr int HEAVY = 96;
+constexpr int HEAVY = 32;
 constexpr int SEG_UNROLL = 4;
 
 template <int NV>
@@ -149,9 +149,11 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) ln_cond_segment_sum_kernel(
     }
   };
 
-  for (int64_t seg0 = static_cast<int64_t>(blockIdx.x) * SEG_WARPS; seg0 < num_segments;
-       seg0 += static_cast<int64_t>(gridDim.x) * SEG_WARPS) {
-    const int64_t seg = seg0 + warp;
+  // Segment -> (block, warp) mapping: the eight segments a block handles in one iteration are gridDim
+  // apart, not consecutive.  High in-degree receivers cluster spatially (the mesh nodes around the
+  // poles), hence in index space after the patch relabelling; striding spreads them over all blocks.
+  for (int64_t base = blockIdx.x; base < num_segments; base += static_cast<int64_t>(gridDim.x) * SEG_WARPS) {
+    const int64_t seg = base + static_cast<int64_t>(warp) * gridDim.x;
     int is_heavy = 0;
     if (seg < num_segments) {
       const int beg = __ldg(row_ptr + seg), end = __ldg(row_ptr + seg + 1);
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) ln_cond_segment_sum_kernel(
     __syncthreads();
     for (int w = 0; w < SEG_WARPS; ++w) {
       if (!heavy_seg[w]) continue;            // block-uniform
-      const int64_t hseg = seg0 + w;
+      const int64_t hseg = base + static_cast<int64_t>(w) * gridDim.x;
       const int beg = __ldg(row_ptr + hseg), end = __ldg(row_ptr + hseg + 1);
       const int per = (end - beg + SEG_WARPS - 1) / SEG_WARPS;
       const int b = min(beg + warp * per, end), e = min(b + per, end);
