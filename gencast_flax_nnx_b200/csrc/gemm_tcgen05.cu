@@ -15,12 +15,21 @@
 // The K dimension may be split in up to three (A_s, W_s) segments: this is how the
 // [e | sender | receiver] and [node | aggregate] concatenations of the reference
 // (common/typed_graph_net.py:301-305, :315-326) are consumed without being built.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
 namespace gc {
 
+long long* g_gemm_trace = nullptr;   // debug: clock stamps of CTA 0 of the persistent kernel (null in normal use)
+
 namespace {
+
+#define GC_GTRACE(role, index)                                                                          \
+  do {                                                                                                  \
+    if (trace != nullptr && blockIdx.x == 0 && (index) < 512) trace[(role) * 512 + (index)] = clock64(); \
+  } while (0)
 
 constexpr int BM = 128;
 constexpr int BK = 64;
@@ -44,13 +53,130 @@ struct GemmCfg {
 struct GemmMaps {
   CUtensorMap a[GC_MAX_SEGMENTS];
   CUtensorMap w[GC_MAX_SEGMENTS];
+  CUtensorMap out;                 // only valid when shape.store_mode != STORE_DIRECT
 };
+
+// How the persistent kernels write their tiles.
+//   STORE_DIRECT  each thread stores its own row segments (general fused epilogue: addend, gathers, ...)
+//   STORE_TMA     bias / activation only: rows are staged in shared memory (128-byte swizzle) and
+//                 written with cp.async.bulk.tensor, i.e. as full lines instead of 32 partial lines
+//                 per instruction
+//   STORE_TMA_ADD fp32 output that is also the residual (x = x + A W^T + b): same staging, written
+//                 with cp.reduce.async.bulk.tensor .add, so the residual is never read by the SM
+constexpr int STORE_DIRECT = 0;
+constexpr int STORE_TMA = 1;
+constexpr int STORE_TMA_ADD = 2;
 
 struct GemmShape {
   int kblocks[GC_MAX_SEGMENTS];
   int num_segments;
   int n_tiles;
+  int store_mode;
 };
+
+// Epilogue of one warp for one accumulator buffer: 32 rows (its TMEM lane quarter) x HALF columns.
+// `release` is called once, as soon as the last tcgen05.ld of the buffer has landed in registers.
+// stage_smem: this warp's two 4 KB staging buffers (1024-byte aligned) for the TMA store modes.
+template <int HALF, typename Release>
+__device__ __forceinline__ void epilogue_warp_tile(const EpilogueParams& ep, const CUtensorMap* out_map, int store_mode,
+                                                   float alpha, uint32_t taddr, const float* bias_ptr, int64_t row0,
+                                                   int col_base, int lane, uint32_t stage_smem, int& stage_use,
+                                                   Release release) {
+  using namespace sm100;
+  const int64_t row = row0 + lane;
+  uint32_t r[32];
+  tmem_ld_32x32b_x32(taddr, r);
+#pragma unroll
+  for (int c = 0; c < HALF; c += 32) {
+    float v[32];
+    tc_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    if (c + 32 < HALF) {
+      tmem_ld_32x32b_x32(taddr + c + 32, r);
+    } else {
+      tc_fence_before();
+      __syncwarp();
+      release();
+    }
+    if (store_mode == STORE_DIRECT) {
+      if (row < ep.m) epilogue_row_segment<32, true>(ep, alpha, row, col_base + c, v, bias_ptr ? bias_ptr + c : nullptr);
+      continue;
+    }
+    // ---- staged path: bias / activation in registers
+    if (ep.alpha_dev != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] *= alpha;
+    }
+    if (bias_ptr != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = reinterpret_cast<const float4*>(bias_ptr + c)[i];
+        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    }
+    if (ep.act == GC_ACT_SWISH) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = swish_fast(v[i]);
+    } else if (ep.act == GC_ACT_GELU_TANH) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_fast(v[i]);
+    }
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
+    if (ep.out_dtype == GC_BF16) {
+      // 32 bf16 = 64 B = units (c/32 & 1) * 4 .. + 3 of this row in a 64-column chunk
+      const int half_chunk = (c >> 5) & 1;
+      if (half_chunk == 0) {
+        // first half of a new chunk: the buffer's previous store must have finished reading it
+        if (lane == 0) bulk_wait_group_read<1>();
+        __syncwarp();
+      }
+      const uint32_t buf = stage_smem + static_cast<uint32_t>(stage_use & 1) * 4096u + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * u + 2 * j], v[8 * u + 2 * j + 1]);
+          pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        const uint32_t unit = static_cast<uint32_t>(half_chunk * 4 + u) ^ sw;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + unit * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                     "r"(pk[3]) : "memory");
+      }
+      if (half_chunk == 1 || c + 32 >= HALF) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(out_map, stage_smem + static_cast<uint32_t>(stage_use & 1) * 4096u, col_base + (c & ~63), static_cast<int>(row0));
+          bulk_commit_group();
+        }
+        ++stage_use;
+      }
+    } else {
+      // 32 fp32 = 128 B = one full row of a 32-column chunk
+      if (lane == 0) bulk_wait_group_read<1>();
+      __syncwarp();
+      const uint32_t buf = stage_smem + static_cast<uint32_t>(stage_use & 1) * 4096u + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t unit = static_cast<uint32_t>(u) ^ sw;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + unit * 16), "r"(__float_as_uint(v[4 * u])),
+                     "r"(__float_as_uint(v[4 * u + 1])), "r"(__float_as_uint(v[4 * u + 2])), "r"(__float_as_uint(v[4 * u + 3]))
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t src = stage_smem + static_cast<uint32_t>(stage_use & 1) * 4096u;
+        if (store_mode == STORE_TMA_ADD) tma_reduce_add_2d(out_map, src, col_base + c, static_cast<int>(row0));
+        else tma_store_2d(out_map, src, col_base + c, static_cast<int>(row0));
+        bulk_commit_group();
+      }
+      ++stage_use;
+    }
+  }
+}
 
 template <int BN, int NSTAGES>
 __global__ void __launch_bounds__(NUM_THREADS, NSTAGES > 4 ? 1 : 2)
@@ -183,10 +309,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmShape 
 // ---------------------------------------------------------------------------------------------
 template <int PBN>
 struct PersistCfg {
-  static constexpr int STAGES = PBN == 256 ? 4 : 6;
+  static constexpr int STAGES = PBN == 256 ? 3 : 4;
   static constexpr int B_STAGE_BYTES = PBN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;        // 8 warps x 2 x 4 KB store staging
+  static constexpr int BAR_OFFSET = STAGING_OFFSET + 8 * 8192;
   static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;
   static constexpr int SMEM_BYTES = BIAS_OFFSET + 2 * PBN * 4 + 1024;
 };
@@ -195,7 +322,7 @@ constexpr int P_THREADS = 320;
 template <int PBN>
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shape, const EpilogueParams ep,
-                                    const int num_tiles) {
+                                    const int num_tiles, long long* trace) {
   using namespace sm100;
   pdl_launch_dependents();     // let the next kernel's launch and prologue overlap this one
   using C = PersistCfg<PBN>;
@@ -247,11 +374,13 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const
       pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
+      int ev = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_blk = tile % shape.n_tiles, m_blk = tile / shape.n_tiles;
         for (int s = 0; s < shape.num_segments; ++s) {
           for (int kb = 0; kb < shape.kblocks[s]; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
+            GC_GTRACE(0, ev); ++ev;
             mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
             tma_load_2d(smem_a + stage * A_STAGE_BYTES, &maps.a[s], full_bar(stage), kb * BK, m_blk * BM);
             // W box is 128 rows: two boxes for a 256-wide tile
@@ -272,7 +401,9 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const
       int lt = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const int b = lt & 1;
+        GC_GTRACE(1, 4 * lt);
         mbar_wait(acc_empty(b), ((lt >> 1) & 1) ^ 1u);      // epilogue has drained this accumulator buffer
+        GC_GTRACE(1, 4 * lt + 1);
         tc_fence_after();
         uint32_t accumulate = 0;
         for (int s = 0; s < shape.num_segments; ++s) {
@@ -291,6 +422,7 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const
           }
         }
         umma_commit(acc_full(b));
+        GC_GTRACE(1, 4 * lt + 2);
       }
     }
   } else {
@@ -300,6 +432,8 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     pdl_wait();
     const float alpha = ep.alpha_dev != nullptr ? __ldg(ep.alpha_dev) : 1.0f;
+    const uint32_t stage_smem = smem_base + C::STAGING_OFFSET + static_cast<uint32_t>(warp - 2) * 8192u;
+    int stage_use = 0;
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int n_blk = tile % shape.n_tiles, m_blk = tile / shape.n_tiles;
@@ -308,34 +442,175 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const
       if (et < PBN) bias_s[b * PBN + et] = ep.bias != nullptr ? __ldg(ep.bias + n_blk * PBN + et) : 0.0f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const float* bias_ptr = ep.bias != nullptr ? bias_s + b * PBN + half * HALF : nullptr;
-      const int64_t row = static_cast<int64_t>(m_blk) * BM + q * 32 + lane;
       const int col_base = n_blk * PBN + half * HALF;
       const uint32_t taddr = tmem_base + b * PBN + half * HALF + lane_addr;
+      if (threadIdx.x == 64) GC_GTRACE(2, 4 * lt);
       mbar_wait(acc_full(b), (lt >> 1) & 1);
+      if (threadIdx.x == 64) GC_GTRACE(2, 4 * lt + 1);
       tc_fence_after();
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(taddr, r);
-#pragma unroll
-      for (int c = 0; c < HALF; c += 32) {
-        float v[32];
-        tc_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (c + 32 < HALF) {
-          tmem_ld_32x32b_x32(taddr + c + 32, r);
-        } else {
-          // last read of this buffer is in registers: hand it back to the MMA warp before the math
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty(b));
-        }
-        if (row < ep.m) epilogue_row_segment<32, true>(ep, alpha, row, col_base + c, v, bias_ptr ? bias_ptr + c : nullptr);
-      }
+      const uint32_t acc_bar = acc_empty(b);
+      epilogue_warp_tile<HALF>(ep, &maps.out, shape.store_mode, alpha, taddr, bias_ptr,
+                               static_cast<int64_t>(m_blk) * BM + q * 32, col_base, lane, stage_smem, stage_use,
+                               [&]() { if (lane == 0) mbar_arrive(acc_bar); });
+      if (threadIdx.x == 64) GC_GTRACE(2, 4 * lt + 2);
     }
+    if (lane == 0) bulk_wait_group_all();        // staged stores have landed before the grid completes
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 2 * PBN);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05.mma.cta_group::2) for the large problems: a cluster of two CTAs owns a
+// 256 x 256 output tile.  Each CTA stages its 128 rows of A and its 128-row half of the W tile,
+// the leader issues M = 256 MMAs that read both halves, each CTA's TMEM receives its 128 x 256
+// slice.  Per SM this halves the W bytes pulled from L2 per FLOP (32 KB per k-block for 128 x 256
+// outputs instead of 48 KB), which is what bounds the single-CTA kernels.  Same persistent loop,
+// double-buffered accumulator and eight epilogue warps per CTA as above.
+// ---------------------------------------------------------------------------------------------
+constexpr int QBN = 256;                        // tile width (both CTAs)
+constexpr int Q_STAGES = 4;
+constexpr int Q_B_STAGE_BYTES = 128 * BK * 2;   // this CTA's half of the W tile
+constexpr int Q_STAGE_BYTES = A_STAGE_BYTES + Q_B_STAGE_BYTES;
+constexpr int Q_STAGING_OFFSET = Q_STAGES * Q_STAGE_BYTES;           // 8 warps x 2 x 4 KB store staging
+constexpr int Q_BAR_OFFSET = Q_STAGING_OFFSET + 8 * 8192;
+constexpr int Q_BIAS_OFFSET = Q_BAR_OFFSET + 256;
+constexpr int Q_SMEM_BYTES = Q_BIAS_OFFSET + 2 * QBN * 4 + 1024;
+
+__global__ void __launch_bounds__(P_THREADS, 1)
+gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shape, const EpilogueParams ep,
+                              const int num_tiles) {
+  using namespace sm100;
+  pdl_launch_dependents();
+  constexpr int HALF = QBN / 2;                 // columns per epilogue warp
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + Q_STAGES * A_STAGE_BYTES;
+  const uint32_t bars = smem_base + Q_BAR_OFFSET;
+  float* bias_s = reinterpret_cast<float*>(smem_gen + Q_BIAS_OFFSET);      // [2][QBN]
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (Q_STAGES + s); };
+  auto acc_full = [&](int b) { return bars + 8u * (2 * Q_STAGES + b); };
+  auto acc_empty = [&](int b) { return bars + 8u * (2 * Q_STAGES + 2 + b); };
+  const uint32_t tmem_ptr_smem = bars + 8u * (2 * Q_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();      // 0 = leader
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < shape.num_segments; ++s) {
+      prefetch_tensormap(&maps.a[s]);
+      prefetch_tensormap(&maps.w[s]);
+    }
+    for (int s = 0; s < Q_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);                // leader's is the one that counts: 1 arrive + both CTAs' bytes
+      mbar_init(empty_bar(s), 1);               // one multicast commit from the leader
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);                // multicast commit from the leader
+      mbar_init(acc_empty(b), 16);              // 8 epilogue warps of each CTA (leader's copy is used)
+    }
+    fence_mbar_init();
+  }
+  __syncwarp();
+  cluster_sync_all();                           // both CTAs' barriers exist before anything remote happens
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_ptr_smem, 2 * QBN);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      pdl_wait();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        const int n_blk = tile % shape.n_tiles, m_pair = tile / shape.n_tiles;
+        const int m_row = m_pair * 256 + static_cast<int>(rank) * 128;
+        const int n_row = n_blk * QBN + static_cast<int>(rank) * 128;
+        for (int s = 0; s < shape.num_segments; ++s) {
+          for (int kb = 0; kb < shape.kblocks[s]; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            // the leader arms its barrier for the bytes of both CTAs
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Q_STAGE_BYTES);
+            tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &maps.a[s], full_bar(stage), kb * BK, m_row);
+            tma_load_2d_pair(smem_b + stage * Q_B_STAGE_BYTES, &maps.w[s], full_bar(stage), kb * BK, n_row);
+            if (++stage == Q_STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = idesc_bf16_f32(256, QBN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int lt = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++lt) {
+        const int b = lt & 1;
+        mbar_wait(acc_empty(b), ((lt >> 1) & 1) ^ 1u);      // both CTAs' epilogues have drained this buffer
+        tc_fence_after();
+        uint32_t accumulate = 0;
+        for (int s = 0; s < shape.num_segments; ++s) {
+          for (int kb = 0; kb < shape.kblocks[s]; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint64_t da = desc_kmajor_sw128(smem_a + stage * A_STAGE_BYTES);
+            const uint64_t db = desc_kmajor_sw128(smem_b + stage * Q_B_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              umma_f16_pair(tmem_base + b * QBN, da + 2u * k, db + 2u * k, idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit_pair(empty_bar(stage));               // frees the stage in both CTAs
+            if (++stage == Q_STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+        umma_commit_pair(acc_full(b));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;             // 0..255 within the epilogue group
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    pdl_wait();
+    const float alpha = ep.alpha_dev != nullptr ? __ldg(ep.alpha_dev) : 1.0f;
+    const uint32_t stage_smem = smem_base + Q_STAGING_OFFSET + static_cast<uint32_t>(warp - 2) * 8192u;
+    int stage_use = 0;
+    int lt = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++lt) {
+      const int n_blk = tile % shape.n_tiles, m_pair = tile / shape.n_tiles;
+      const int b = lt & 1;
+      if (et < QBN) bias_s[b * QBN + et] = ep.bias != nullptr ? __ldg(ep.bias + n_blk * QBN + et) : 0.0f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float* bias_ptr = ep.bias != nullptr ? bias_s + b * QBN + half * HALF : nullptr;
+      const int col_base = n_blk * QBN + half * HALF;
+      const uint32_t taddr = tmem_base + b * QBN + half * HALF + lane_addr;
+      mbar_wait(acc_full(b), (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc_bar = acc_empty(b);
+      epilogue_warp_tile<HALF>(ep, &maps.out, shape.store_mode, alpha, taddr, bias_ptr,
+                               static_cast<int64_t>(m_pair) * 256 + rank * 128 + q * 32, col_base, lane, stage_smem, stage_use,
+                               [&]() { if (lane == 0) mbar_arrive_cluster(acc_bar, 0); });
+    }
+    if (lane == 0) bulk_wait_group_all();
+  }
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();                           // the peer may still be signalling / reading this CTA
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 2 * QBN);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -377,12 +652,35 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return GC_OK;
 }
 
+int make_tmap_out_2d(CUtensorMap* out, void* base, int dtype, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return GC_ERR_CUDA;
+  }
+  const uint64_t esize = dtype == GC_BF16 ? 2 : 4;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * esize};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esize), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, dtype == GC_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(out) failed with CUresult %d (rows=%llu cols=%llu ld=%llu)", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+    return GC_ERR_CUDA;
+  }
+  return GC_OK;
+}
+
 template <int BN, int NSTAGES>
 int launch_cfg(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
   using C = GemmCfg<BN, NSTAGES>;
   GemmMaps maps;
   GemmShape shape;
   shape.num_segments = a.num_segments;
+  shape.store_mode = STORE_DIRECT;
   shape.n_tiles = a.n / BN;
   for (int s = 0; s < GC_MAX_SEGMENTS; ++s) shape.kblocks[s] = 0;
   for (int s = 0; s < a.num_segments; ++s) {
@@ -409,6 +707,8 @@ int launch_cfg(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams&
   return GC_OK;
 }
 
+int fill_out_map(GemmMaps& maps, GemmShape& shape, const gc_gemm_args& a);
+
 template <int PBN>
 int launch_persistent(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
   using C = PersistCfg<PBN>;
@@ -428,6 +728,10 @@ int launch_persistent(cudaStream_t stream, const gc_gemm_args& a, const Epilogue
     maps.a[s] = maps.a[0];
     maps.w[s] = maps.w[0];
   }
+  {
+    const int rc = fill_out_map(maps, shape, a);
+    if (rc != GC_OK) return rc;
+  }
   GC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_persistent_kernel<PBN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::SMEM_BYTES), "cudaFuncSetAttribute(gemm_bf16_tcgen05_persistent_kernel)");
   const int64_t num_tiles = ((a.m + BM - 1) / BM) * shape.n_tiles;
@@ -439,8 +743,78 @@ int launch_persistent(cudaStream_t stream, const gc_gemm_args& a, const Epilogue
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)(num_tiles < sms ? num_tiles : sms);
   GC_CHECK_CUDA(launch_kernel(gemm_bf16_tcgen05_persistent_kernel<PBN>, dim3(grid), dim3(P_THREADS), (size_t)C::SMEM_BYTES,
-                              stream, maps, shape, ep, (int)num_tiles), "gemm_bf16_tcgen05_persistent_kernel");
+                              stream, maps, shape, ep, (int)num_tiles, g_gemm_trace), "gemm_bf16_tcgen05_persistent_kernel");
   return GC_OK;
+}
+
+bool pair_kernel_enabled() {
+  static const bool on = []() {
+    const char* v = getenv("GENCAST_GEMM_PAIR");
+    return !(v != nullptr && v[0] == '0');
+  }();
+  return on;
+}
+
+int launch_pair(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
+  GemmMaps maps;
+  GemmShape shape;
+  shape.num_segments = a.num_segments;
+  shape.n_tiles = a.n / QBN;
+  for (int s = 0; s < GC_MAX_SEGMENTS; ++s) shape.kblocks[s] = 0;
+  for (int s = 0; s < a.num_segments; ++s) {
+    shape.kblocks[s] = a.k[s] / BK;
+    int rc = make_tmap_bf16_2d(&maps.a[s], a.a[s], (uint64_t)a.m, (uint64_t)a.k[s], (uint64_t)a.lda[s], BK, BM);
+    if (rc != GC_OK) return rc;
+    rc = make_tmap_bf16_2d(&maps.w[s], a.w[s], (uint64_t)a.n, (uint64_t)a.k[s], (uint64_t)a.ldw[s], BK, 128);
+    if (rc != GC_OK) return rc;
+  }
+  for (int s = a.num_segments; s < GC_MAX_SEGMENTS; ++s) {
+    maps.a[s] = maps.a[0];
+    maps.w[s] = maps.w[0];
+  }
+  {
+    const int rc = fill_out_map(maps, shape, a);
+    if (rc != GC_OK) return rc;
+  }
+  GC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES),
+                "cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel)");
+  const int64_t num_tiles = ((a.m + 255) / 256) * shape.n_tiles;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t pairs = sms / 2;
+  if (num_tiles < pairs) pairs = num_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(P_THREADS);
+  cfg.dynamicSmemBytes = Q_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  GC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_pair_kernel, maps, shape, ep, (int)num_tiles),
+                "gemm_bf16_tcgen05_pair_kernel");
+  return GC_OK;
+}
+
+// STORE_TMA / STORE_TMA_ADD when the fused epilogue is bias + activation (+ in-place fp32 residual) only.
+int choose_store_mode(const gc_gemm_args& a) {
+  if (a.addend != nullptr || a.gather_src[0] != nullptr || a.gather_src[1] != nullptr) return STORE_DIRECT;
+  if (a.residual == nullptr) return STORE_TMA;
+  if (a.residual == a.out && a.res_dtype == GC_F32 && a.out_dtype == GC_F32 && a.ld_res == a.ldo) return STORE_TMA_ADD;
+  return STORE_DIRECT;
+}
+
+int fill_out_map(GemmMaps& maps, GemmShape& shape, const gc_gemm_args& a) {
+  shape.store_mode = choose_store_mode(a);
+  if (shape.store_mode == STORE_DIRECT) {
+    maps.out = maps.a[0];
+    return GC_OK;
+  }
+  return make_tmap_out_2d(&maps.out, a.out, a.out_dtype, (uint64_t)a.m, (uint64_t)a.n, (uint64_t)a.ldo, 32);
 }
 
 int launch_gemm_tcgen05(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
@@ -448,7 +822,10 @@ int launch_gemm_tcgen05(cudaStream_t stream, const gc_gemm_args& a, const Epilog
   const int64_t tiles128 = ((a.m + BM - 1) / BM) * (a.n / 128);
   if (tiles128 >= 2 * 148) {
     // 256-wide tiles when N allows it and there are still >= 2 tiles per SM
-    if (a.n % 256 == 0 && tiles128 >= 4 * 148) return launch_persistent<256>(stream, a, ep);
+    if (a.n % 256 == 0 && tiles128 >= 4 * 148) {
+      if (pair_kernel_enabled()) return launch_pair(stream, a, ep);
+      return launch_persistent<256>(stream, a, ep);
+    }
     return launch_persistent<128>(stream, a, ep);
   }
   // One CTA per SM at most: a deep ring (8 x 24 KB in flight) keeps the per-SM L2 link busy
@@ -458,3 +835,8 @@ int launch_gemm_tcgen05(cudaStream_t stream, const gc_gemm_args& a, const Epilog
 }
 
 }  // namespace gc
+
+// Debug hook (not part of the public header): clock-stamp buffer of at least 3 * 512 int64.
+extern "C" __attribute__((visibility("default"))) void gc_debug_set_gemm_trace(void* ptr) {
+  gc::g_gemm_trace = reinterpret_cast<long long*>(ptr);
+}

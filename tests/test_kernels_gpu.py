@@ -74,6 +74,34 @@ def test_gemm_fused_epilogue(cuda_device, dtype, act):
         assert _rel(out.cpu(), ref) < tol
 
 
+@pytest.mark.parametrize("m,n,k", [(40000, 512, 256), (40000, 128, 128), (9000, 2048, 256), (5000, 1536, 128)])
+def test_gemm_large_staged_store_paths(cuda_device, m, n, k):
+    """Large problems take the persistent / CTA-pair kernels whose bias+activation epilogues are staged
+    in shared memory and written with TMA stores (bf16 and fp32), and whose in-place fp32 residual
+    update is a TMA reduce-add."""
+    from gencast_flax_nnx_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(n + k)
+    a = torch.randn(m, k, generator=g).to(torch.bfloat16)
+    w = (torch.randn(n, k, generator=g) / math.sqrt(k)).to(torch.bfloat16)
+    bias = torch.randn(n, generator=g)
+    d = cuda_device
+    ref = a.double() @ w.double().t() + bias.double()
+    out = torch.full((m, n), float("nan"), dtype=torch.bfloat16, device=d)
+    ops.gemm([(a.to(d), w.to(d))], out, bias=bias.to(d), act="gelu_tanh")
+    assert _rel(out.cpu(), _gelu_tanh(ref)) < 1e-2
+    out32 = torch.full((m, n), float("nan"), dtype=torch.float32, device=d)
+    ops.gemm([(a.to(d), w.to(d))], out32, bias=bias.to(d), act="swish")
+    assert _rel(out32.cpu(), _swish(ref)) < 3e-3          # MUFU tanh in the bf16-path activations
+    x0 = torch.randn(m, n, generator=g)
+    x = x0.to(d).clone()
+    ops.gemm([(a.to(d), w.to(d))], x, bias=bias.to(d), residual=x)      # x += a @ w^T + b, in place
+    assert _rel(x.cpu(), ref + x0.double()) < 3e-5
+    # view with a leading dimension larger than n
+    big = torch.zeros(m, n + 64, dtype=torch.bfloat16, device=d)
+    ops.gemm([(a.to(d), w.to(d))], big[:, :n], bias=bias.to(d))
+    assert _rel(big[:, :n].cpu(), ref) < 1e-2 and torch.all(big[:, n:] == 0)
+
+
 @pytest.mark.parametrize("cols", [128, 256, 512])
 @pytest.mark.parametrize("in_dtype,out_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
                                                 (torch.bfloat16, torch.float32)])
