@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from . import stacking
+from .device_stacking import DeviceStacker
 from .configs import DenoiserArchitectureConfig, NoiseEncoderConfig
 from .engine import ChannelLayout, DenoiserEngine
 from .graph import build_denoiser_graphs
@@ -43,6 +44,7 @@ class Denoiser:
         self._param_init = param_init
         self._engine: Optional[DenoiserEngine] = None
         self._grid_key = None
+        self._stacker: Optional[DeviceStacker] = None
 
     # -- lazy construction, as in DenoiserArchitecture._maybe_init (denoiser.py:343-416)
     def _maybe_init(self, inputs: Dataset, noisy_targets: Dataset, forcings: Optional[Dataset]) -> DenoiserEngine:
@@ -84,11 +86,16 @@ class Denoiser:
     def params(self) -> Dict[str, np.ndarray]:
         return self._params
 
+    @property
+    def stacker(self) -> DeviceStacker:
+        if self._stacker is None:
+            self._stacker = DeviceStacker(self.engine.device)
+        return self._stacker
+
     def stack_constants(self, inputs: Dataset, forcings: Optional[Dataset], sizes):
-        inp, _ = stacking.dataset_to_nodes(inputs, sizes)
+        """(inputs, forcings) as device tensors [G, B, C] (layout transposes run on the GPU)."""
         forc = forcings if forcings is not None else Dataset({}, inputs.coords)
-        frc, _ = stacking.dataset_to_nodes(forc, sizes)
-        return inp, frc
+        return self.stacker.to_nodes("inputs", inputs, sizes), self.stacker.to_nodes("forcings", forc, sizes)
 
     def __call__(self, inputs: Dataset, noisy_targets: Dataset, noise_levels: DataArray,
                  forcings: Optional[Dataset] = None, **kwargs) -> Dataset:
@@ -100,13 +107,13 @@ class Denoiser:
         batch = sizes["batch"]
         if noise_levels.shape[0] != batch:
             raise ValueError("noise_levels must have one entry per batch element")
-        inp, frc = self.stack_constants(inputs, forcings, sizes)
-        noisy, _ = stacking.dataset_to_nodes(noisy_targets, sizes)
-        out = np.empty((engine.G, batch, engine.n_out), np.float32)
         with torch.cuda.device(engine.device):
+            inp, frc = self.stack_constants(inputs, forcings, sizes)
+            noisy = self.stacker.to_nodes("noisy", noisy_targets, sizes)
+            out = torch.empty(engine.G, batch, engine.n_out, dtype=torch.float32, device=engine.device)
             for b in range(batch):
                 engine.set_constant_features(inp[:, b], frc[:, b])
                 engine.set_network_input(noisy[:, b])
                 f = engine.forward(engine.sigma_context(float(noise_levels.data[b])))
-                out[:, b] = engine.read_output(f)
-        return stacking.nodes_to_dataset(out, noisy_targets)
+                out[:, b] = f[:, :engine.n_out]
+            return self.stacker.from_nodes(out, noisy_targets)

@@ -61,10 +61,10 @@ class Sampler:
         sizes = dict(targets_template.sizes)
         sizes.setdefault("batch", 1)
         batch = sizes["batch"]
-        inp, frc = den.stack_constants(inputs, forcings, sizes)
         se = self.sampler_engine()
-        out = np.empty((engine.G, batch, engine.n_out), np.float32)
         with torch.cuda.device(engine.device):
+            inp, frc = den.stack_constants(inputs, forcings, sizes)
+            out = torch.empty(engine.G, batch, engine.n_out, dtype=torch.float32, device=engine.device)
             gen = torch.Generator(device=engine.device)
             gen.manual_seed(int(key) & 0x7FFFFFFFFFFFFFFF)
             for b in range(batch):
@@ -74,5 +74,5 @@ class Sampler:
                 else:
                     noise = torch.randn(engine.G, engine.n_out, generator=gen, device=engine.device)
                 res = se.sample(noise, use_graph=self._use_graph)
-                out[:, b] = engine.read_output(res)
-        return stacking.nodes_to_dataset(out, targets_template)
+                out[:, b] = res
+            return den.stacker.from_nodes(out, targets_template)

@@ -133,3 +133,22 @@ def test_full_size_1deg_properties(cuda_device):
     errs = per_variable_error(case, got32, ref32)
     print(f"1deg f32 patch vs reference mesh order: {max(errs.values()):.3e}")
     assert max(errs.values()) <= 1e-4, errs
+
+
+def test_device_stacking_equals_host_stacking(cuda_device):
+    """The GPU layout transposes reproduce stacking.py (common/model_utils.py:594-725) bit for bit."""
+    from gencast_flax_nnx_b200 import graph, stacking, synthetic
+    from gencast_flax_nnx_b200.device_stacking import DeviceStacker
+    lat, lon = graph.regular_grid(30.0)
+    inputs, targets, forcings = synthetic.make_example(lat, lon, batch=2, seed=5)
+    sizes = dict(targets.sizes)
+    st = DeviceStacker(cuda_device)
+    for key, ds in (("inputs", inputs), ("forcings", forcings)):
+        host, _ = stacking.dataset_to_nodes(ds, sizes)
+        dev = st.to_nodes(key, ds, sizes)
+        assert np.array_equal(dev.cpu().numpy(), host)
+    x = np.random.default_rng(0).standard_normal((len(lat) * len(lon), 2, 82)).astype(np.float32)
+    ref = stacking.nodes_to_dataset(x, targets)
+    got = st.from_nodes(torch.from_numpy(x).to(cuda_device), targets)
+    for k in ref.keys():
+        assert got[k].dims == ref[k].dims and np.array_equal(got[k].data, ref[k].data)
