@@ -89,12 +89,12 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_case(config: str, seed: int = 0):
+def build_case(config: str, seed: int = 0, batch: int = 1):
     from gencast_flax_nnx_b200 import configs, graph, params, stacking, synthetic
     from gencast_flax_nnx_b200.engine import ChannelLayout
     res, arch = configs.named_config(config)
     lat, lon = graph.regular_grid(res)
-    inputs, targets, forcings = synthetic.make_example(lat, lon, batch=1, seed=seed)
+    inputs, targets, forcings = synthetic.make_example(lat, lon, batch=batch, seed=seed)
     sizes = dict(targets.sizes)
     inp_nodes, _ = stacking.dataset_to_nodes(inputs, sizes)
     frc_nodes, frc_layout = stacking.dataset_to_nodes(forcings, sizes)
@@ -111,6 +111,8 @@ def workload_name(config: str) -> str:
                     "12 h step = 20-level DPM-Solver++ 2S",
             "1deg": "GenCast 1deg (181x360 grid, mesh 5, L=512, 16 layers, k-hop 8), one member per GPU, "
                     "12 h step = 20-level DPM-Solver++ 2S",
+            "0p25deg": "GenCast 0.25deg (721x1440 grid, mesh 6, L=512, 16 layers, k-hop 8), one member per GPU, "
+                       "12 h step = 20-level DPM-Solver++ 2S",
             "tiny": "test-size GenCast 10deg (19x36 grid, mesh 2, L=128, 2 layers), 12 h step = 20-level DPM-Solver++ 2S",
             }[config]
 
@@ -207,13 +209,16 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    case = build_case(args.config)
+    MB = args.members_per_gpu
+    case = build_case(args.config, batch=MB)
     graphs = oracle_graph(case)
-    eng = DenoiserEngine(graphs, case["arch"], case["params"], case["layout"], compute_dtype=args.dtype, device=dev)
+    eng = DenoiserEngine(graphs, case["arch"], case["params"], case["layout"], compute_dtype=args.dtype, device=dev,
+                         members=MB)
     sigmas = noise_schedule(80.0, 0.03, 20, 7.0)
     se = SamplerEngine(eng, sigmas, evaluate_discarded_call=True)
-    eng.set_constant_features(case["inp_nodes"][:, 0], case["frc_nodes"][:, 0])
-    G, C = eng.G, eng.n_out
+    member_major = lambda a: np.ascontiguousarray(np.transpose(a, (1, 0, 2))).reshape(-1, a.shape[-1])
+    eng.set_constant_features(member_major(case["inp_nodes"]), member_major(case["frc_nodes"]))
+    G, C = eng.Gt, eng.n_out
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
     noises = [torch.randn(G, C, generator=gen, device=dev) for _ in range(max(args.steps, 1))]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -252,7 +257,7 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    value = world * args.steps / (total_ms / 1e3)
+    value = world * MB * args.steps / (total_ms / 1e3)
     clock_summary = clocks.summary()
 
     # ---- e2e through the public API: host Datasets in, host Dataset out
@@ -277,8 +282,8 @@ def run_gpu(args):
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps / float(t.item())
-    h2d = (case["layout"].num_input_channels + case["layout"].num_forcings) * G * 4
+    e2e_value = world * MB * e2e_steps / float(t.item())
+    h2d = sum(int(np.prod(v.shape)) for ds in (case["inputs"], case["forcings"]) for v in ds.data_vars.values()) * 4
     d2h = C * G * 4
 
     if rank != 0:
@@ -335,7 +340,7 @@ def run_gpu(args):
     if world == 1 and not args.no_cpu_baseline:
         reps = 2 if args.config == "nano" else 1
         times = cpu_solver_iteration_seconds(case, repeats=reps, warmup=1 if args.config != "1deg" else 0)
-        v = 1.0 / (float(np.mean(times)) * 20)
+        v = MB / (float(np.mean(times)) * 20)
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                "sample": f"{reps} of the 20 solver iterations (2 denoiser evaluations each) of the torch-fp32 oracle "
                          f"of the reference algorithm, all host threads; step time = 20 x mean iteration"}
@@ -343,7 +348,7 @@ def run_gpu(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": workload_name(args.config), "members": world,
+            "config": {"workload": workload_name(args.config), "members": world * MB, "members_per_gpu": MB,
                        "denoiser_evaluations_per_step": se.num_network_evaluations,
                        "weights": "random N(0, 1/fan_in) (reference init makes the transformer an identity)",
                        "l2": "flushed between timed steps (256 MiB write, not timed)",
@@ -371,9 +376,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
-    ap.add_argument("--config", default="nano", choices=["tiny", "nano", "1deg"])
+    ap.add_argument("--config", default="nano", choices=["tiny", "nano", "1deg", "0p25deg"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--members-per-gpu", type=int, default=1,
+                    help="ensemble members evaluated together on each GPU (default 1 = BASELINE configs[1])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

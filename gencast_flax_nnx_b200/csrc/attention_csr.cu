@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128) khop_attention_csr_kernel(const void* __r
           }
         }
       }
-      const float inv = 1.0f / l;
+      const float inv = l > 0.0f ? 1.0f / l : 0.0f;     // rows without neighbours (padding) produce zeros
       const int64_t ooff = node * ldo + static_cast<int64_t>(head) * D + lane * DPL;
 #pragma unroll
       for (int i = 0; i < DPL; ++i) {

@@ -71,8 +71,11 @@ class Denoiser:
                 seed = self._rngs.params()
             init = init_reference_like if self._param_init == "reference" else init_perturbed
             self._params = init(shapes, seed=seed)
+        # all batch elements of a call are evaluated together when they share the noise level (the
+        # sampler's case): the engine is built for that many members
         self._engine = DenoiserEngine(graphs, self._arch, self._params, layout, self._noise_cfg,
-                                      compute_dtype=self._compute_dtype, device=self._device)
+                                      compute_dtype=self._compute_dtype, device=self._device,
+                                      members=int(sizes.get("batch", 1)))
         self._grid_key = key
         return self._engine
 
@@ -107,13 +110,22 @@ class Denoiser:
         batch = sizes["batch"]
         if noise_levels.shape[0] != batch:
             raise ValueError("noise_levels must have one entry per batch element")
+        levels = np.asarray(noise_levels.data, np.float64)
+        if engine.B != batch:
+            raise ValueError(f"Denoiser was initialised for batch size {engine.B}, got {batch}")
+        if batch > 1 and not np.all(levels == levels[0]):
+            raise NotImplementedError("batch elements with different noise levels in one call: evaluate them "
+                                      "separately (the sampler always passes one level)")
         with torch.cuda.device(engine.device):
             inp, frc = self.stack_constants(inputs, forcings, sizes)
             noisy = self.stacker.to_nodes("noisy", noisy_targets, sizes)
-            out = torch.empty(engine.G, batch, engine.n_out, dtype=torch.float32, device=engine.device)
-            for b in range(batch):
-                engine.set_constant_features(inp[:, b], frc[:, b])
-                engine.set_network_input(noisy[:, b])
-                f = engine.forward(engine.sigma_context(float(noise_levels.data[b])))
-                out[:, b] = f[:, :engine.n_out]
+            engine.set_constant_features(self.member_major(inp), self.member_major(frc))
+            engine.set_network_input(self.member_major(noisy))
+            f = engine.forward(engine.sigma_context(float(levels[0])))
+            out = f[:, :engine.n_out].reshape(batch, engine.G, engine.n_out).permute(1, 0, 2)
             return self.stacker.from_nodes(out, noisy_targets)
+
+    @staticmethod
+    def member_major(nodes: torch.Tensor) -> torch.Tensor:
+        """[G, B, C] (the reference's node-major layout, gencast/denoiser.py:833-837) -> [B * G, C]."""
+        return nodes.permute(1, 0, 2).reshape(nodes.shape[0] * nodes.shape[1], nodes.shape[2]).contiguous()

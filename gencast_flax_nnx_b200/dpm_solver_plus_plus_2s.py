@@ -61,18 +61,19 @@ class Sampler:
         sizes = dict(targets_template.sizes)
         sizes.setdefault("batch", 1)
         batch = sizes["batch"]
+        if engine.B != batch:
+            raise ValueError(f"Sampler was initialised for batch size {engine.B}, got {batch}")
         se = self.sampler_engine()
         with torch.cuda.device(engine.device):
             inp, frc = den.stack_constants(inputs, forcings, sizes)
-            out = torch.empty(engine.G, batch, engine.n_out, dtype=torch.float32, device=engine.device)
-            gen = torch.Generator(device=engine.device)
-            gen.manual_seed(int(key) & 0x7FFFFFFFFFFFFFFF)
-            for b in range(batch):
-                engine.set_constant_features(inp[:, b], frc[:, b])
-                if init_noise is not None:
-                    noise = np.ascontiguousarray(init_noise[:, b], dtype=np.float32)
-                else:
-                    noise = torch.randn(engine.G, engine.n_out, generator=gen, device=engine.device)
-                res = se.sample(noise, use_graph=self._use_graph)
-                out[:, b] = res
+            engine.set_constant_features(den.member_major(inp), den.member_major(frc))
+            if init_noise is not None:
+                noise = np.ascontiguousarray(np.transpose(np.asarray(init_noise, np.float32), (1, 0, 2))).reshape(
+                    batch * engine.G, engine.n_out)
+            else:
+                gen = torch.Generator(device=engine.device)
+                gen.manual_seed(int(key) & 0x7FFFFFFFFFFFFFFF)
+                noise = torch.randn(batch * engine.G, engine.n_out, generator=gen, device=engine.device)
+            res = se.sample(noise, use_graph=self._use_graph)
+            out = res.reshape(batch, engine.G, engine.n_out).permute(1, 0, 2)
             return den.stacker.from_nodes(out, targets_template)

@@ -111,11 +111,15 @@ class DenoiserEngine:
     def __init__(self, graphs: DenoiserGraphs, arch: DenoiserArchitectureConfig, params: Dict[str, np.ndarray],
                  layout: ChannelLayout, noise_cfg: NoiseEncoderConfig = NoiseEncoderConfig(),
                  compute_dtype: str = "bf16", device: Optional[torch.device] = None,
-                 mesh_order: str = "patch", attention: str = "auto"):
+                 mesh_order: str = "patch", attention: str = "auto", members: int = 1):
         """mesh_order: 'patch' relabels mesh nodes into compact 128-node patches (fewer attention
         tiles), 'reference' keeps the reference's band ordering.  attention: 'auto' uses the
         tensor-core tile kernel for bf16 with head_dim 64/128 and the CSR kernel otherwise;
-        'csr' forces the CSR kernel."""
+        'csr' forces the CSR kernel.  members: ensemble members evaluated together (they share the
+        noise level but nothing else): all node / edge tables hold `members` blocks of rows, index
+        tables carry the block offsets, and each member's mesh rows are padded to a multiple of 128 so
+        attention tiles never straddle members.  More rows per launch is what the small grids need to
+        fill the machine."""
         if not torch.cuda.is_available():
             raise RuntimeError("DenoiserEngine needs a CUDA device: there is no CPU path")
         ops._lib.load()
@@ -133,6 +137,12 @@ class DenoiserEngine:
         self.head_dim = L // self.H
         self.G, self.V = graphs.num_grid_nodes, graphs.num_mesh_nodes
         self.E1, self.E2 = len(graphs.g2m_senders), len(graphs.m2g_senders)
+        self.B = int(members)
+        if self.B < 1:
+            raise ValueError("members must be >= 1")
+        self.Vp = self.V if self.B == 1 else _pad_to(self.V, 128)      # mesh rows per member
+        self.Gt, self.Vt = self.B * self.G, self.B * self.Vp           # total rows
+        self.E1t, self.E2t = self.B * self.E1, self.B * self.E2
         self.n_out = layout.num_targets
         self.KN = _pad_to(self.n_out, 64)
         self.n_const = 3 + layout.num_input_channels + layout.num_forcings
@@ -198,32 +208,62 @@ class DenoiserEngine:
         g2m_recv = inv[g.g2m_receivers]
         m2g_send = inv[g.m2g_senders]
         self._mesh_feat = g.g2m_mesh_feat[order]
-        self.g2m_s = self._dev(g.g2m_senders.astype(np.int32))
-        self.g2m_r = self._dev(g2m_recv.astype(np.int32))
-        rp, perm = csr_by_receiver(g2m_recv, self.V)
+        B, G, V, Vp, E1, E2 = self.B, self.G, self.V, self.Vp, self.E1, self.E2
+
+        def blocks(idx, stride):
+            """Index table of one member -> all members (block b offset by b * stride)."""
+            idx = np.asarray(idx, np.int64)
+            return (idx[None, :] + (np.arange(B, dtype=np.int64) * stride)[:, None]).reshape(-1).astype(np.int32)
+
+        def csr_blocks(row_ptr, perm, n_seg, n_seg_padded, n_edges):
+            rp = np.zeros(B * n_seg_padded + 1, np.int64)
+            for b in range(B):
+                rp[b * n_seg_padded: b * n_seg_padded + n_seg + 1] = row_ptr.astype(np.int64) + b * n_edges
+                rp[b * n_seg_padded + n_seg + 1: (b + 1) * n_seg_padded + 1] = (b + 1) * n_edges   # padded rows: empty
+            return rp.astype(np.int32), (None if perm is None else blocks(perm, n_edges))
+
+        self.g2m_s = self._dev(blocks(g.g2m_senders, G))
+        self.g2m_r = self._dev(blocks(g2m_recv, Vp))
+        rp, perm = csr_by_receiver(g2m_recv, V)
+        rp, perm = csr_blocks(rp, perm, V, Vp, E1)
         self.g2m_row_ptr, self.g2m_perm = self._dev(rp), self._dev(perm)
-        self.m2g_s = self._dev(m2g_send.astype(np.int32))
-        self.m2g_r = self._dev(g.m2g_receivers.astype(np.int32))
+        self.m2g_s = self._dev(blocks(m2g_send, Vp))
+        self.m2g_r = self._dev(blocks(g.m2g_receivers, G))
         # mesh2grid edges are emitted grid-major, three per grid node
         # (common/grid_mesh_connectivity.py:125-131): already receiver sorted.
-        if not np.array_equal(g.m2g_receivers, np.repeat(np.arange(self.G), 3)):
-            rp2, perm2 = csr_by_receiver(g.m2g_receivers, self.G)
+        if not np.array_equal(g.m2g_receivers, np.repeat(np.arange(G), 3)):
+            rp2, perm2 = csr_by_receiver(g.m2g_receivers, G)
+            rp2, perm2 = csr_blocks(rp2, perm2, G, G, E2)
             self.m2g_row_ptr, self.m2g_perm = self._dev(rp2), self._dev(perm2)
         else:
-            self.m2g_row_ptr = torch.arange(0, 3 * self.G + 1, 3, dtype=i32, device=self.device)
+            self.m2g_row_ptr = torch.arange(0, 3 * B * G + 1, 3, dtype=i32, device=self.device)
             self.m2g_perm = None
         khop = g.khop.tocsr()[order][:, order].tocsr()
         khop.sort_indices()
-        self.khop_nnz = int(khop.nnz)
+        self.khop_nnz = int(khop.nnz) * B
         self.max_degree = int(np.diff(khop.indptr).max())
         if self.use_tc_attention:
             tp, tk, tm = khop_tiles(khop, 128)
+            nq = len(tp) - 1                                   # query / key tiles per member (= ceil(V / 128))
+            if B > 1:
+                assert nq * 128 == Vp
+                tp = np.concatenate([tp[:-1].astype(np.int64) + b * len(tk) for b in range(B)] + [[B * len(tk)]]).astype(np.int32)
+                tk = blocks(tk, nq)
+                tm = np.tile(tm, (B, 1, 1))
             self.tile_ptr, self.tile_kv = self._dev(tp), self._dev(tk)
             self.tile_mask = self._dev(tm.view(np.int32)).view(torch.int32)
             self.num_attention_tiles = int(len(tk))
         else:
-            self.nbr_ptr = self._dev(khop.indptr.astype(np.int32))
-            self.nbr_idx = self._dev(khop.indices.astype(np.int32))
+            ptr, idx = khop.indptr.astype(np.int64), khop.indices.astype(np.int64)
+            if B > 1:
+                nnz = len(idx)
+                full = np.zeros(B * Vp + 1, np.int64)
+                for b in range(B):
+                    full[b * Vp: b * Vp + V + 1] = ptr + b * nnz
+                    full[b * Vp + V + 1: (b + 1) * Vp + 1] = (b + 1) * nnz
+                ptr, idx = full, blocks(idx, Vp).astype(np.int64)
+            self.nbr_ptr = self._dev(ptr.astype(np.int32))
+            self.nbr_idx = self._dev(idx.astype(np.int32))
 
     def _upload_weights(self):
         p, pre, L = self._p, self._pre, self.L
@@ -287,7 +327,7 @@ class DenoiserEngine:
             raise ValueError("noise-level encoder must be 2*num_frequencies -> 32 -> 16 (gc_cond_tables)")
 
     def _alloc_workspace(self):
-        L, G, V, E1, E2 = self.L, self.G, self.V, self.E1, self.E2
+        L, G, V, E1, E2 = self.L, self.Gt, self.Vt, self.E1t, self.E2t
         b = self._buf
         self.xin = b(G, self.KN)                 # c_in * noisy targets (network input operand)
         self.a_const = b(G, self.KC)             # struct | inputs | forcings, constant over a sampling step
@@ -323,12 +363,16 @@ class DenoiserEngine:
 
     def _precompute_static(self):
         g, pre = self.graphs, self._pre
-        self.g2m_e_ln = self._static_embed(pre["g2m_edge_embed"], g.g2m_edge_feat, slice(0, 4))
-        self.m2g_e_ln = self._static_embed(pre["m2g_edge_embed"], g.m2g_edge_feat, slice(0, 4))
+        B = self.B
+        self.g2m_e_ln = self._static_embed(pre["g2m_edge_embed"], g.g2m_edge_feat, slice(0, 4)).repeat(B, 1)
+        self.m2g_e_ln = self._static_embed(pre["m2g_edge_embed"], g.m2g_edge_feat, slice(0, 4)).repeat(B, 1)
         # mesh nodes: [structural | zeros] (gencast/denoiser.py:640-657) -> only the first 3 kernel rows matter
-        self.m0_ln = self._static_embed(pre["g2m_mesh_embed"], self._mesh_feat, slice(0, 3))
+        m0 = self._static_embed(pre["g2m_mesh_embed"], self._mesh_feat, slice(0, 3))
+        if self.Vp != self.V:
+            m0 = torch.cat([m0, torch.zeros(self.Vp - self.V, self.L, dtype=m0.dtype, device=m0.device)])
+        self.m0_ln = m0.repeat(B, 1).contiguous()
         # structural part of the constant grid operand
-        self.a_const[:, :3] = self._dev(g.g2m_grid_feat, self.cd)
+        self.a_const[:, :3] = self._dev(g.g2m_grid_feat, self.cd).repeat(B, 1)
 
     # ------------------------------------------------------------------ per-sigma
     def sigma_context(self, sigma: float) -> SigmaContext:
@@ -355,28 +399,29 @@ class DenoiserEngine:
         """(pinned host, device) fp32 staging pair of shape [G, cols], allocated once."""
         st = self.__dict__.setdefault("_staging", {})
         if name not in st:
-            st[name] = (torch.empty(self.G, cols, dtype=torch.float32, pin_memory=True),
-                        torch.empty(self.G, cols, dtype=torch.float32, device=self.device))
+            st[name] = (torch.empty(self.Gt, cols, dtype=torch.float32, pin_memory=True),
+                        torch.empty(self.Gt, cols, dtype=torch.float32, device=self.device))
         return st[name]
 
     def _to_device_f32(self, name: str, parts: Sequence) -> torch.Tensor:
         """Host arrays go through pinned memory (async H2D on the current stream); device tensors are used as is."""
-        cols = sum(int(np.prod(p.shape)) // self.G for p in parts)
+        cols = sum(int(np.prod(p.shape)) // self.Gt for p in parts)
         if all(isinstance(p, torch.Tensor) and p.is_cuda for p in parts):
-            t = torch.cat([p.reshape(self.G, -1).to(torch.float32) for p in parts], dim=1)
+            t = torch.cat([p.reshape(self.Gt, -1).to(torch.float32) for p in parts], dim=1)
             return t.contiguous()
         pin, dev = self._stage(name, cols)
         c = 0
         for p in parts:
             a = p.detach().cpu().numpy() if isinstance(p, torch.Tensor) else np.asarray(p)
-            a = a.reshape(self.G, -1)
+            a = a.reshape(self.Gt, -1)
             pin[:, c:c + a.shape[1]] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
             c += a.shape[1]
         dev.copy_(pin, non_blocking=True)
         return dev
 
     def set_constant_features(self, inputs_nodes, forcings_nodes) -> None:
-        """Per-step constants: stacked inputs [G, C_in] and forcings [G, C_f] (host or device, fp32)."""
+        """Per-step constants: stacked inputs [members * G, C_in] and forcings [members * G, C_f]
+        (member-major blocks of grid rows; host or device, fp32)."""
         ni, nf = self.layout.num_input_channels, self.layout.num_forcings
         with torch.cuda.device(self.device):
             cat = self._to_device_f32("const", [inputs_nodes, forcings_nodes])
@@ -409,7 +454,7 @@ class DenoiserEngine:
         Enqueues on torch's current stream; reads self.xin and self.a_const.
         """
         w, T = self.w, ctx.table
-        E1, E2 = self.E1, self.E2
+        E1, E2 = self.E1t, self.E2t
         # ---- encoder (gencast/denoiser.py:602-688)
         self._mlp_ln([(self.xin, w["ge_w1n"]), (self.a_const, w["ge_w1c"])], w["ge_b1"], w["ge_w2"], w["ge_b2"],
                      self.g_h, self.g_y, self.g0, T[self.C_G2M_GE])
@@ -523,7 +568,7 @@ class SamplerEngine:
         self.sched = torch.from_numpy(sched).to(e.device)
         self.init_scale = torch.tensor([self.sigmas[0], self.sigmas[0] * _c_in(self.sigmas[0])], dtype=torch.float32,
                                        device=e.device)
-        G, C = e.G, e.n_out
+        G, C = e.Gt, e.n_out
         self.noise = torch.zeros(G, C, dtype=torch.float32, device=e.device)    # unit-variance initial noise (input)
         self.x = torch.zeros(G, C, dtype=torch.float32, device=e.device)
         self.x_mid = torch.zeros(G, C, dtype=torch.float32, device=e.device)
