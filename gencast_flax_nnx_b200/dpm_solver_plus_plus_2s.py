@@ -19,7 +19,8 @@ class Sampler:
     def __init__(self, denoiser, max_noise_level: float, min_noise_level: float, num_noise_levels: int,
                  rho: float, stochastic_churn_rate: float, churn_min_noise_level: float,
                  churn_max_noise_level: float, noise_level_inflation_factor: float, *,
-                 evaluate_discarded_call: bool = True, use_cuda_graph: bool = True):
+                 evaluate_discarded_call: bool = True, use_cuda_graph: bool = True,
+                 initial_noise: str = "spherical"):
         self._noise_levels = noise_schedule(max_noise_level, min_noise_level, num_noise_levels, rho)
         self._stochastic_churn = stochastic_churn_rate > 0
         if self._stochastic_churn:
@@ -33,6 +34,10 @@ class Sampler:
         self.sigma_data = 1.0
         self._evaluate_discarded_call = evaluate_discarded_call
         self._use_graph = use_cuda_graph
+        if initial_noise not in ("spherical", "white"):
+            raise ValueError("initial_noise must be 'spherical' (the reference's, samplers_utils.py:333-346) or 'white'")
+        self._initial_noise = initial_noise
+        self._noise_gen = None
         self._engine: Optional[SamplerEngine] = None
 
     @property
@@ -48,8 +53,9 @@ class Sampler:
                  rngs=None, *, init_noise: Optional[np.ndarray] = None) -> Dataset:
         """One 12 h step.  `init_noise` ([G, batch, n_out], unit variance) overrides the generator.
 
-        The reference draws spherical-harmonic white noise (samplers_utils.py:333-346, dinosaur);
-        here the default is white noise in grid space drawn on the device from `rngs.noise()`.
+        Like the reference (samplers_utils.py:333-346) the default initial state is isotropic
+        spherical-harmonic white noise (spherical_noise.py), drawn on the device from `rngs.noise()`;
+        `initial_noise='white'` draws independent grid-point noise instead.
         Surface variables are carried once (the reference broadcasts them over 13 levels and
         selects level 0, :59, :93-95 -- an equivalent state).
         """
@@ -73,7 +79,14 @@ class Sampler:
             else:
                 gen = torch.Generator(device=engine.device)
                 gen.manual_seed(int(key) & 0x7FFFFFFFFFFFFFFF)
-                noise = torch.randn(batch * engine.G, engine.n_out, generator=gen, device=engine.device)
+                if self._initial_noise == "spherical":
+                    if self._noise_gen is None:
+                        from .spherical_noise import SphericalNoise
+                        self._noise_gen = SphericalNoise(targets_template.coords["lat"], targets_template.coords["lon"],
+                                                         engine.device)
+                    noise = self._noise_gen.sample_nodes(engine.n_out, members=batch, generator=gen)
+                else:
+                    noise = torch.randn(batch * engine.G, engine.n_out, generator=gen, device=engine.device)
             res = se.sample(noise, use_graph=self._use_graph)
             out = res.reshape(batch, engine.G, engine.n_out).permute(1, 0, 2)
             return den.stacker.from_nodes(out, targets_template)

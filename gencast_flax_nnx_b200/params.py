@@ -178,3 +178,37 @@ def init_reference_like(shapes: Dict[str, Tuple[int, ...]], seed: int = 0, num_l
             w = rng.uniform(-lim, lim, shape)
         out[name] = w.astype(np.float32)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# Weight interchange: the flat dict <-> files / NNX state
+# ----------------------------------------------------------------------------------------------
+
+def save_npz(params: Dict[str, np.ndarray], path: str) -> None:
+    """One array per NNX attribute path ('/' separated), float32."""
+    np.savez(path, **{k.replace("/", "|"): np.asarray(v, np.float32) for k, v in params.items()})
+
+
+def load_npz(path: str) -> Dict[str, np.ndarray]:
+    with np.load(path) as f:
+        return {k.replace("|", "/"): f[k] for k in f.files}
+
+
+def from_nnx_state(flat_state) -> Dict[str, np.ndarray]:
+    """Flattens `nnx.state(model, nnx.Param).flat_state()` (an iterable of (path tuple, variable)) into the
+    flat dict used here.  The Orbax checkpoints of the reference additionally wrap the update functions
+    in `graph_network` / `edge_fn` / `node_fn` levels, which are already part of these paths
+    (training/evaluation.py:143-148); integer path components (list indices) are kept as digits."""
+    out = {}
+    for path, var in flat_state:
+        value = getattr(var, "value", var)
+        out["/".join(str(p) for p in path)] = np.asarray(value, np.float32)
+    return out
+
+
+def check_complete(params: Dict[str, np.ndarray], shapes: Dict[str, Tuple[int, ...]]) -> None:
+    """Raises with the list of missing / mis-shaped entries."""
+    missing = [k for k in shapes if k not in params]
+    bad = [f"{k}: {tuple(params[k].shape)} != {shapes[k]}" for k in shapes if k in params and tuple(params[k].shape) != tuple(shapes[k])]
+    if missing or bad:
+        raise ValueError(f"parameter tree mismatch; missing={missing[:5]}{'...' if len(missing) > 5 else ''} bad={bad[:5]}")

@@ -244,3 +244,26 @@ def test_library_exports_every_declared_symbol():
     loaded = _lib.load()
     assert loaded.gc_abi_version() >= 1
     assert loaded.gc_sizeof_gemm_args() == ctypes.sizeof(_lib.GemmArgs)      # struct layout agrees with the C side
+
+
+def test_param_interchange_round_trip(tmp_path):
+    from gencast_flax_nnx_b200 import params
+    res, arch = configs.named_config("tiny")
+    shapes = params.param_shapes(arch, 260, 82)
+    p = params.init_perturbed(shapes, seed=3)
+    path = str(tmp_path / "w.npz")
+    params.save_npz(p, path)
+    q = params.load_npz(path)
+    assert set(q) == set(p) and all(np.array_equal(p[k], q[k]) for k in p)
+    params.check_complete(q, shapes)
+    del q[next(iter(q))]
+    with pytest.raises(ValueError):
+        params.check_complete(q, shapes)
+
+    class V:                                     # stands for an nnx.Param
+        def __init__(self, v): self.value = v
+    flat = params.from_nnx_state([(("denoiser", "blocks", 3, "kernel"), V(np.ones((2, 2))))])
+    assert list(flat) == ["denoiser/blocks/3/kernel"]
+    ref = params.init_reference_like(shapes)
+    # at the reference initialisation every transformer block is the identity
+    assert not ref["denoiser/predictor/mesh_gnn/batch_first_transformer/blocks/0/attn_module/final_linear/kernel"].any()
