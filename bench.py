@@ -185,7 +185,7 @@ def run_reference(args):
             "config": {"workload": workload_name(args.config), "members": 1},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -207,6 +207,7 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     MB = args.members_per_gpu
@@ -371,7 +372,7 @@ def run_gpu(args):
                             "replayed denoiser evaluations (queued behind a device delay); shares are of their sum"}
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -380,7 +381,22 @@ def roofline_clean(r):
     return {k: (float(v) if isinstance(v, (np.floating, float)) else v) for k, v in r.items()}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The single JSON line goes to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    # Libraries (NCCL's version banner, torchrun notices) write to fd 1: keep the real stdout for the
+    # JSON line only and send everything else to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
