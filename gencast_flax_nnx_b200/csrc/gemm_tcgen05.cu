@@ -72,24 +72,89 @@ struct GemmShape {
   int num_segments;
   int n_tiles;
   int store_mode;
+  int gather_staged;               // row gathers go through the shared-memory transposition (staged store modes only)
 };
 
 // Epilogue of one warp for one accumulator buffer: 32 rows (its TMEM lane quarter) x HALF columns.
 // `release` is called once, as soon as the last tcgen05.ld of the buffer has landed in registers.
 // stage_smem: this warp's two 4 KB staging buffers (1024-byte aligned) for the TMA store modes.
-template <int HALF, typename Release>
+//
+// Row gathers in the staged modes (gather_smem != 0): the rows of a gather table that the 32 output
+// rows of this warp need are fetched with coalesced 16-byte loads (4 lanes per 64-byte row segment,
+// 8 rows per instruction), transposed through a 2 KB swizzled shared-memory buffer into the
+// row-per-thread layout of the accumulator, and added in fp32.  A thread-per-row global load touches
+// 32 lines per instruction and made the L1 tag stage the bottleneck of the edge GEMMs (2.8 x the time
+// of the same GEMM without gathers); this way it is 8.  Loads run one 32-column chunk ahead.
+template <int HALF, typename WaitAcc, typename Release>
 __device__ __forceinline__ void epilogue_warp_tile(const EpilogueParams& ep, const CUtensorMap* out_map, int store_mode,
                                                    float alpha, uint32_t taddr, const float* bias_ptr, int64_t row0,
                                                    int col_base, int lane, uint32_t stage_smem, int& stage_use,
-                                                   Release release) {
+                                                   uint32_t gather_smem, WaitAcc wait_acc, Release release,
+                                                   long long* etrace = nullptr, int* etrace_ev = nullptr) {
   using namespace sm100;
+#define GC_ESTAMP()                                                                                     \
+  do {                                                                                                  \
+    if (etrace != nullptr && *etrace_ev < 4 * 512) { etrace[4 * 512 + *etrace_ev] = clock64(); ++*etrace_ev; } \
+  } while (0)
   const int64_t row = row0 + lane;
+  const bool gathers = gather_smem != 0u && store_mode != STORE_DIRECT;
+  const bool has_g1 = gathers && ep.gsrc1 != nullptr;
+  int gi0 = 0, gi1 = 0;
+  if (gathers && row < ep.m) {
+    gi0 = __ldg(ep.gidx0 + row);
+    if (has_g1) gi1 = __ldg(ep.gidx1 + row);
+  }
+  // lane -> (row 8 i + lane / 4, 16-byte unit lane % 4) of a [32 rows x 32 bf16] block
+  const int g_sub = lane >> 2, g_unit = lane & 3;
+  auto gather_issue = [&](const void* src, int64_t ld, int gi, int c, uint4 (&g)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t idx = __shfl_sync(0xffffffffu, gi, 8 * i + g_sub);
+      g[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src) + idx * ld + col_base + c) + g_unit);
+    }
+  };
+  auto gather_add = [&](const uint4 (&g)[4], float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t rl = static_cast<uint32_t>(8 * i + g_sub);
+      const uint32_t addr = gather_smem + rl * 64u + ((static_cast<uint32_t>(g_unit) ^ ((rl >> 1) & 3u)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(g[i].x), "r"(g[i].y), "r"(g[i].z), "r"(g[i].w)
+                   : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t addr = gather_smem + static_cast<uint32_t>(lane) * 64u +
+                            ((static_cast<uint32_t>(u) ^ ((static_cast<uint32_t>(lane) >> 1) & 3u)) << 4);
+      uint4 raw;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "r"(addr));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h[j]);
+        v[8 * u + 2 * j] += f.x;
+        v[8 * u + 2 * j + 1] += f.y;
+      }
+    }
+    __syncwarp();
+  };
+  uint4 ga[4], gb[4];
+  if (gathers) {
+    gather_issue(ep.gsrc0, ep.ldg0, gi0, 0, ga);
+    if (has_g1) gather_issue(ep.gsrc1, ep.ldg1, gi1, 0, gb);
+  }
+  wait_acc();
   uint32_t r[32];
   tmem_ld_32x32b_x32(taddr, r);
-#pragma unroll
+  // Not unrolled: every register array is indexed by compile-time constants inside one chunk, and four
+  // copies of this body (~35 KB of SASS each way through the store modes) thrash the instruction cache
+  // of an SM whose ten warps sit in different copies ('no_inst' stalls in the source-level profile).
+#pragma unroll 1
   for (int c = 0; c < HALF; c += 32) {
     float v[32];
+    GC_ESTAMP();                 // chunk start
     tc_wait_ld();
+    GC_ESTAMP();                 // accumulator chunk in registers
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
     if (c + 32 < HALF) {
@@ -115,6 +180,21 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpilogueParams& ep, con
         v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
       }
     }
+    if (gathers) {
+      // this chunk's rows are in ga / gb; the next chunk's loads are issued before they are consumed
+      uint4 na[4] = {}, nb[4] = {};
+      const bool more = c + 32 < HALF;
+      if (more) gather_issue(ep.gsrc0, ep.ldg0, gi0, c + 32, na);
+      gather_add(ga, v);
+      if (has_g1) {
+        if (more) gather_issue(ep.gsrc1, ep.ldg1, gi1, c + 32, nb);
+        gather_add(gb, v);
+      }
+      if (more) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ga[i] = na[i]; gb[i] = nb[i]; }
+      }
+    }
     if (ep.act == GC_ACT_SWISH) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = swish_fast(v[i]);
@@ -131,6 +211,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpilogueParams& ep, con
         if (lane == 0) bulk_wait_group_read<1>();
         __syncwarp();
       }
+      GC_ESTAMP();               // staging buffer free
       const uint32_t buf = stage_smem + static_cast<uint32_t>(stage_use & 1) * 4096u + static_cast<uint32_t>(lane) * 128u;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -153,6 +234,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpilogueParams& ep, con
         }
         ++stage_use;
       }
+      GC_ESTAMP();               // chunk stored / TMA store issued
     } else {
       // 32 fp32 = 128 B = one full row of a 32-column chunk
       if (lane == 0) bulk_wait_group_read<1>();
@@ -313,7 +395,9 @@ struct PersistCfg {
   static constexpr int B_STAGE_BYTES = PBN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;        // 8 warps x 2 x 4 KB store staging
-  static constexpr int BAR_OFFSET = STAGING_OFFSET + 8 * 8192;
+  static constexpr int GATHER_BYTES = PBN == 256 ? 0 : 8 * 2048;     // 8 warps x 2 KB gather transposition (no room at 256)
+  static constexpr int GATHER_OFFSET = STAGING_OFFSET + 8 * 8192;
+  static constexpr int BAR_OFFSET = GATHER_OFFSET + GATHER_BYTES;
   static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;
   static constexpr int SMEM_BYTES = BIAS_OFFSET + 2 * PBN * 4 + 1024;
 };
@@ -433,6 +517,8 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const
     pdl_wait();
     const float alpha = ep.alpha_dev != nullptr ? __ldg(ep.alpha_dev) : 1.0f;
     const uint32_t stage_smem = smem_base + C::STAGING_OFFSET + static_cast<uint32_t>(warp - 2) * 8192u;
+    const uint32_t gather_smem = (C::GATHER_BYTES != 0 && shape.gather_staged)
+                                     ? smem_base + C::GATHER_OFFSET + static_cast<uint32_t>(warp - 2) * 2048u : 0u;
     int stage_use = 0;
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
@@ -445,12 +531,11 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const
       const int col_base = n_blk * PBN + half * HALF;
       const uint32_t taddr = tmem_base + b * PBN + half * HALF + lane_addr;
       if (threadIdx.x == 64) GC_GTRACE(2, 4 * lt);
-      mbar_wait(acc_full(b), (lt >> 1) & 1);
-      if (threadIdx.x == 64) GC_GTRACE(2, 4 * lt + 1);
-      tc_fence_after();
-      const uint32_t acc_bar = acc_empty(b);
+      const uint32_t acc_bar = acc_empty(b), full_bar_b = acc_full(b);
+      const uint32_t full_parity = (lt >> 1) & 1;
       epilogue_warp_tile<HALF>(ep, &maps.out, shape.store_mode, alpha, taddr, bias_ptr,
-                               static_cast<int64_t>(m_blk) * BM + q * 32, col_base, lane, stage_smem, stage_use,
+                               static_cast<int64_t>(m_blk) * BM + q * 32, col_base, lane, stage_smem, stage_use, gather_smem,
+                               [&]() { mbar_wait(full_bar_b, full_parity); tc_fence_after(); },
                                [&]() { if (lane == 0) mbar_arrive(acc_bar); });
       if (threadIdx.x == 64) GC_GTRACE(2, 4 * lt + 2);
     }
@@ -474,13 +559,14 @@ constexpr int Q_STAGES = 4;
 constexpr int Q_B_STAGE_BYTES = 128 * BK * 2;   // this CTA's half of the W tile
 constexpr int Q_STAGE_BYTES = A_STAGE_BYTES + Q_B_STAGE_BYTES;
 constexpr int Q_STAGING_OFFSET = Q_STAGES * Q_STAGE_BYTES;           // 8 warps x 2 x 4 KB store staging
-constexpr int Q_BAR_OFFSET = Q_STAGING_OFFSET + 8 * 8192;
+constexpr int Q_GATHER_OFFSET = Q_STAGING_OFFSET + 8 * 8192;       // 8 warps x 2 KB gather transposition
+constexpr int Q_BAR_OFFSET = Q_GATHER_OFFSET + 8 * 2048;
 constexpr int Q_BIAS_OFFSET = Q_BAR_OFFSET + 256;
 constexpr int Q_SMEM_BYTES = Q_BIAS_OFFSET + 2 * QBN * 4 + 1024;
 
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shape, const EpilogueParams ep,
-                              const int num_tiles) {
+                              const int num_tiles, long long* trace) {
   using namespace sm100;
   pdl_launch_dependents();
   constexpr int HALF = QBN / 2;                 // columns per epilogue warp
@@ -535,6 +621,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmS
       pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
+      int ev = 0;
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
         const int n_blk = tile % shape.n_tiles, m_pair = tile / shape.n_tiles;
         const int m_row = m_pair * 256 + static_cast<int>(rank) * 128;
@@ -542,6 +629,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmS
         for (int s = 0; s < shape.num_segments; ++s) {
           for (int kb = 0; kb < shape.kblocks[s]; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
+            GC_GTRACE(0, ev); ++ev;
             // the leader arms its barrier for the bytes of both CTAs
             if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Q_STAGE_BYTES);
             tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &maps.a[s], full_bar(stage), kb * BK, m_row);
@@ -557,14 +645,18 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmS
       int stage = 0;
       uint32_t phase = 0;
       int lt = 0;
+      int mev = 0;
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++lt) {
         const int b = lt & 1;
+        GC_GTRACE(1, 4 * lt);
         mbar_wait(acc_empty(b), ((lt >> 1) & 1) ^ 1u);      // both CTAs' epilogues have drained this buffer
+        GC_GTRACE(1, 4 * lt + 1);
         tc_fence_after();
         uint32_t accumulate = 0;
         for (int s = 0; s < shape.num_segments; ++s) {
           for (int kb = 0; kb < shape.kblocks[s]; ++kb) {
             mbar_wait(full_bar(stage), phase);
+            GC_GTRACE(3, mev); ++mev;
             tc_fence_after();
             const uint64_t da = desc_kmajor_sw128(smem_a + stage * A_STAGE_BYTES);
             const uint64_t db = desc_kmajor_sw128(smem_b + stage * Q_B_STAGE_BYTES);
@@ -578,6 +670,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmS
           }
         }
         umma_commit_pair(acc_full(b));
+        GC_GTRACE(1, 4 * lt + 2);
       }
     }
   } else {
@@ -588,7 +681,9 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmS
     pdl_wait();
     const float alpha = ep.alpha_dev != nullptr ? __ldg(ep.alpha_dev) : 1.0f;
     const uint32_t stage_smem = smem_base + Q_STAGING_OFFSET + static_cast<uint32_t>(warp - 2) * 8192u;
+    const uint32_t gather_smem = shape.gather_staged ? smem_base + Q_GATHER_OFFSET + static_cast<uint32_t>(warp - 2) * 2048u : 0u;
     int stage_use = 0;
+    int etrace_ev = 0;
     int lt = 0;
     for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++lt) {
       const int n_blk = tile % shape.n_tiles, m_pair = tile / shape.n_tiles;
@@ -598,12 +693,20 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmS
       const float* bias_ptr = ep.bias != nullptr ? bias_s + b * QBN + half * HALF : nullptr;
       const int col_base = n_blk * QBN + half * HALF;
       const uint32_t taddr = tmem_base + b * QBN + half * HALF + lane_addr;
-      mbar_wait(acc_full(b), (lt >> 1) & 1);
-      tc_fence_after();
-      const uint32_t acc_bar = acc_empty(b);
+      const uint32_t acc_bar = acc_empty(b), full_bar_b = acc_full(b);
+      const uint32_t full_parity = (lt >> 1) & 1;
       epilogue_warp_tile<HALF>(ep, &maps.out, shape.store_mode, alpha, taddr, bias_ptr,
                                static_cast<int64_t>(m_pair) * 256 + rank * 128 + q * 32, col_base, lane, stage_smem, stage_use,
-                               [&]() { if (lane == 0) mbar_arrive_cluster(acc_bar, 0); });
+                               gather_smem,
+                               [&]() {
+                                 if (threadIdx.x == 64) GC_GTRACE(2, 4 * lt);
+                                 mbar_wait(full_bar_b, full_parity);
+                                 if (threadIdx.x == 64) GC_GTRACE(2, 4 * lt + 1);
+                                 tc_fence_after();
+                               },
+                               [&]() { if (lane == 0) mbar_arrive_cluster(acc_bar, 0); },
+                               (trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64) ? trace : nullptr, &etrace_ev);
+      if (threadIdx.x == 64) GC_GTRACE(2, 4 * lt + 2);
     }
     if (lane == 0) bulk_wait_group_all();
   }
@@ -681,6 +784,7 @@ int launch_cfg(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams&
   GemmShape shape;
   shape.num_segments = a.num_segments;
   shape.store_mode = STORE_DIRECT;
+  shape.gather_staged = 0;
   shape.n_tiles = a.n / BN;
   for (int s = 0; s < GC_MAX_SEGMENTS; ++s) shape.kblocks[s] = 0;
   for (int s = 0; s < a.num_segments; ++s) {
@@ -707,7 +811,7 @@ int launch_cfg(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams&
   return GC_OK;
 }
 
-int fill_out_map(GemmMaps& maps, GemmShape& shape, const gc_gemm_args& a);
+int fill_out_map(GemmMaps& maps, GemmShape& shape, const gc_gemm_args& a, bool can_stage_gathers);
 
 template <int PBN>
 int launch_persistent(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
@@ -729,7 +833,7 @@ int launch_persistent(cudaStream_t stream, const gc_gemm_args& a, const Epilogue
     maps.w[s] = maps.w[0];
   }
   {
-    const int rc = fill_out_map(maps, shape, a);
+    const int rc = fill_out_map(maps, shape, a, C::GATHER_BYTES != 0);
     if (rc != GC_OK) return rc;
   }
   GC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_persistent_kernel<PBN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -773,7 +877,7 @@ int launch_pair(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams
     maps.w[s] = maps.w[0];
   }
   {
-    const int rc = fill_out_map(maps, shape, a);
+    const int rc = fill_out_map(maps, shape, a, true);
     if (rc != GC_OK) return rc;
   }
   GC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES),
@@ -795,21 +899,29 @@ int launch_pair(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  GC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_pair_kernel, maps, shape, ep, (int)num_tiles),
+  GC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_pair_kernel, maps, shape, ep, (int)num_tiles, g_gemm_trace),
                 "gemm_bf16_tcgen05_pair_kernel");
   return GC_OK;
 }
 
 // STORE_TMA / STORE_TMA_ADD when the fused epilogue is bias + activation (+ in-place fp32 residual) only.
-int choose_store_mode(const gc_gemm_args& a) {
-  if (a.addend != nullptr || a.gather_src[0] != nullptr || a.gather_src[1] != nullptr) return STORE_DIRECT;
+bool gathers_stageable(const gc_gemm_args& a) {
+  // bf16 tables, first slot used, 16-byte aligned rows (checked by gc_gemm), 256-wide column blocks stay inside a row
+  return a.gather_src[0] != nullptr && a.gather_dtype == GC_BF16;
+}
+
+int choose_store_mode(const gc_gemm_args& a, bool can_stage_gathers) {
+  const bool has_gather = a.gather_src[0] != nullptr || a.gather_src[1] != nullptr;
+  if (a.addend != nullptr) return STORE_DIRECT;
+  if (has_gather && !(can_stage_gathers && gathers_stageable(a))) return STORE_DIRECT;
   if (a.residual == nullptr) return STORE_TMA;
   if (a.residual == a.out && a.res_dtype == GC_F32 && a.out_dtype == GC_F32 && a.ld_res == a.ldo) return STORE_TMA_ADD;
   return STORE_DIRECT;
 }
 
-int fill_out_map(GemmMaps& maps, GemmShape& shape, const gc_gemm_args& a) {
-  shape.store_mode = choose_store_mode(a);
+int fill_out_map(GemmMaps& maps, GemmShape& shape, const gc_gemm_args& a, bool can_stage_gathers) {
+  shape.store_mode = choose_store_mode(a, can_stage_gathers);
+  shape.gather_staged = (shape.store_mode != STORE_DIRECT && a.gather_src[0] != nullptr) ? 1 : 0;
   if (shape.store_mode == STORE_DIRECT) {
     maps.out = maps.a[0];
     return GC_OK;
@@ -818,6 +930,7 @@ int fill_out_map(GemmMaps& maps, GemmShape& shape, const gc_gemm_args& a) {
 }
 
 int launch_gemm_tcgen05(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
+
   // Fewer than ~2 CTAs per SM with 128-wide tiles: halve the tile width to spread the work.
   const int64_t tiles128 = ((a.m + BM - 1) / BM) * (a.n / 128);
   if (tiles128 >= 2 * 148) {
@@ -836,7 +949,7 @@ int launch_gemm_tcgen05(cudaStream_t stream, const gc_gemm_args& a, const Epilog
 
 }  // namespace gc
 
-// Debug hook (not part of the public header): clock-stamp buffer of at least 3 * 512 int64.
+// Debug hook (not part of the public header): clock-stamp buffer of at least 8 * 512 int64.
 extern "C" __attribute__((visibility("default"))) void gc_debug_set_gemm_trace(void* ptr) {
   gc::g_gemm_trace = reinterpret_cast<long long*>(ptr);
 }

@@ -220,12 +220,15 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                ::"r"(bar), "h"(static_cast<uint16_t>(3))
                : "memory");
 }
-// Arrive on the barrier at the same offset in CTA `target` of the cluster.
+// Arrive on the barrier at the same offset in CTA `target` of the cluster.  Relaxed: the callers
+// order what the waiter depends on themselves (tcgen05.wait::ld + tcgen05.fence::before_thread_sync
+// for TMEM reads); a .release.cluster arrive costs a MEMBAR.ALL + ERRBAR that waits for every
+// outstanding memory operation of the thread (20 % of the pair kernel's stall samples).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t target) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(target)
       : "memory");
 }

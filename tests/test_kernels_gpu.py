@@ -102,6 +102,37 @@ def test_gemm_large_staged_store_paths(cuda_device, m, n, k):
     assert _rel(big[:, :n].cpu(), ref) < 1e-2 and torch.all(big[:, n:] == 0)
 
 
+@pytest.mark.parametrize("m,n,k,two", [(40001, 512, 128, True), (20000, 256, 64, True), (30000, 512, 64, False),
+                                       (40001, 384, 64, True)])
+def test_gemm_large_staged_gathers(cuda_device, m, n, k, two):
+    """Edge-MLP shape (common/typed_graph_net.py:134-159): e @ W1e + P_s[senders] + P_r[receivers], swish.
+    At these sizes the CTA-pair / persistent kernels run and the row gathers go through the
+    shared-memory transposition; m is not a multiple of the tile so the last tile is ragged."""
+    from gencast_flax_nnx_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(m + n)
+    ns, nr = 5000, 1237
+    a = torch.randn(m, k, generator=g).to(torch.bfloat16)
+    w = (torch.randn(n, k, generator=g) / math.sqrt(k)).to(torch.bfloat16)
+    bias = torch.randn(n, generator=g)
+    gs = torch.randn(ns, n, generator=g).to(torch.bfloat16)
+    gr = torch.randn(nr, n, generator=g).to(torch.bfloat16)
+    si = torch.randint(0, ns, (m,), generator=g, dtype=torch.int32)
+    ri = torch.sort(torch.randint(0, nr, (m,), generator=g, dtype=torch.int32)).values
+    d = cuda_device
+    pre = a.double() @ w.double().t() + bias.double() + gs.double()[si.long()]
+    gathers = [(gs.to(d), si.to(d))]
+    if two:
+        pre = pre + gr.double()[ri.long()]
+        gathers.append((gr.to(d), ri.to(d)))
+    for out_dtype, tol in ((torch.bfloat16, 1e-2), (torch.float32, 3e-3)):
+        out = torch.full((m, n), float("nan"), dtype=out_dtype, device=d)
+        ops.gemm([(a.to(d), w.to(d))], out, bias=bias.to(d), act="swish", gathers=gathers)
+        assert _rel(out.cpu(), _swish(pre)) < tol
+    out = torch.full((m, n), float("nan"), dtype=torch.float32, device=d)
+    ops.gemm([(a.to(d), w.to(d))], out, bias=bias.to(d), gathers=gathers)
+    assert _rel(out.cpu(), pre) < 3e-5
+
+
 @pytest.mark.parametrize("cols", [128, 256, 512])
 @pytest.mark.parametrize("in_dtype,out_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
                                                 (torch.bfloat16, torch.float32)])
