@@ -1,13 +1,17 @@
 #!/usr/bin/env python
 """Benchmark of the GenCast sampling hot path (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--config nano|1deg|tiny] [--dtype bf16|f32]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1deg|nano|0p25deg|tiny] [--members-per-gpu B]
   python bench.py --impl reference ...      # the reference algorithm's CPU restatement (oracle/) on host cores
 
-One "step" = one 12 h forecast step of one ensemble member: the 20-level DPM-Solver++ 2S
-loop, 40 denoiser evaluations (the reference evaluates and discards the 40th; so do we).
-Members are independent: rank r runs member r (weak scaling, no collective on the data
-path); with N > 1 the per-step ensemble sum / sum-of-squares is all-reduced over NCCL.
+One "step" = one 12 h forecast step of the ensemble members resident on a GPU: the 20-level
+DPM-Solver++ 2S loop, 40 denoiser evaluations per member (the reference evaluates and discards
+the 40th; so do we).  Default workload = the configuration the north-star target is quoted on,
+GenCast 1 deg with BASELINE.json configs[3]'s sharding (32 members over 8 GPUs = 4 members per
+GPU, evaluated together: member-major row blocks through the same kernels); members are
+independent, so N GPUs run 4 N members (weak scaling, no collective on the data path; with
+N > 1 the per-step ensemble sum / sum-of-squares is all-reduced over NCCL).  The same line also
+carries configs[1] (nano-GenCast 2.5 deg, one member per GPU) under "also".
 `value` = members x steps / max-over-ranks device time with inputs resident in HBM.
 `e2e` = the same through GenCast.full_sampling with host Datasets (H2D of the step's
 inputs from pinned memory and D2H of the prediction inside the timed region).
@@ -107,14 +111,17 @@ def build_case(config: str, seed: int = 0, batch: int = 1):
 
 
 def workload_name(config: str) -> str:
-    return {"nano": "nano-GenCast 2.5deg (73x144 grid, mesh 4, L=256, 16 layers, k-hop 8), one member per GPU, "
+    return {"nano": "nano-GenCast 2.5deg (73x144 grid, mesh 4, L=256, 16 layers, k-hop 8), "
                     "12 h step = 20-level DPM-Solver++ 2S",
-            "1deg": "GenCast 1deg (181x360 grid, mesh 5, L=512, 16 layers, k-hop 8), one member per GPU, "
+            "1deg": "GenCast 1deg (181x360 grid, mesh 5, L=512, 16 layers, k-hop 8), "
                     "12 h step = 20-level DPM-Solver++ 2S",
-            "0p25deg": "GenCast 0.25deg (721x1440 grid, mesh 6, L=512, 16 layers, k-hop 8), one member per GPU, "
+            "0p25deg": "GenCast 0.25deg (721x1440 grid, mesh 6, L=512, 16 layers, k-hop 8), "
                        "12 h step = 20-level DPM-Solver++ 2S",
             "tiny": "test-size GenCast 10deg (19x36 grid, mesh 2, L=128, 2 layers), 12 h step = 20-level DPM-Solver++ 2S",
             }[config]
+
+
+DEFAULT_MEMBERS_PER_GPU = {"1deg": 4}      # BASELINE.json configs[3]: 32 members / 8 GPUs
 
 
 # ----------------------------------------------------------------------------------------------
@@ -138,9 +145,9 @@ def cpu_solver_iteration_seconds(case, repeats: int, warmup: int = 0):
         i += c
     frc, i = {}, 0
     for n, c in case["frc_layout"]:
-        frc[n] = torch.as_tensor(case["frc_nodes"][:, :, i:i + c])
+        frc[n] = torch.as_tensor(np.ascontiguousarray(case["frc_nodes"][:, :1, i:i + c]))      # one member
         i += c
-    inp = torch.as_tensor(case["inp_nodes"])
+    inp = torch.as_tensor(np.ascontiguousarray(case["inp_nodes"][:, :1]))
     st = case["arch"].sparse_transformer_config
     arch = dict(num_layers=st.num_layers, num_heads=st.num_heads)
     sig = [80.0, 60.0]
@@ -182,7 +189,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_iter * iters_per_step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.config), "members": 1},
+            "config": {"workload": workload_name(args.config), "members": 1,
+                       "note": "CPU arm: one member at a time; member-steps/s does not depend on how members are grouped"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -192,26 +200,16 @@ def run_reference(args):
 # GPU arm
 # ----------------------------------------------------------------------------------------------
 
-def run_gpu(args):
+def measure(args, config: str, MB: int, steps: int, warmup: int, dev, rank: int, world: int, detailed: bool):
+    """Device-timed steps, e2e steps and (detailed) the per-kernel roofline leg of one workload."""
     import torch
     import torch.distributed as dist
     from gencast_flax_nnx_b200 import configs, gencast, ops
     from gencast_flax_nnx_b200.engine import DenoiserEngine, SamplerEngine, noise_schedule
+    from gencast_flax_nnx_b200.parallel import EnsembleStatistics
     from gencast_flax_nnx_b200.rngs import Rngs
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep stdout to the single JSON line
-        dist.init_process_group("nccl", device_id=dev)
-
-    MB = args.members_per_gpu
-    case = build_case(args.config, batch=MB)
+    case = build_case(config, batch=MB)
     graphs = oracle_graph(case)
     eng = DenoiserEngine(graphs, case["arch"], case["params"], case["layout"], compute_dtype=args.dtype, device=dev,
                          members=MB)
@@ -221,9 +219,8 @@ def run_gpu(args):
     eng.set_constant_features(member_major(case["inp_nodes"]), member_major(case["frc_nodes"]))
     G, C = eng.Gt, eng.n_out
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
-    noises = [torch.randn(G, C, generator=gen, device=dev) for _ in range(max(args.steps, 1))]
+    noises = [torch.randn(G, C, generator=gen, device=dev) for _ in range(max(steps, 1))]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    from gencast_flax_nnx_b200.parallel import EnsembleStatistics
     stats = EnsembleStatistics((G, C), dev)
 
     def one_step(noise):
@@ -232,19 +229,19 @@ def run_gpu(args):
             # ensemble mean / spread over the members of all ranks: local accumulate kernel + one NCCL all-reduce
             stats.reset()
             stats.add(out)
-            stats.finalize(total_members=world)
+            stats.finalize(total_members=world * MB)
         return out
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         one_step(noises[i % len(noises)])
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    with ClockSampler(local_rank) as clocks:
-        for i in range(args.steps):
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    with ClockSampler(dev.index) as clocks:
+        for i in range(steps):
             flush.fill_(i & 0xFF)           # evict L2 between timed steps (not timed)
             starts[i].record()
             one_step(noises[i])
@@ -258,8 +255,9 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    value = world * MB * args.steps / (total_ms / 1e3)
-    clock_summary = clocks.summary()
+    res = {"value": world * MB * steps / (total_ms / 1e3), "ms_per_step": total_ms / steps, "clocks": clocks.summary(),
+           "members_per_gpu": MB, "evals": se.num_network_evaluations, "launches_per_step": se.launches_per_step,
+           "denoiser_fwd_ms": total_ms / steps / se.num_network_evaluations}
 
     # ---- e2e through the public API: host Datasets in, host Dataset out
     sc = configs.SamplerConfig(stochastic_churn_rate=0.0)
@@ -269,7 +267,7 @@ def run_gpu(args):
     model.denoiser._grid_key = (np.asarray(case["inputs"].coords["lat"]).tobytes(),
                                 np.asarray(case["inputs"].coords["lon"]).tobytes())
     model._sampler._engine = se
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(steps, 5))
     for _ in range(2):
         model.full_sampling(case["inputs"], case["targets"], case["forcings"])
     torch.cuda.synchronize()
@@ -277,20 +275,22 @@ def run_gpu(args):
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        pred = model.full_sampling(case["inputs"], case["targets"], case["forcings"])
+        model.full_sampling(case["inputs"], case["targets"], case["forcings"])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * MB * e2e_steps / float(t.item())
-    h2d = sum(int(np.prod(v.shape)) for ds in (case["inputs"], case["forcings"]) for v in ds.data_vars.values()) * 4
-    d2h = C * G * 4
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    res["e2e"] = {"value": world * MB * e2e_steps / float(t.item()), "unit": UNIT,
+                  "h2d_bytes_per_step": sum(int(np.prod(v.shape)) for ds in (case["inputs"], case["forcings"])
+                                            for v in ds.data_vars.values()) * 4,
+                  "d2h_bytes_per_step": C * G * 4, "steps": e2e_steps,
+                  "api": "GenCast.full_sampling(inputs, targets_template, forcings)"}
+    res["case"] = case
+    if not detailed or rank != 0:
+        del model, se, eng, stats, flush, noises
+        torch.cuda.empty_cache()
+        return res
 
     # ---- roofline leg (rank 0): CUDA-event pair around every launch of denoiser evaluations of the
     # sampling step, replayed eagerly.  The launches are enqueued behind a device-side delay so that
@@ -300,12 +300,11 @@ def run_gpu(args):
     rec = ops.Recorder()
     se.sample(noises[0], use_graph=False)
     torch.cuda.synchronize()
-    G1 = eng.n_out
     for j in (3, 17, 31):                                   # three noise levels of the schedule
         torch.cuda._sleep(int(2.5e7))                       # ~13 ms of head start for the host
         ops.set_recorder(rec)
         f = eng.forward(se.ctx[j])
-        ops.dpm_update(f, se.x, se.x, se.sched[j], se.x_mid, eng.xin, G1)
+        ops.dpm_update(f, se.x, se.x, se.sched[j], se.x_mid, eng.xin, C)
         ops.set_recorder(None)
         torch.cuda.synchronize()
     agg = rec.summary()
@@ -327,9 +326,16 @@ def run_gpu(args):
     else:
         roof = {"kernel": dom, "bound": "hbm", "achieved": domk["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": domk["gbs"] / peaks["hbm"], "traffic": None}
-    roof["peak_source"] = peaks["source"] + (" (sustained bf16 GEMM)" if tensor_bound else " (copy bandwidth)")
+    roof["peak_source"] = peaks["source"] + (" (sustained bf16 GEMM: the kernel is timed inside a long step)"
+                                             if tensor_bound else " (copy bandwidth)")
     roof["avg_launch_us"] = domk["avg_us"]
     roof["share_of_step"] = domk["share"]
+    # whole-evaluation figure: algorithmic FLOPs of one member's forward (exact k-hop attention)
+    f_alg = algorithmic_flops(eng)
+    roof["forward_alg_tflops_per_member"] = f_alg / 1e12
+    roof["forward_achieved_tflops"] = MB * f_alg / (res["denoiser_fwd_ms"] * 1e-3) / 1e12
+    roof["forward_frac_of_peak"] = roof["forward_achieved_tflops"] / peaks["tensor_sustained"]
+    res["roofline"], res["kernels"] = roofline_clean(roof), kernels
 
     # ---- single denoiser evaluation latency (graph-free, events)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -341,35 +347,84 @@ def run_gpu(args):
         eng.forward(ctx)
     b.record()
     torch.cuda.synchronize()
-    fwd_ms_eager = a.elapsed_time(b) / 10
-    fwd_ms_graph = total_ms / args.steps / se.num_network_evaluations
+    res["denoiser_fwd_ms_eager_launch"] = a.elapsed_time(b) / 10
+    del model, se, eng, stats, flush, noises
+    torch.cuda.empty_cache()
+    return res
+
+
+def algorithmic_flops(eng) -> float:
+    """F_alg of one member's denoiser evaluation: every MLP as 2 n (i h + h o) with the reference's
+    operand widths ([e|s|r] = 3L, [n|agg] = 2L), attention at the exact k-hop nnz; the dead mesh-node MLP excluded."""
+    L, G, V, E1, E2, F, NL = eng.L, eng.G, eng.V, eng.E1, eng.E2, eng.F, eng.NL
+    cin = 3 + eng.layout.num_data_channels
+    mlp = lambda n, i, h, o: 2.0 * n * (i * h + h * o)
+    enc = mlp(G, cin, L, L) + mlp(V, cin, L, L) + mlp(E1, 4, L, L) + mlp(E1, 3 * L, L, L) + mlp(V, 2 * L, L, L) + mlp(G, L, L, L)
+    dec = mlp(E2, 4, L, L) + mlp(E2, 3 * L, L, L) + mlp(G, 2 * L, L, L) + mlp(G, L, L, eng.n_out)
+    nnz = eng.khop_nnz / eng.B
+    proc = NL * (8.0 * V * L * L + 4.0 * V * L * F + 4.0 * nnz * L)
+    return enc + proc + dec
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep stdout to the single JSON line
+        dist.init_process_group("nccl", device_id=dev)
+
+    MB = args.members_per_gpu
+    main = measure(args, args.config, MB, args.steps, args.warmup, dev, rank, world, detailed=True)
+    also = None
+    if args.config == "1deg" and not args.no_secondary:
+        # BASELINE.json configs[1]: nano-GenCast, one member per GPU (launch / latency bound: 139 kernels of ~8 us)
+        nano = measure(args, "nano", 1, max(args.steps, 3), 3, dev, rank, world, detailed=False)
+        also = {"nano_2p5deg_one_member_per_gpu": {
+            "workload": workload_name("nano"), "value": nano["value"], "unit": UNIT, "ms_per_step": nano["ms_per_step"],
+            "denoiser_fwd_ms": nano["denoiser_fwd_ms"], "e2e": nano["e2e"], "members": world}}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- CPU baseline beside it (bounded sample; rank 0, N = 1 only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        reps = 2 if args.config == "nano" else 1
-        times = cpu_solver_iteration_seconds(case, repeats=reps, warmup=1 if args.config != "1deg" else 0)
-        v = MB / (float(np.mean(times)) * 20)
+        case = main["case"]
+        reps = 2 if args.config in ("nano", "tiny") else 1
+        times = cpu_solver_iteration_seconds(case, repeats=reps, warmup=1 if args.config in ("nano", "tiny") else 0)
+        v = 1.0 / (float(np.mean(times)) * 20)
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": f"{reps} of the 20 solver iterations (2 denoiser evaluations each) of the torch-fp32 oracle "
-                         f"of the reference algorithm, all host threads; step time = 20 x mean iteration"}
+               "sample": f"{reps} of the 20 solver iterations (2 denoiser evaluations each) of one member, torch-fp32 oracle "
+                         f"of the reference algorithm, all host threads; member-step time = 20 x mean iteration"}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    line = {"metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload_name(args.config), "members": world * MB, "members_per_gpu": MB,
-                       "denoiser_evaluations_per_step": se.num_network_evaluations,
+                       "denoiser_evaluations_per_step": main["evals"],
                        "weights": "random N(0, 1/fan_in) (reference init makes the transformer an identity)",
                        "l2": "flushed between timed steps (256 MiB write, not timed)",
                        "execution": "one CUDA graph per 12 h step",
                        "collective": "nccl all_reduce of ensemble sum / sum-of-squares per step" if world > 1 else "none"},
-            "denoiser_fwd_ms": fwd_ms_graph, "denoiser_fwd_ms_eager_launch": fwd_ms_eager,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "GenCast.full_sampling(inputs, targets_template, forcings)"},
-            "gpu_launches": args.steps * se.launches_per_step,
-            "clocks": clock_summary, "roofline": roofline_clean(roof), "kernels": kernels,
+            "denoiser_fwd_ms": main["denoiser_fwd_ms"], "denoiser_fwd_ms_per_member": main["denoiser_fwd_ms"] / MB,
+            "denoiser_fwd_ms_eager_launch": main["denoiser_fwd_ms_eager_launch"],
+            "e2e": main["e2e"],
+            "gpu_launches": args.steps * main["launches_per_step"],
+            "clocks": main["clocks"], "roofline": main["roofline"], "kernels": main["kernels"],
             "kernels_note": "per-launch device durations from CUDA-event pairs around each launch of 3 eagerly "
                             "replayed denoiser evaluations (queued behind a device delay); shares are of their sum"}
+    if also is not None:
+        line["also"] = also
     if cpu is not None:
         line["cpu_baseline"] = cpu
     emit(line)
@@ -402,12 +457,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
-    ap.add_argument("--config", default="nano", choices=["tiny", "nano", "1deg", "0p25deg"])
+    ap.add_argument("--config", default="1deg", choices=["tiny", "nano", "1deg", "0p25deg"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--members-per-gpu", type=int, default=1,
-                    help="ensemble members evaluated together on each GPU (default 1 = BASELINE configs[1])")
+    ap.add_argument("--members-per-gpu", type=int, default=None,
+                    help="ensemble members evaluated together on each GPU (default: 4 for 1deg = BASELINE configs[3]'s "
+                         "32 members / 8 GPUs, 1 otherwise)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the nano (configs[1]) measurement in the 1deg run")
     args = ap.parse_args()
+    if args.members_per_gpu is None:
+        args.members_per_gpu = DEFAULT_MEMBERS_PER_GPU.get(args.config, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
