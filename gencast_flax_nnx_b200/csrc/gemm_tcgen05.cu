@@ -85,7 +85,8 @@ struct GemmShape {
 // row-per-thread layout of the accumulator, and added in fp32.  A thread-per-row global load touches
 // 32 lines per instruction and made the L1 tag stage the bottleneck of the edge GEMMs (2.8 x the time
 // of the same GEMM without gathers); this way it is 8.  Loads run one 32-column chunk ahead.
-template <int HALF, typename WaitAcc, typename Release>
+// NBUF: staging buffers of 4 KB per warp (2 = a TMA store may still be reading one while the next is filled).
+template <int HALF, int NBUF = 2, typename WaitAcc, typename Release>
 __device__ __forceinline__ void epilogue_warp_tile(const EpilogueParams& ep, const CUtensorMap* out_map, int store_mode,
                                                    float alpha, uint32_t taddr, const float* bias_ptr, int64_t row0,
                                                    int col_base, int lane, uint32_t stage_smem, int& stage_use,
@@ -208,11 +209,11 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpilogueParams& ep, con
       const int half_chunk = (c >> 5) & 1;
       if (half_chunk == 0) {
         // first half of a new chunk: the buffer's previous store must have finished reading it
-        if (lane == 0) bulk_wait_group_read<1>();
+        if (lane == 0) bulk_wait_group_read<NBUF - 1>();
         __syncwarp();
       }
       GC_ESTAMP();               // staging buffer free
-      const uint32_t buf = stage_smem + static_cast<uint32_t>(stage_use & 1) * 4096u + static_cast<uint32_t>(lane) * 128u;
+      const uint32_t buf = stage_smem + static_cast<uint32_t>(stage_use & (NBUF - 1)) * 4096u + static_cast<uint32_t>(lane) * 128u;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         uint32_t pk[4];
@@ -229,7 +230,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpilogueParams& ep, con
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(out_map, stage_smem + static_cast<uint32_t>(stage_use & 1) * 4096u, col_base + (c & ~63), static_cast<int>(row0));
+          tma_store_2d(out_map, stage_smem + static_cast<uint32_t>(stage_use & (NBUF - 1)) * 4096u, col_base + (c & ~63), static_cast<int>(row0));
           bulk_commit_group();
         }
         ++stage_use;
@@ -237,9 +238,9 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpilogueParams& ep, con
       GC_ESTAMP();               // chunk stored / TMA store issued
     } else {
       // 32 fp32 = 128 B = one full row of a 32-column chunk
-      if (lane == 0) bulk_wait_group_read<1>();
+      if (lane == 0) bulk_wait_group_read<NBUF - 1>();
       __syncwarp();
-      const uint32_t buf = stage_smem + static_cast<uint32_t>(stage_use & 1) * 4096u + static_cast<uint32_t>(lane) * 128u;
+      const uint32_t buf = stage_smem + static_cast<uint32_t>(stage_use & (NBUF - 1)) * 4096u + static_cast<uint32_t>(lane) * 128u;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const uint32_t unit = static_cast<uint32_t>(u) ^ sw;
@@ -250,7 +251,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpilogueParams& ep, con
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        const uint32_t src = stage_smem + static_cast<uint32_t>(stage_use & 1) * 4096u;
+        const uint32_t src = stage_smem + static_cast<uint32_t>(stage_use & (NBUF - 1)) * 4096u;
         if (store_mode == STORE_TMA_ADD) tma_reduce_add_2d(out_map, src, col_base + c, static_cast<int>(row0));
         else tma_store_2d(out_map, src, col_base + c, static_cast<int>(row0));
         bulk_commit_group();
@@ -716,6 +717,164 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmS
   if (warp == 1) tmem_dealloc_pair(tmem_base, 2 * QBN);
 }
 
+// ---------------------------------------------------------------------------------------------
+// A-resident CTA-pair variant for single-segment problems with K <= 512 (the QKV / out-projection /
+// FFW-in GEMMs of the transformer and the K = L node / edge MLP layers): an experiment, opt-in.  The
+// 256 x 256 pair tile pulls 32 KB per CTA per 64-wide k-block from L2, i.e. 64 B/clk/SM at the tensor
+// peak, 9.5 KB/clk chip-wide.  Here each pair walks a contiguous range of the (m, n) tile order
+// with n fastest, keeps its 128 rows x K of A in shared memory (8 x 16 KB) for all the n-tiles of that
+// row block and streams only its half of the W tile (16 KB per k-block): 32 B/clk/SM.  A k-block slots
+// are released one by one during the last n-tile of a row block, so the next block's A streams in under
+// the running MMAs.  W ring of 3 stages, one 4 KB store-staging buffer per epilogue warp.
+// ---------------------------------------------------------------------------------------------
+constexpr int R_KB_MAX = 8;
+constexpr int R_STAGES = 3;
+constexpr int R_A_BYTES = R_KB_MAX * A_STAGE_BYTES;                  // 128 KB
+constexpr int R_B_STAGE_BYTES = 128 * BK * 2;
+constexpr int R_STAGING_OFFSET = R_A_BYTES + R_STAGES * R_B_STAGE_BYTES;
+constexpr int R_BAR_OFFSET = R_STAGING_OFFSET + 8 * 4096;
+constexpr int R_BIAS_OFFSET = R_BAR_OFFSET + 256;
+constexpr int R_SMEM_BYTES = R_BIAS_OFFSET + 2 * QBN * 4 + 1024;
+
+__global__ void __launch_bounds__(P_THREADS, 1)
+gemm_bf16_tcgen05_pair_resident_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shape, const EpilogueParams ep,
+                                       const int num_tiles) {
+  using namespace sm100;
+  pdl_launch_dependents();
+  constexpr int HALF = QBN / 2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + R_A_BYTES;
+  const uint32_t bars = smem_base + R_BAR_OFFSET;
+  float* bias_s = reinterpret_cast<float*>(smem_gen + R_BIAS_OFFSET);      // [2][QBN]
+  auto a_full = [&](int kb) { return bars + 8u * kb; };
+  auto a_empty = [&](int kb) { return bars + 8u * (R_KB_MAX + kb); };
+  auto b_full = [&](int s) { return bars + 8u * (2 * R_KB_MAX + s); };
+  auto b_empty = [&](int s) { return bars + 8u * (2 * R_KB_MAX + R_STAGES + s); };
+  auto acc_full = [&](int b) { return bars + 8u * (2 * R_KB_MAX + 2 * R_STAGES + b); };
+  auto acc_empty = [&](int b) { return bars + 8u * (2 * R_KB_MAX + 2 * R_STAGES + 2 + b); };
+  const uint32_t tmem_ptr_smem = bars + 8u * (2 * R_KB_MAX + 2 * R_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();      // 0 = leader
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int KB = shape.kblocks[0];
+  const int t_begin = static_cast<int>(static_cast<int64_t>(pair_id) * num_tiles / num_pairs);
+  const int t_end = static_cast<int>(static_cast<int64_t>(pair_id + 1) * num_tiles / num_pairs);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&maps.a[0]);
+    prefetch_tensormap(&maps.w[0]);
+    for (int kb = 0; kb < R_KB_MAX; ++kb) { mbar_init(a_full(kb), 1); mbar_init(a_empty(kb), 1); }
+    for (int s = 0; s < R_STAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 16); }
+    fence_mbar_init();
+  }
+  __syncwarp();
+  cluster_sync_all();
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_ptr_smem, 2 * QBN);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      pdl_wait();
+      int stage = 0, group = -1, prev_m = -1;
+      uint32_t phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        const int n_blk = tile % shape.n_tiles, m_pair = tile / shape.n_tiles;
+        const bool new_group = m_pair != prev_m;
+        if (new_group) { ++group; prev_m = m_pair; }
+        const int m_row = m_pair * 256 + static_cast<int>(rank) * 128;
+        const int n_row = n_blk * QBN + static_cast<int>(rank) * 128;
+        for (int kb = 0; kb < KB; ++kb) {
+          if (new_group) {
+            mbar_wait(a_empty(kb), (static_cast<uint32_t>(group) & 1u) ^ 1u);
+            if (rank == 0) mbar_arrive_expect_tx(a_full(kb), 2 * A_STAGE_BYTES);
+            tma_load_2d_pair(smem_a + kb * A_STAGE_BYTES, &maps.a[0], a_full(kb), kb * BK, m_row);
+          }
+          mbar_wait(b_empty(stage), phase ^ 1u);
+          if (rank == 0) mbar_arrive_expect_tx(b_full(stage), 2 * R_B_STAGE_BYTES);
+          tma_load_2d_pair(smem_b + stage * R_B_STAGE_BYTES, &maps.w[0], b_full(stage), kb * BK, n_row);
+          if (++stage == R_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = idesc_bf16_f32(256, QBN, 0, 0);
+      int stage = 0, group = -1, prev_m = -1, lt = 0;
+      uint32_t phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
+        const int m_pair = tile / shape.n_tiles;
+        const bool new_group = m_pair != prev_m;
+        if (new_group) { ++group; prev_m = m_pair; }
+        const bool last_of_group = tile + 1 == t_end || (tile + 1) / shape.n_tiles != m_pair;
+        const int b = lt & 1;
+        mbar_wait(acc_empty(b), ((lt >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < KB; ++kb) {
+          if (new_group) mbar_wait(a_full(kb), static_cast<uint32_t>(group) & 1u);
+          mbar_wait(b_full(stage), phase);
+          tc_fence_after();
+          const uint64_t da = desc_kmajor_sw128(smem_a + kb * A_STAGE_BYTES);
+          const uint64_t db = desc_kmajor_sw128(smem_b + stage * R_B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            umma_f16_pair(tmem_base + b * QBN, da + 2u * k, db + 2u * k, idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit_pair(b_empty(stage));
+          if (last_of_group) umma_commit_pair(a_empty(kb));     // this A k-block is free in both CTAs
+          if (++stage == R_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(acc_full(b));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    pdl_wait();
+    const float alpha = ep.alpha_dev != nullptr ? __ldg(ep.alpha_dev) : 1.0f;
+    const uint32_t stage_smem = smem_base + R_STAGING_OFFSET + static_cast<uint32_t>(warp - 2) * 4096u;
+    int stage_use = 0;
+    int lt = 0;
+    for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
+      const int n_blk = tile % shape.n_tiles, m_pair = tile / shape.n_tiles;
+      const int b = lt & 1;
+      if (et < QBN) bias_s[b * QBN + et] = ep.bias != nullptr ? __ldg(ep.bias + n_blk * QBN + et) : 0.0f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float* bias_ptr = ep.bias != nullptr ? bias_s + b * QBN + half * HALF : nullptr;
+      const int col_base = n_blk * QBN + half * HALF;
+      const uint32_t taddr = tmem_base + b * QBN + half * HALF + lane_addr;
+      const uint32_t acc_bar = acc_empty(b), full_bar_b = acc_full(b);
+      const uint32_t full_parity = (lt >> 1) & 1;
+      epilogue_warp_tile<HALF, 1>(ep, &maps.out, shape.store_mode, alpha, taddr, bias_ptr,
+                                  static_cast<int64_t>(m_pair) * 256 + rank * 128 + q * 32, col_base, lane, stage_smem, stage_use,
+                                  0u, [&]() { mbar_wait(full_bar_b, full_parity); tc_fence_after(); },
+                                  [&]() { if (lane == 0) mbar_arrive_cluster(acc_bar, 0); });
+    }
+    if (lane == 0) bulk_wait_group_all();
+  }
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 2 * QBN);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -904,6 +1063,58 @@ int launch_pair(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams
   return GC_OK;
 }
 
+// Opt-in (GENCAST_GEMM_ARES=1): measured on B200 at M = 40 968 it halves the L2 -> SM operand bytes but is
+// time-neutral (QKV 65.0 vs 60.8 us, FFW-in 89.9 vs 92.2 us, M = 260 640 N = K = 512: 138.5 vs 140.6 us), i.e. the
+// operand feed is not what holds the pair kernel at ~87 % MMA issue inside a tile; see profiles/README.md.
+bool resident_kernel_enabled() {
+  static const bool on = []() {
+    const char* v = getenv("GENCAST_GEMM_ARES");
+    return v != nullptr && v[0] == '1';
+  }();
+  return on;
+}
+
+int launch_pair_resident(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
+  GemmMaps maps;
+  GemmShape shape;
+  shape.num_segments = 1;
+  shape.n_tiles = a.n / QBN;
+  for (int s = 0; s < GC_MAX_SEGMENTS; ++s) shape.kblocks[s] = 0;
+  shape.kblocks[0] = a.k[0] / BK;
+  int rc = make_tmap_bf16_2d(&maps.a[0], a.a[0], (uint64_t)a.m, (uint64_t)a.k[0], (uint64_t)a.lda[0], BK, BM);
+  if (rc != GC_OK) return rc;
+  rc = make_tmap_bf16_2d(&maps.w[0], a.w[0], (uint64_t)a.n, (uint64_t)a.k[0], (uint64_t)a.ldw[0], BK, 128);
+  if (rc != GC_OK) return rc;
+  for (int s = 1; s < GC_MAX_SEGMENTS; ++s) {
+    maps.a[s] = maps.a[0];
+    maps.w[s] = maps.w[0];
+  }
+  rc = fill_out_map(maps, shape, a, false);
+  if (rc != GC_OK) return rc;
+  GC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     R_SMEM_BYTES), "cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_resident_kernel)");
+  const int64_t num_tiles = ((a.m + 255) / 256) * shape.n_tiles;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t pairs = sms / 2;
+  if (num_tiles < pairs) pairs = num_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(P_THREADS);
+  cfg.dynamicSmemBytes = R_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  GC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_pair_resident_kernel, maps, shape, ep, (int)num_tiles),
+                "gemm_bf16_tcgen05_pair_resident_kernel");
+  return GC_OK;
+}
+
 // STORE_TMA / STORE_TMA_ADD when the fused epilogue is bias + activation (+ in-place fp32 residual) only.
 bool gathers_stageable(const gc_gemm_args& a) {
   // bf16 tables, first slot used, 16-byte aligned rows (checked by gc_gemm), 256-wide column blocks stay inside a row
@@ -936,7 +1147,13 @@ int launch_gemm_tcgen05(cudaStream_t stream, const gc_gemm_args& a, const Epilog
   if (tiles128 >= 2 * 148) {
     // 256-wide tiles when N allows it and there are still >= 2 tiles per SM
     if (a.n % 256 == 0 && tiles128 >= 4 * 148) {
-      if (pair_kernel_enabled()) return launch_pair(stream, a, ep);
+      if (pair_kernel_enabled()) {
+        const bool has_gather = a.gather_src[0] != nullptr || a.gather_src[1] != nullptr;
+        if (resident_kernel_enabled() && a.num_segments == 1 && a.k[0] <= R_KB_MAX * BK && a.n / QBN >= 2 && !has_gather &&
+            a.addend == nullptr)
+          return launch_pair_resident(stream, a, ep);
+        return launch_pair(stream, a, ep);
+      }
       return launch_persistent<256>(stream, a, ep);
     }
     return launch_persistent<128>(stream, a, ep);
