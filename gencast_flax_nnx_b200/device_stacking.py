@@ -10,6 +10,7 @@ inside its jitted function (xarray_jax + jnp transposes); doing it in numpy cost
 """
 from __future__ import annotations
 
+import weakref
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -18,6 +19,28 @@ import torch
 from .xarray_lite import DataArray, Dataset
 
 PRESERVED = ("batch", "lat", "lon")
+MAX_LEASED_OUTPUT_BUFFERS = 4
+
+
+def pin_dataset(ds: Dataset) -> Dataset:
+    """Copy of `ds` whose arrays live in page-locked host memory (what a loader that feeds the GPU
+    would allocate).  DeviceStacker.to_nodes then copies each variable host -> device straight from
+    the caller's arrays, without the packing memcpy through its own pinned staging buffer."""
+    out = {}
+    for name, v in ds.data_vars.items():
+        a = np.ascontiguousarray(v.data, dtype=np.float32)
+        t = torch.empty(a.shape, dtype=torch.float32, pin_memory=True)
+        t.numpy()[...] = a
+        out[name] = DataArray(t.numpy(), v.dims)
+    return Dataset(out, ds.coords)
+
+
+def _pinned_f32(a) -> Optional[torch.Tensor]:
+    """torch view of a numpy array if it is contiguous fp32 in page-locked memory, else None."""
+    if not isinstance(a, np.ndarray) or a.dtype != np.float32 or not a.flags.c_contiguous or a.size == 0:
+        return None
+    t = torch.from_numpy(a)
+    return t if t.is_pinned() else None
 
 
 class _Plan:
@@ -44,6 +67,9 @@ class DeviceStacker:
         self.device = torch.device(device)
         self._plans = {}
         self._pinned = {}
+        self._devbuf = {}
+        self._out_pool = {}         # numel -> free pinned output buffers
+        self._out_leased = 0
 
     def _plan(self, key: str, ds: Dataset, sizes) -> _Plan:
         names = sorted(ds.keys())
@@ -63,10 +89,27 @@ class DeviceStacker:
             return torch.zeros(n_lat * n_lon, B, 0, dtype=torch.float32, device=self.device)
         pin = self._pinned[key]
         host = pin.numpy()
+        dev = self._devbuf.get(key)
+        if dev is None or dev.numel() != pin.numel():
+            dev = torch.empty(pin.numel(), dtype=torch.float32, device=self.device)
+            self._devbuf[key] = dev
+        # Variables already in page-locked memory go host -> device directly; the rest are packed into
+        # the stacker's pinned buffer first and moved with one copy per contiguous packed run.
+        run_start = None
         for name, off, shape, dims, c in plan.entries:
             n = int(np.prod(shape, dtype=np.int64))
-            host[off:off + n] = np.asarray(ds[name].data, dtype=np.float32).reshape(-1)
-        dev = pin.to(self.device, non_blocking=True)
+            direct = _pinned_f32(ds[name].data)
+            if direct is not None:
+                if run_start is not None:
+                    dev[run_start:off].copy_(pin[run_start:off], non_blocking=True)
+                    run_start = None
+                dev[off:off + n].copy_(direct.view(-1), non_blocking=True)
+            else:
+                host[off:off + n] = np.asarray(ds[name].data, dtype=np.float32).reshape(-1)
+                if run_start is None:
+                    run_start = off
+        if run_start is not None:
+            dev[run_start:plan.total].copy_(pin[run_start:plan.total], non_blocking=True)
         blocks = []
         for name, off, shape, dims, c in plan.entries:
             n = int(np.prod(shape, dtype=np.int64))
@@ -110,17 +153,39 @@ class DeviceStacker:
         if i != nodes.shape[-1]:
             raise ValueError(f"Expected {i} channels but found {nodes.shape[-1]}")
         flat = torch.cat(pieces)
-        key = ("out", flat.numel())
-        pin = self._pinned.get(key)
-        if pin is None:
-            pin = torch.empty(flat.numel(), dtype=torch.float32, pin_memory=True)
-            self._pinned[key] = pin
+        pin, leased = self._lease_output(flat.numel())
         pin.copy_(flat, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         host = pin.numpy()
+        if leased:
+            # The returned arrays are views of this page-locked buffer (no second host copy).  The buffer
+            # goes back to the pool when the last view of it is garbage collected; a caller that keeps
+            # results alive simply keeps their buffers, and past MAX_LEASED_OUTPUT_BUFFERS outstanding
+            # results the arrays are copied into ordinary memory instead.
+            weakref.finalize(host, self._release_output, pin)
         out, off = {}, 0
         for name, shape, dims in meta:
             n = int(np.prod(shape, dtype=np.int64))
-            out[name] = DataArray(host[off:off + n].reshape(shape).copy(), dims)
+            view = host[off:off + n].reshape(shape)
+            out[name] = DataArray(view if leased else view.copy(), dims)
             off += n
         return Dataset(out, template.coords)
+
+    def _lease_output(self, numel: int):
+        free = self._out_pool.setdefault(numel, [])
+        if free:
+            self._out_leased += 1
+            return free.pop(), True
+        if self._out_leased < MAX_LEASED_OUTPUT_BUFFERS:
+            self._out_leased += 1
+            return torch.empty(numel, dtype=torch.float32, pin_memory=True), True
+        key = ("out_copy", numel)
+        pin = self._pinned.get(key)
+        if pin is None:
+            pin = torch.empty(numel, dtype=torch.float32, pin_memory=True)
+            self._pinned[key] = pin
+        return pin, False
+
+    def _release_output(self, pin: torch.Tensor) -> None:
+        self._out_leased -= 1
+        self._out_pool.setdefault(pin.numel(), []).append(pin)

@@ -183,3 +183,34 @@ def test_batched_members_equal_single_member_runs(cuda_device, dtype):
     for b in range(B):
         assert np.abs(got[b] - single[b]).max() <= tol * np.abs(single[b]).max()
         assert np.abs(got_s[b] - single_s[b]).max() <= 10 * tol * np.abs(single_s[b]).max()
+
+
+def test_device_stacker_pinned_inputs_and_leased_outputs(cuda_device):
+    """Host edge of the public API: Datasets in page-locked memory are copied host -> device directly
+    (same result as the packed path), and predictions are views of leased page-locked buffers that stay
+    intact while the caller holds them and are reused once dropped."""
+    import gc
+    from gencast_flax_nnx_b200 import device_stacking, stacking
+    case = make_case("tiny")
+    st = device_stacking.DeviceStacker(cuda_device)
+    sizes = dict(case.targets.sizes)
+    a = st.to_nodes("inputs", case.inputs, sizes).clone()
+    b = st.to_nodes("inputs", device_stacking.pin_dataset(case.inputs), sizes)
+    assert torch.equal(a, b)
+    ref, _ = stacking.dataset_to_nodes(case.inputs, sizes)
+    np.testing.assert_array_equal(a.cpu().numpy(), ref)
+    tgt_nodes, _ = stacking.dataset_to_nodes(case.targets, sizes)
+    n1 = torch.from_numpy(tgt_nodes).to(cuda_device)
+    d1 = st.from_nodes(n1, case.targets)
+    held = {k: v.data for k, v in d1.items()}
+    snap = {k: v.copy() for k, v in held.items()}
+    outs = [st.from_nodes(n1 * float(i + 2), case.targets) for i in range(device_stacking.MAX_LEASED_OUTPUT_BUFFERS + 2)]
+    for k in held:                                   # earlier results are untouched by later calls
+        np.testing.assert_array_equal(held[k], snap[k])
+        np.testing.assert_array_equal(outs[-1][k].data, snap[k] * float(len(outs) + 1))
+        np.testing.assert_array_equal(snap[k], case.targets[k].data.astype(np.float32))
+    leased_before = st._out_leased
+    del outs, d1, held
+    gc.collect()
+    assert st._out_leased < leased_before            # dropped results hand their buffers back
+    assert sum(len(v) for v in st._out_pool.values()) >= 1
