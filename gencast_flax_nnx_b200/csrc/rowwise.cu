@@ -86,99 +86,214 @@ __global__ void __launch_bounds__(256) ln_cond_kernel(const void* __restrict__ x
   }
 }
 
-// One warp per receiver.  Receivers whose in-degree exceeds HEAVY are deferred
-// and then summed by the whole block (each warp a contiguous slice of the edge
-// range, partial sums combined in warp order): the polar mesh nodes collect
-// hundreds to thousands of grid edges and would otherwise
-// be a serial tail.  Summation order is a pure function of (row_ptr, edge_perm),
-// so results are bitwise reproducible.
+// One warp per receiver; a block owns the receivers blockIdx.x + k * gridDim.x (strided: high
+// in-degree receivers -- the mesh nodes around the poles, SURVEY.md Appendix A -- cluster in index
+// space, striding spreads them over all blocks), warp w takes k = w, w + 8, ...
+// Receivers whose in-degree exceeds HEAVY are only listed in that pass and afterwards summed by
+// the whole block (each warp a contiguous slice of the edge range, partial sums combined in warp
+// order): hundreds to thousands of edges on one warp would be a serial tail.  Summation order is
+// a pure function of (row_ptr, edge_perm, grid size), so results are bitwise reproducible.
 //
-// The kernel is latency bound unless many rows are in flight: edges are taken in
-// batches of SEG_UNROLL whose (index ->) row loads are all issued before the first
-// LayerNorm reduction, and the scale / offset vectors live in shared memory to keep
-// the register budget for those in-flight rows.
+// The kernel is bound by memory latency, not by instructions: what matters is how many row bytes
+// each SM keeps in flight.  Hence
+//  * rows stay in registers as loaded (bf16 pairs: 8 registers per 512-wide row and lane) until
+//    they are consumed, 16-byte loads;
+//  * while a warp reduces the rows of receiver k it already has the first SEG_UNROLL rows of its
+//    next receiver (and that receiver's row_ptr entries) in flight, so the memory pipe is fed
+//    during the LayerNorm shuffles as well;
+//  * the conditional affine is applied once per receiver instead of once per edge:
+//        sum_e (LN(y_e) (1 + s) + o) = (1 + s) sum_e LN(y_e) + deg o
+//    (same value up to fp32 rounding).
 constexpr int SEG_WARPS = 8;
 constexpr int HEAVY = 32;
-constexpr int SEG_UNROLL = 4;
+constexpr int SEG_UNROLL = 3;
+constexpr int SEG_HEAVY_PER_WARP = 64;   // heavy receivers a warp can defer to the block (beyond: it sums them itself)
 
-template <int NV>
-__global__ void __launch_bounds__(SEG_WARPS * 32) ln_cond_segment_sum_kernel(
-    const void* __restrict__ y, int y_dtype, int64_t ldy, const float* __restrict__ scale_offset, int do_ln,
+template <int NV, bool BF16>
+__global__ void __launch_bounds__(SEG_WARPS * 32, 2) ln_cond_segment_sum_kernel(
+    const void* __restrict__ y, int64_t ldy, const float* __restrict__ scale_offset, int do_ln,
     const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ edge_perm, void* __restrict__ out,
     int out_dtype, int64_t ldo, int64_t num_segments) {
   constexpr int cols = NV * 32;
+  constexpr int W = NV % 8 == 0 ? 8 : 4;            // consecutive elements per lane and chunk
+  constexpr int NCH = NV / W;
+  constexpr int RAW = BF16 ? NV / 2 : NV;           // 32-bit registers of one row per lane, as loaded
   __shared__ __align__(16) float partial[SEG_WARPS][cols];
   __shared__ __align__(16) float so_s[2 * cols];
-  __shared__ int heavy_seg[SEG_WARPS];
+  __shared__ int heavy_list[SEG_WARPS][SEG_HEAVY_PER_WARP];
+  __shared__ int heavy_count[SEG_WARPS];
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const float inv_n = 1.0f / static_cast<float>(cols);
   pdl_wait();
   for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x)
     so_s[c] = scale_offset != nullptr ? __ldg(scale_offset + c) : (c < cols ? 1.0f : 0.0f);
   __syncthreads();
 
-  auto accumulate_range = [&](int beg, int end, float (&acc)[NV]) {
+  auto load_raw = [&](int64_t e, uint32_t (&raw)[RAW]) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
-    for (int j0 = beg; j0 < end; j0 += SEG_UNROLL) {
-      int64_t e[SEG_UNROLL];
+    for (int j = 0; j < NCH; ++j) {
+      const int64_t off = e * ldy + (j * 32 + lane) * W;
+      if constexpr (BF16) {
+        const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(y) + off;
+        if constexpr (W == 8) {
+          const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+          raw[4 * j] = q.x; raw[4 * j + 1] = q.y; raw[4 * j + 2] = q.z; raw[4 * j + 3] = q.w;
+        } else {
+          const uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+          raw[2 * j] = q.x; raw[2 * j + 1] = q.y;
+        }
+      } else {
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(y) + off);
 #pragma unroll
-      for (int u = 0; u < SEG_UNROLL; ++u) {
-        const int j = min(j0 + u, end - 1);
-        e[u] = edge_perm != nullptr ? __ldg(edge_perm + j) : j;
-      }
-      float v[SEG_UNROLL][NV];
-#pragma unroll
-      for (int u = 0; u < SEG_UNROLL; ++u) load_row<NV>(y, y_dtype, e[u] * ldy, lane, v[u]);
-#pragma unroll
-      for (int u = 0; u < SEG_UNROLL; ++u) {
-        if (j0 + u < end) {                    // warp-uniform
-          if (do_ln) layer_norm_inplace<NV>(v[u], cols);
-#pragma unroll
-          for (int jj = 0; jj < NV / 4; ++jj) {
-            const float4 sc = *reinterpret_cast<const float4*>(&so_s[(jj * 32 + lane) * 4]);
-            const float4 of = *reinterpret_cast<const float4*>(&so_s[cols + (jj * 32 + lane) * 4]);
-            acc[jj * 4 + 0] += fmaf(v[u][jj * 4 + 0], sc.x, of.x);
-            acc[jj * 4 + 1] += fmaf(v[u][jj * 4 + 1], sc.y, of.y);
-            acc[jj * 4 + 2] += fmaf(v[u][jj * 4 + 2], sc.z, of.z);
-            acc[jj * 4 + 3] += fmaf(v[u][jj * 4 + 3], sc.w, of.w);
-          }
+        for (int i = 0; i < W / 4; ++i) {
+          const float4 q = __ldg(p + i);
+          raw[W * j + 4 * i] = __float_as_uint(q.x); raw[W * j + 4 * i + 1] = __float_as_uint(q.y);
+          raw[W * j + 4 * i + 2] = __float_as_uint(q.z); raw[W * j + 4 * i + 3] = __float_as_uint(q.w);
         }
       }
     }
   };
-
-  // Segment -> (block, warp) mapping: the eight segments a block handles in one iteration are gridDim
-  // apart, not consecutive.  High in-degree receivers cluster spatially (the mesh nodes around the
-  // poles), hence in index space after the patch relabelling; striding spreads them over all blocks.
-  for (int64_t base = blockIdx.x; base < num_segments; base += static_cast<int64_t>(gridDim.x) * SEG_WARPS) {
-    const int64_t seg = base + static_cast<int64_t>(warp) * gridDim.x;
-    int is_heavy = 0;
-    if (seg < num_segments) {
-      const int beg = __ldg(row_ptr + seg), end = __ldg(row_ptr + seg + 1);
-      if (end - beg > HEAVY) {
-        is_heavy = 1;
-      } else {
-        float acc[NV];
-        accumulate_range(beg, end, acc);
-        store_row<NV>(out, out_dtype, seg * ldo, lane, acc);
+  // rows [j0, min(j0 + SEG_UNROLL, end)) of the edge list -> raw
+  auto load_batch = [&](int j0, int end, uint32_t (&raw)[SEG_UNROLL][RAW]) {
+#pragma unroll
+    for (int u = 0; u < SEG_UNROLL; ++u) {
+      if (j0 + u < end) {                        // warp-uniform
+        const int64_t e = edge_perm != nullptr ? __ldg(edge_perm + j0 + u) : j0 + u;
+        load_raw(e, raw[u]);
       }
     }
-    if (lane == 0) heavy_seg[warp] = is_heavy;
-    __syncthreads();
-    for (int w = 0; w < SEG_WARPS; ++w) {
-      if (!heavy_seg[w]) continue;            // block-uniform
-      const int64_t hseg = base + static_cast<int64_t>(w) * gridDim.x;
-      const int beg = __ldg(row_ptr + hseg), end = __ldg(row_ptr + hseg + 1);
-      const int per = (end - beg + SEG_WARPS - 1) / SEG_WARPS;
-      const int b = min(beg + warp * per, end), e = min(b + per, end);
+  };
+  // acc += LN(row) (or row) for the rows of one batch, in edge order
+  auto consume_batch = [&](int j0, int end, const uint32_t (&raw)[SEG_UNROLL][RAW], float (&acc)[NV]) {
+#pragma unroll
+    for (int u = 0; u < SEG_UNROLL; ++u) {
+      if (j0 + u < end) {
+        float v[NV];
+        if constexpr (BF16) {
+#pragma unroll
+          for (int i = 0; i < NV / 2; ++i) {     // bf16 -> fp32 is a 16-bit shift
+            v[2 * i] = __uint_as_float(raw[u][i] << 16);
+            v[2 * i + 1] = __uint_as_float(raw[u][i] & 0xffff0000u);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NV; ++i) v[i] = __uint_as_float(raw[u][i]);
+        }
+        if (do_ln) {
+          float s = 0.0f, ss = 0.0f;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) { s += v[i]; ss = fmaf(v[i], v[i], ss); }
+          s = warp_sum(s);
+          ss = warp_sum(ss);
+          const float mean = s * inv_n;
+          const float rstd = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.0f) + LN_EPS);
+#pragma unroll
+          for (int i = 0; i < NV; ++i) acc[i] = fmaf(v[i] - mean, rstd, acc[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < NV; ++i) acc[i] += v[i];
+        }
+      }
+    }
+  };
+  // remaining batches of a range whose first batch is already in `first`
+  auto accumulate_rest = [&](int beg, int end, const uint32_t (&first)[SEG_UNROLL][RAW], float (&acc)[NV]) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
+    consume_batch(beg, end, first, acc);
+    for (int j0 = beg + SEG_UNROLL; j0 < end; j0 += SEG_UNROLL) {
+      uint32_t raw[SEG_UNROLL][RAW];
+      load_batch(j0, end, raw);
+      consume_batch(j0, end, raw, acc);
+    }
+  };
+  // out[seg] = (1 + s) * acc + deg * o
+  auto finish = [&](int64_t seg, int deg, float (&acc)[NV]) {
+    const float fdeg = static_cast<float>(deg);
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      float t[W];
+#pragma unroll
+      for (int i = 0; i < W / 4; ++i) {
+        const float4 sc = *reinterpret_cast<const float4*>(&so_s[(j * 32 + lane) * W + 4 * i]);
+        const float4 of = *reinterpret_cast<const float4*>(&so_s[cols + (j * 32 + lane) * W + 4 * i]);
+        const float* a = &acc[j * W + 4 * i];
+        t[4 * i] = fmaf(a[0], sc.x, fdeg * of.x); t[4 * i + 1] = fmaf(a[1], sc.y, fdeg * of.y);
+        t[4 * i + 2] = fmaf(a[2], sc.z, fdeg * of.z); t[4 * i + 3] = fmaf(a[3], sc.w, fdeg * of.w);
+      }
+      store_from_float<W>(out, out_dtype, seg * ldo + (j * 32 + lane) * W, t);
+    }
+  };
+
+  // ---- pass 1: light receivers, one warp each.  Software pipeline over the warp's receivers
+  // k, k + 8, ...: the row_ptr pair of receiver i + 2 and the first rows of receiver i + 1 are
+  // requested before receiver i is reduced, so neither the index load nor the row loads sit on
+  // the critical path of the in-order warp.
+  const int64_t stride = static_cast<int64_t>(gridDim.x);
+  auto seg_of = [&](int64_t k) { return static_cast<int64_t>(blockIdx.x) + k * stride; };
+  auto load_bounds = [&](int64_t kk, int& b, int& e) {
+    const int64_t sg = seg_of(kk);
+    b = 0; e = -1;                                  // e < b marks "no such receiver"
+    if (sg < num_segments) { b = __ldg(row_ptr + sg); e = __ldg(row_ptr + sg + 1); }
+  };
+  int my_heavy = 0;
+  // decides what to do with receiver kk given its bounds; light ones get their first rows requested
+  auto open_segment = [&](int64_t kk, int b, int e, bool& is_light, uint32_t (&raw)[SEG_UNROLL][RAW]) {
+    is_light = false;
+    if (e < b) return;
+    is_light = (e - b <= HEAVY) || my_heavy >= SEG_HEAVY_PER_WARP;
+    if (is_light) {
+      load_batch(b, e, raw);
+    } else {
+      if (lane == 0) heavy_list[warp][my_heavy] = static_cast<int>(kk);
+      ++my_heavy;
+    }
+  };
+  int64_t k = warp;
+  int beg, end, nbeg, nend;
+  bool light = false;
+  uint32_t cur[SEG_UNROLL][RAW];
+  load_bounds(k, beg, end);
+  load_bounds(k + SEG_WARPS, nbeg, nend);
+  open_segment(k, beg, end, light, cur);
+  while (end >= beg) {
+    int n2beg, n2end;
+    load_bounds(k + 2 * SEG_WARPS, n2beg, n2end);   // consumed in the next iteration
+    bool nlight = false;
+    uint32_t nxt[SEG_UNROLL][RAW];
+    open_segment(k + SEG_WARPS, nbeg, nend, nlight, nxt);
+    if (light) {
       float acc[NV];
-      accumulate_range(b, e, acc);
+      accumulate_rest(beg, end, cur, acc);
+      finish(seg_of(k), end - beg, acc);
+    }
+    k += SEG_WARPS;
+    beg = nbeg; end = nend; light = nlight;
+    nbeg = n2beg; nend = n2end;
 #pragma unroll
-      for (int j = 0; j < NV / 4; ++j)
+    for (int u = 0; u < SEG_UNROLL; ++u)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) partial[warp][(j * 32 + lane) * 4 + i] = acc[j * 4 + i];
+      for (int i = 0; i < RAW; ++i) cur[u][i] = nxt[u][i];
+  }
+  if (lane == 0) heavy_count[warp] = my_heavy;
+  __syncthreads();
+
+  // ---- pass 2: deferred receivers (warp lists in warp order), the whole block each
+  for (int w = 0; w < SEG_WARPS; ++w) {
+    const int cnt = heavy_count[w];
+    for (int h = 0; h < cnt; ++h) {
+      const int64_t hseg = seg_of(heavy_list[w][h]);
+      const int hb = __ldg(row_ptr + hseg), he = __ldg(row_ptr + hseg + 1);
+      const int per = (he - hb + SEG_WARPS - 1) / SEG_WARPS;
+      const int b = min(hb + warp * per, he), e = min(b + per, he);
+      float acc[NV];
+      uint32_t first[SEG_UNROLL][RAW];
+      load_batch(b, e, first);
+      accumulate_rest(b, e, first, acc);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) partial[warp][i * 32 + lane] = acc[i];
       __syncthreads();
       if (warp == 0) {
         float tot[NV];
@@ -186,14 +301,11 @@ __global__ void __launch_bounds__(SEG_WARPS * 32) ln_cond_segment_sum_kernel(
         for (int i = 0; i < NV; ++i) tot[i] = 0.0f;
         for (int ww = 0; ww < SEG_WARPS; ++ww)
 #pragma unroll
-          for (int j = 0; j < NV / 4; ++j)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) tot[j * 4 + i] += partial[ww][(j * 32 + lane) * 4 + i];
-        store_row<NV>(out, out_dtype, hseg * ldo, lane, tot);
+          for (int i = 0; i < NV; ++i) tot[i] += partial[ww][i * 32 + lane];
+        finish(hseg, he - hb, tot);
       }
       __syncthreads();
     }
-    __syncthreads();
   }
 }
 
@@ -382,17 +494,24 @@ int gc_ln_cond_segment_sum(void* stream, const void* y, int32_t y_dtype, int64_t
   GC_REQUIRE(y && out && row_ptr, "gc_ln_cond_segment_sum: null buffer");
   GC_REQUIRE(cols == 128 || cols == 256 || cols == 512, "gc_ln_cond_segment_sum: cols=%d (supported: 128, 256, 512)", cols);
   GC_REQUIRE(dtype_ok(y_dtype) && dtype_ok(out_dtype), "gc_ln_cond_segment_sum: bad dtype");
-  GC_REQUIRE(ldy % 4 == 0 && ldo % 4 == 0 && aligned16(y) && aligned16(out), "gc_ln_cond_segment_sum: alignment");
+  GC_REQUIRE(ldy % 8 == 0 && ldo % 8 == 0 && aligned16(y) && aligned16(out), "gc_ln_cond_segment_sum: alignment");
+  if (scale_offset) GC_REQUIRE(aligned16(scale_offset), "gc_ln_cond_segment_sum: scale_offset alignment");
   if (num_segments <= 0) return GC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const unsigned grid = grid_for(num_segments, SEG_WARPS, 8);
-#define GC_LAUNCH_SEG(NV)                                                                                      \
-  GC_CHECK_CUDA(launch_kernel(ln_cond_segment_sum_kernel<NV>, dim3(grid), dim3(SEG_WARPS * 32), 0, st, y, y_dtype, ldy, \
+#define GC_LAUNCH_SEG(NV, BF)                                                                                  \
+  GC_CHECK_CUDA(launch_kernel(ln_cond_segment_sum_kernel<NV, BF>, dim3(grid), dim3(SEG_WARPS * 32), 0, st, y, ldy,     \
                               scale_offset, do_layer_norm, row_ptr, edge_perm, out, out_dtype, ldo, num_segments),      \
                 "ln_cond_segment_sum_kernel")
-  if (cols == 128) GC_LAUNCH_SEG(4);
-  else if (cols == 256) GC_LAUNCH_SEG(8);
-  else GC_LAUNCH_SEG(16);
+  if (y_dtype == GC_BF16) {
+    if (cols == 128) GC_LAUNCH_SEG(4, true);
+    else if (cols == 256) GC_LAUNCH_SEG(8, true);
+    else GC_LAUNCH_SEG(16, true);
+  } else {
+    if (cols == 128) GC_LAUNCH_SEG(4, false);
+    else if (cols == 256) GC_LAUNCH_SEG(8, false);
+    else GC_LAUNCH_SEG(16, false);
+  }
 #undef GC_LAUNCH_SEG
   GC_CHECK_LAUNCH("ln_cond_segment_sum_kernel");
   return GC_OK;
