@@ -239,18 +239,17 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
       tc_fence_after();
       // (a) masked maximum of the row over this tile; the tcgen05.ld of the next sub-block is in
       // flight while the current one is reduced
+      // Tensor memory is read at 64 B/clk per SM: a 128 x 128 fp32 S tile costs 1024 clk per pass,
+      // as much as both MMAs of the tile together, so sub-blocks without a neighbour are not read at
+      // all (neither here nor in the exponential pass).
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       {
-        uint32_t nx[32];
-        tmem_ld_32x32b_x32(s_addr, nx);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tc_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = nx[i];
-          if (c < 3) tmem_ld_32x32b_x32(s_addr + (c + 1) * 32, nx);
           if (live[c]) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(s_addr + c * 32, v);
+            tc_wait_ld();
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               mx[i & 3] = fmaxf(mx[i & 3], (mw[c] & (1u << i)) ? __uint_as_float(v[i]) : -INFINITY);
@@ -295,21 +294,27 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
       const float offset = (m == -INFINITY) ? 0.0f : m * c2;
       // (b) P = exp2(S c - offset) on the live sub-blocks, zeros elsewhere -> swizzled K-major operand
       {
-        uint32_t nx[32];
-        tmem_ld_32x32b_x32(s_addr, nx);
+        int last_live = -1;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (live[c]) last_live = c;
+        if (last_live < 0) {
+          // nothing of S is read: the buffer can go back at once
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_free(grp));
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t v[32];
-          tc_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = nx[i];
-          if (c < 3) {
-            tmem_ld_32x32b_x32(s_addr + (c + 1) * 32, nx);
-          } else {
-            // last read of S is in registers: hand the buffer back before the remaining arithmetic
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_free(grp));
+          if (live[c]) {
+            tmem_ld_32x32b_x32(s_addr + c * 32, v);
+            tc_wait_ld();
+            if (c == last_live) {
+              // last read of S is in registers: hand the buffer back before the remaining arithmetic
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(s_free(grp));
+            }
           }
           uint32_t packed[16];
           if (live[c]) {
