@@ -5,28 +5,36 @@
 // (built once on the host from adj^k, gencast/transformer.py:21-47 /
 // gencast/sparse_transformer.py:555).  For each listed key tile:
 //     S = Q K^T          tcgen05.mma  M=128 N=128 K=d      (operands TMA-staged, 128B swizzle)
-//     P = exp2(S - max)  softmax warps read S from TMEM, apply the bit mask, write bf16 P
-//                        to shared memory in the K-major swizzled operand layout
-//     O += P V           tcgen05.mma  M=128 N=d K=128      (V consumed MN-major, no transpose)
+//     P = exp2(S - max)  softmax warps read S from TMEM, apply the bit mask and write bf16 P
+//                        back into TENSOR MEMORY, over the columns of the S tile they came from
+//     O += P V           tcgen05.mma  M=128 N=d K=128, A = P read from tensor memory (TS form),
+//                        B = V consumed MN-major straight from its TMA tile
 // Softmax is exact, single pass and online: every row keeps a running offset m and sum l;
 // a tile's masked maximum only replaces m when it exceeds it by more than 2^8 (then l and
 // the row of O in TMEM are rescaled by the softmax warps themselves, which is rare after
 // the first tile), otherwise exponentials are taken against the stale offset, which is
-// exact after the final division by l.  The kernel is bound by the L2 -> SM operand feed
-// (K and V tiles are re-read by every query tile that lists them), so K is staged once
-// per tile, not twice.  Masked logits contribute exactly 0, which is what the reference's
-// where(mask, logits, -1e30) + softmax evaluates to (gencast/sparse_transformer.py:100-125,
-// :340-347).
+// exact after the final division by l.  Masked logits contribute exactly 0, which is what
+// the reference's where(mask, logits, -1e30) + softmax evaluates to
+// (gencast/sparse_transformer.py:100-125, :340-347).
+//
+// Why P lives in tensor memory: with 128 x 128 tiles every MMA instruction reads 4 KB of A and
+// 4 KB of B from shared memory per 64 clk, i.e. the full 128 B/clk of the SM; with P in shared
+// memory the clock-stamp trace showed 110 clk per MMA instead of 64 (tile period 2 000 clk for
+// 1 024 clk of tensor work), the MMA-issuing thread being the critical path.  Reading P from TMEM
+// halves the shared-memory traffic of the PV product and removes the P stores and their
+// proxy fences; the 64 KB of P buffers become two more K/V slots.
 //
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
 // warps 2-9 softmax / epilogue in two groups of four (one warp per TMEM lane quarter each):
-// group g owns the key tiles t = g, g+2, ... with its own S buffer, P buffer, O accumulator
-// and (m, l) state, so the two groups are independent online-softmax streams that are merged
-// once at the end (O = (a0 O_0 + a1 O_1) / (a0 l_0 + a1 l_1), a_g = 2^(m_g - m)); no per-tile
-// exchange between warps is needed and each SM sub-partition has two warps to interleave.
+// group g owns the key tiles t = g, g+2, ... with its own S/P columns, O accumulator and (m, l)
+// state, so the two groups are independent online-softmax streams that are merged once at the
+// end (O = (a0 O_0 + a1 O_1) / (a0 l_0 + a1 l_1), a_g = 2^(m_g - m)).  The tensor pipe executes
+// MMAs in issue order, so S(t+2), issued right after PV(t), may overwrite the columns P(t) was
+// read from without any further synchronisation, and its completion implies that of PV(t-2):
+// the group may rescale O_g as soon as S(t) has arrived.
 // 32 x 32 sub-blocks of a tile whose mask bits are all zero (about half of them with the
-// hierarchical patch ordering of the mesh) skip the exponentials altogether.
-// TMEM: S_0, S_1 (2 x 128 columns) + O_0, O_1 (2 x d columns).
+// hierarchical patch ordering of the mesh) are neither read nor exponentiated.
+// TMEM: S_0 / P_0, S_1 / P_1 (2 x 128 columns, P in the first 64) + O_0, O_1 (2 x d columns).
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -45,10 +53,9 @@ struct AttCfg {
   static constexpr int CHUNKS = D / 64;                  // 64-element (128 B) operand chunks along d
   static constexpr int SLOT_BYTES = TK * D * 2;          // one K or V tile
   static constexpr int Q_BYTES = TQ * D * 2;
-  static constexpr int P_BYTES = TQ * TK * 2;            // 32 KB, two 64-key chunks
-  static constexpr int NPBUF = 2;
-  static constexpr int NSLOT = D == 64 ? 6 : 3;   // K / V tile ring
-  static constexpr int SMEM = Q_BYTES + NSLOT * SLOT_BYTES + NPBUF * P_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 3072 /*exchange*/;
+  // K / V tile ring: a K tile and the V tile listed with it are consumed back to back (PV(t), S(t+2))
+  static constexpr int NSLOT = D == 64 ? 10 : 6;
+  static constexpr int SMEM = Q_BYTES + NSLOT * SLOT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct AttParams {
@@ -81,19 +88,16 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t q_smem = base;
   const uint32_t slot_smem = q_smem + C::Q_BYTES;
-  const uint32_t p_smem = slot_smem + C::NSLOT * C::SLOT_BYTES;
-  const uint32_t bars = p_smem + C::NPBUF * C::P_BYTES;
+  const uint32_t bars = slot_smem + C::NSLOT * C::SLOT_BYTES;
   // barrier block
   const uint32_t q_full = bars;
   auto slot_full = [&](int s) { return bars + 8u * (1 + s); };
   auto slot_empty = [&](int s) { return bars + 8u * (1 + C::NSLOT + s); };
   const uint32_t b2 = bars + 8u * (1 + 2 * C::NSLOT);
   auto s_full = [&](int b) { return b2 + 8u * b; };
-  auto s_free = [&](int b) { return b2 + 8u * (2 + b); };
-  auto p_full = [&](int b) { return b2 + 8u * (4 + b); };
-  auto p_empty = [&](int b) { return b2 + 8u * (6 + b); };
-  const uint32_t o_full = b2 + 8u * 8;
-  const uint32_t tmem_ptr_smem = b2 + 8u * 9;
+  auto p_full = [&](int b) { return b2 + 8u * (2 + b); };
+  const uint32_t o_full = b2 + 8u * 4;
+  const uint32_t tmem_ptr_smem = b2 + 8u * 5;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -105,8 +109,8 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
     mbar_init(q_full, 1);
     for (int s = 0; s < C::NSLOT; ++s) { mbar_init(slot_full(s), 1); mbar_init(slot_empty(s), 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(s_full(b), 1); mbar_init(s_free(b), 4);
-      mbar_init(p_full(b), 4); mbar_init(p_empty(b), 1);
+      mbar_init(s_full(b), 1);
+      mbar_init(p_full(b), 4);
     }
     mbar_init(o_full, 1);
     fence_mbar_init();
@@ -147,11 +151,11 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
           tma_load_2d(slot_smem + slot * C::SLOT_BYTES + c * (TK * 128), &qkv_map, slot_full(slot), col + 64 * c, kv * TK);
         if (++slot == C::NSLOT) { slot = 0; phase ^= 1u; }
       };
-      // consumption order: K_0, K_1, then per tile t: K_{t+2}, V_t
+      // consumption order: K_0, K_1, then per tile t: V_t, K_{t+2}
       for (int t = 0; t < 2 && t < T; ++t) load_tile(k_col, __ldg(p.tile_kv + t_beg + t));
       for (int t = 0; t < T; ++t) {
-        if (t + 2 < T) load_tile(k_col, __ldg(p.tile_kv + t_beg + t + 2));
         load_tile(v_col, __ldg(p.tile_kv + t_beg + t));
+        if (t + 2 < T) load_tile(k_col, __ldg(p.tile_kv + t_beg + t + 2));
       }
     }
   } else if (warp == 1) {
@@ -167,7 +171,6 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
         const int b = g & 1;
         mbar_wait(slot_full(slot), slot_phase);
         GC_TRACE(1, 2 * mma_ev);
-        mbar_wait(s_free(b), ((g >> 1) & 1) ^ 1u);
         GC_TRACE(1, 2 * mma_ev + 1); ++mma_ev;
         tc_fence_after();
         const uint32_t k_base = slot_smem + slot * C::SLOT_BYTES;
@@ -182,30 +185,27 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
         ++g;
       };
       mbar_wait(q_full, 0);
-      // S runs two tiles ahead of PV: the softmax group releases its S buffer as soon as its last
-      // read is in registers, so S(t+2) is formed under the tail of softmax(t)
       for (int t = 0; t < 2 && t < T; ++t) issue_s();
       for (int t = 0; t < T; ++t) {
-        if (t + 2 < T) issue_s();
-        const int pb = t % C::NPBUF;
+        const int pb = t & 1;
         mbar_wait(slot_full(slot), slot_phase);
         GC_TRACE(2, 2 * t);
-        mbar_wait(p_full(pb), (t / C::NPBUF) & 1);
+        mbar_wait(p_full(pb), (t >> 1) & 1);
         GC_TRACE(2, 2 * t + 1);
         tc_fence_after();
         const uint32_t v_base = slot_smem + slot * C::SLOT_BYTES;
-        const uint32_t p_base = p_smem + pb * C::P_BYTES;
 #pragma unroll
         for (int j = 0; j < TK / 16; ++j) {
-          // A: P[128 x 16 keys], K-major, 64-key chunks of 16 KB.  B: V[16 keys x D], MN-major:
-          // 16 key rows of 128 B start at j * 2048; 64-wide d chunks are TK * 128 bytes apart.
-          const uint64_t da = desc_kmajor_sw128(p_base + (j >> 2) * (TQ * 128) + (j & 3) * 32);
+          // A: P[128 x 16 keys] from tensor memory: lane = query row, 8 columns of two bf16 each.
+          // B: V[16 keys x D], MN-major: 16 key rows of 128 B start at j * 2048; 64-wide d chunks are
+          // TK * 128 bytes apart.
           const uint64_t db = desc_mnmajor_sw128(v_base + j * 2048, TK * 128, 1024);
-          umma_f16(tmem_o + (t & 1) * D, da, db, idesc_o, (t > 1 || j > 0) ? 1u : 0u);
+          umma_f16_ts(tmem_o + (t & 1) * D, tmem_s0 + pb * 128 + 8 * j, db, idesc_o, (t > 1 || j > 0) ? 1u : 0u);
         }
         umma_commit(slot_empty(slot));
-        umma_commit(p_empty(pb));
         if (++slot == C::NSLOT) { slot = 0; slot_phase ^= 1u; }
+        // S(t+2) overwrites the columns of S(t) / P(t): in issue order behind PV(t), which read them
+        if (t + 2 < T) issue_s();
       }
       umma_commit(o_full);
     }
@@ -215,11 +215,12 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
     const int grp = (warp - 2) >> 2;                   // softmax group = parity of the key tiles it owns
     const int r = q * 32 + lane;                       // row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    float* xch = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + 8 * 32);   // [2 groups][m, l][128]
+    // [2 groups][m, l][128] floats, in the Q tile's shared memory: every S MMA (the only reader of Q) has
+    // completed before any softmax warp leaves its tile loop
+    float* xch = reinterpret_cast<float*>(smem_raw + (q_smem - smem_u32(smem_raw)));
     const float c2 = p.scale_log2e;
     const uint32_t s_addr = tmem_s0 + grp * 128 + lane_addr;
     const uint32_t o_addr = tmem_o + grp * D + lane_addr;
-    const uint32_t p_row = p_smem + grp * C::P_BYTES + r * 128;
     float m = -INFINITY;                               // running offset (raw logit units)
     float ls[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     uint4 mk_next = make_uint4(0u, 0u, 0u, 0u);
@@ -258,11 +259,7 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
       }
       const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       const float m_new = fmaxf(m, mt);
-      // the P buffer is free and O_grp is at rest once PV(t-2) has completed
-      if (use > 0) {
-        mbar_wait(p_empty(grp), (use - 1) & 1);
-        tc_fence_after();
-      }
+      // O_grp is at rest: S(t) was issued behind PV(t-2) and has completed
       if (threadIdx.x == 64) GC_TRACE(4, t);
       if (use == 0) {
         m = m_new;                                     // nothing accumulated yet
@@ -294,30 +291,13 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
       const float offset = (m == -INFINITY) ? 0.0f : m * c2;
       // (b) P = exp2(S c - offset) on the live sub-blocks, zeros elsewhere -> swizzled K-major operand
       {
-        int last_live = -1;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) if (live[c]) last_live = c;
-        if (last_live < 0) {
-          // nothing of S is read: the buffer can go back at once
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(s_free(grp));
-        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          if (live[c]) {
-            tmem_ld_32x32b_x32(s_addr + c * 32, v);
-            tc_wait_ld();
-            if (c == last_live) {
-              // last read of S is in registers: hand the buffer back before the remaining arithmetic
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(s_free(grp));
-            }
-          }
           uint32_t packed[16];
           if (live[c]) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(s_addr + c * 32, v);
+            tc_wait_ld();
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
               float e0, e1;
@@ -333,24 +313,20 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
 #pragma unroll
             for (int i = 0; i < 16; ++i) packed[i] = 0u;
           }
-          // keys 32c .. 32c+31 -> 64-key chunk (c >> 1), 16-byte units (c & 1) * 4 + u, swizzled by row
-          const uint32_t chunk_base = p_row + (c >> 1) * (TQ * 128);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint32_t unit = static_cast<uint32_t>((c & 1) * 4 + u) ^ static_cast<uint32_t>(r & 7);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(chunk_base + unit * 16), "r"(packed[4 * u]),
-                         "r"(packed[4 * u + 1]), "r"(packed[4 * u + 2]), "r"(packed[4 * u + 3])
-                         : "memory");
-          }
+          // keys 32c .. 32c+31 of this row -> columns 16c .. 16c+15 of the tile's TMEM region: over S
+          // columns that have been read already (chunk c of S sits at columns 32c .. 32c+31)
+          tmem_st_32x32b_x16(s_addr + c * 16, packed);
         }
       }
+      tc_wait_st();
       tc_fence_before();
-      fence_proxy_async_smem();       // generic-proxy stores of P -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(grp));
     }
     // ---- merge the two streams: every thread publishes (m, l) of its row
     const float l_own = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+    // both groups are past their last S tile: no S MMA is left that reads Q, its memory can be reused
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     xch[grp * 256 + r] = m;
     xch[grp * 256 + 128 + r] = l_own;
     asm volatile("bar.sync 1, 256;" ::: "memory");
