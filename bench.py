@@ -331,6 +331,17 @@ def measure(args, config: str, MB: int, steps: int, warmup: int, dev, rank: int,
     else:
         roof = {"kernel": dom, "bound": "hbm", "achieved": domk["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": domk["gbs"] / peaks["hbm"], "traffic": None}
+    try:
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel family from an ncu capture of
+        # the same workload (profiles/r01_gemm_dram_traffic.json names the command); not measured live
+        with open(os.path.join(ROOT, "profiles", "r01_gemm_dram_traffic.json")) as f:
+            tr = json.load(f)
+        if tr["workload"] == config and tr["members_per_gpu"] == MB and dom.startswith(tr["kernel"]):
+            roof["traffic"] = tr["dram_bytes_per_launch"]
+            roof["traffic_unit"] = "bytes per launch (ncu capture, profiles/r01_gemm_dram_traffic.json)"
+            roof["algorithmic_bytes_per_launch"] = domk["gbs"] * 1e9 * domk["avg_us"] * 1e-6
+    except Exception:
+        pass
     roof["peak_source"] = peaks["source"] + (" (sustained bf16 GEMM: the kernel is timed inside a long step)"
                                              if tensor_bound else " (copy bandwidth)")
     roof["avg_launch_us"] = domk["avg_us"]
