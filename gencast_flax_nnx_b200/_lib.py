@@ -75,6 +75,8 @@ SIGNATURES = {
                                 c_void_p, c_int32, c_int64, c_int64, c_int32]),
     "gc_cast_pad": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_int32, c_int64, c_int32,
                               c_void_p, c_int64]),
+    "gc_select_columns": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
+                                    c_int64, c_int64, c_int32]),
     "gc_ensemble_accumulate": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),
 }
 

@@ -432,6 +432,26 @@ __global__ void __launch_bounds__(256) cast_pad_kernel(const void* __restrict__ 
   }
 }
 
+__global__ void __launch_bounds__(256) select_columns_kernel(const float* __restrict__ s0, int64_t ld0,
+                                                             const float* __restrict__ s1, int64_t ld1,
+                                                             const float* __restrict__ s2, int64_t ld2,
+                                                             const int32_t* __restrict__ table, float* __restrict__ out,
+                                                             int64_t ldo, int64_t rows, int cols) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t total = rows * cols;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols;
+    const int j = static_cast<int>(i - r * cols);
+    const int code = __ldg(table + j);
+    const int k = code >> 24, c = code & 0xffffff;
+    const float* src = k == 0 ? s0 : (k == 1 ? s1 : s2);
+    const int64_t ld = k == 0 ? ld0 : (k == 1 ? ld1 : ld2);
+    out[r * ldo + j] = __ldg(src + r * ld + c);
+  }
+}
+
 __global__ void __launch_bounds__(256) ensemble_accumulate_kernel(const float* __restrict__ x, float* __restrict__ sum,
                                                                   float* __restrict__ sumsq, int64_t n) {
   pdl_launch_dependents();
@@ -566,6 +586,19 @@ int gc_cast_pad(void* stream, const void* src, int32_t src_dtype, int64_t ld_src
   GC_CHECK_CUDA(launch_kernel(cast_pad_kernel, dim3(grid_for(rows * cols_dst, 256 * 4, 8)), dim3(256), 0, st, src, src_dtype,
                               ld_src, cols_src, dst, dst_dtype, ld_dst, cols_dst, scale_dev, rows), "cast_pad_kernel");
   GC_CHECK_LAUNCH("cast_pad_kernel");
+  return GC_OK;
+}
+
+int gc_select_columns(void* stream, const float* src0, int64_t ld0, const float* src1, int64_t ld1, const float* src2,
+                      int64_t ld2, const int32_t* table, float* out, int64_t ldo, int64_t rows, int32_t cols_out) {
+  GC_REQUIRE(src0 && table && out, "gc_select_columns: null buffer");
+  GC_REQUIRE(cols_out > 0 && ldo >= cols_out, "gc_select_columns: bad sizes");
+  GC_REQUIRE(out != src0 && out != src1 && out != src2, "gc_select_columns: out aliases a source");
+  if (rows <= 0) return GC_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GC_CHECK_CUDA(launch_kernel(select_columns_kernel, dim3(grid_for(rows * cols_out, 256 * 4, 8)), dim3(256), 0, st, src0, ld0,
+                              src1, ld1, src2, ld2, table, out, ldo, rows, cols_out), "select_columns_kernel");
+  GC_CHECK_LAUNCH("select_columns_kernel");
   return GC_OK;
 }
 

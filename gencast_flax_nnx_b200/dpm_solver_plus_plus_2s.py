@@ -66,13 +66,23 @@ class Sampler:
         engine = den._maybe_init(inputs, targets_template, forcings)
         sizes = dict(targets_template.sizes)
         sizes.setdefault("batch", 1)
-        batch = sizes["batch"]
+        with torch.cuda.device(engine.device):
+            inp, frc = den.stack_constants(inputs, forcings, sizes)
+            engine.set_constant_features(den.member_major(inp), den.member_major(frc))
+            res = self.sample_on_device(targets_template, key, init_noise=init_noise)
+            out = res.reshape(sizes["batch"], engine.G, engine.n_out).permute(1, 0, 2)
+            return den.stacker.from_nodes(out, targets_template)
+
+    def sample_on_device(self, targets_template: Dataset, key: int, *, init_noise: Optional[np.ndarray] = None) -> torch.Tensor:
+        """Runs the solver on the engine's resident constant features (set_constant_features) and returns
+        the prediction as a device tensor [batch * G, n_out] fp32 (member-major blocks of grid rows), valid
+        until the next call.  `key` seeds the initial noise (one value of `rngs.noise()`)."""
+        engine = self._denoiser.engine
+        batch = dict(targets_template.sizes).get("batch", 1)
         if engine.B != batch:
             raise ValueError(f"Sampler was initialised for batch size {engine.B}, got {batch}")
         se = self.sampler_engine()
         with torch.cuda.device(engine.device):
-            inp, frc = den.stack_constants(inputs, forcings, sizes)
-            engine.set_constant_features(den.member_major(inp), den.member_major(frc))
             if init_noise is not None:
                 noise = np.ascontiguousarray(np.transpose(np.asarray(init_noise, np.float32), (1, 0, 2))).reshape(
                     batch * engine.G, engine.n_out)
@@ -87,6 +97,4 @@ class Sampler:
                     noise = self._noise_gen.sample_nodes(engine.n_out, members=batch, generator=gen)
                 else:
                     noise = torch.randn(batch * engine.G, engine.n_out, generator=gen, device=engine.device)
-            res = se.sample(noise, use_graph=self._use_graph)
-            out = res.reshape(batch, engine.G, engine.n_out).permute(1, 0, 2)
-            return den.stacker.from_nodes(out, targets_template)
+            return se.sample(noise, use_graph=self._use_graph)

@@ -238,6 +238,23 @@ def cast_pad(src: torch.Tensor, dst: torch.Tensor, cols_src: Optional[int] = Non
     return dst
 
 
+def select_columns(sources: Sequence[Optional[torch.Tensor]], table: torch.Tensor, out: torch.Tensor):
+    """out[r, j] = sources[table[j] >> 24][r, table[j] & 0xffffff] (fp32 matrices; the rollout's window update)."""
+    lib = _lib.load()
+    src = list(sources) + [None] * (3 - len(sources))
+    if table.dtype != torch.int32 or table.numel() != out.shape[1]:
+        raise ValueError("select_columns: table must be int32 [out columns]")
+    for t in src:
+        if t is not None and (t.dtype != torch.float32 or t.shape[0] != out.shape[0]):
+            raise TypeError("select_columns: sources must be fp32 with the rows of out")
+    if out.dtype != torch.float32:
+        raise TypeError("select_columns: out must be fp32")
+    ld = [(_row_major(t, "source") if t is not None else 0) for t in src]
+    _lib.check(lib.gc_select_columns(_stream(), _p(src[0]), ld[0], _p(src[1]), ld[1], _p(src[2]), ld[2], table.data_ptr(),
+                                     out.data_ptr(), _row_major(out, "out"), out.shape[0], out.shape[1]), "gc_select_columns")
+    return out
+
+
 def ensemble_accumulate(x: torch.Tensor, total: torch.Tensor, total_sq: torch.Tensor):
     lib = _lib.load()
     _lib.check(lib.gc_ensemble_accumulate(_stream(), x.data_ptr(), total.data_ptr(), total_sq.data_ptr(), x.numel()),

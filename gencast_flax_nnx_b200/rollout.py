@@ -74,3 +74,113 @@ def chunked_prediction(predictor_fn: PredictorFn, rng, inputs: Dataset, targets_
     chunks = list(chunked_prediction_generator(predictor_fn, rng, inputs, targets_template, forcings,
                                                num_steps_per_chunk, verbose))
     return concat_time(chunks)
+
+
+# ----------------------------------------------------------------------------------------------
+# The same rollout with the autoregressive window resident on the GPU
+# ----------------------------------------------------------------------------------------------
+
+_PRESERVED = ("batch", "lat", "lon")
+
+
+def _channel_index(var: DataArray):
+    """Integer array over the variable's non-(batch, lat, lon) dims (in its own dim order) holding the channel
+    number each element is stacked to (stacking.variable_to_nodes: row-major over those dims)."""
+    extra = [d for d in var.dims if d not in _PRESERVED]
+    shape = [var.sizes[d] for d in extra]
+    return extra, np.arange(int(np.prod(shape, dtype=np.int64)) if shape else 1, dtype=np.int64).reshape(shape or ())
+
+
+def window_update_table(inputs: Dataset, predictions: Dataset, forcings: Dataset) -> np.ndarray:
+    """Column table of the on-device window update (gc_select_columns): entry j says where channel j of the
+    next step's stacked inputs comes from -- (0, c) the current stacked inputs, (1, c) the stacked prediction,
+    (2, c) the stacked forcings of the step -- encoded as source << 24 | c.
+
+    Semantics of the reference's `_get_next_inputs` (common/rollout.py:379-401) with a one-step chunk: for every
+    input variable with a time axis, frames shift by one and the last frame is the variable's value in
+    merge([predictions, forcings]); variables without a time axis are kept; an input with a time axis that is
+    neither predicted nor forced is an error."""
+    def offsets(ds):
+        out, off = {}, 0
+        for n in sorted(ds.keys()):
+            _, idx = _channel_index(ds[n])
+            out[n] = off
+            off += idx.size
+        return out, off
+    in_off, n_in = offsets(inputs)
+    pr_off, _ = offsets(predictions)
+    fr_off, _ = offsets(forcings)
+    table = np.zeros(n_in, np.int64)
+    for name in sorted(inputs.keys()):
+        v = inputs[name]
+        extra, idx = _channel_index(v)
+        base = in_off[name]
+        if "time" not in extra:
+            table[base + idx.reshape(-1)] = (0 << 24) | (base + idx.reshape(-1))
+            continue
+        if name in predictions:
+            src_id, src_var, src_base = 1, predictions[name], pr_off[name]
+        elif name in forcings:
+            src_id, src_var, src_base = 2, forcings[name], fr_off[name]
+        else:
+            raise ValueError("Found an input with a time index that is not predicted or forced.")
+        s_extra, s_idx = _channel_index(src_var)
+        if "time" not in s_extra or src_var.sizes["time"] != 1:
+            raise ValueError("the on-device rollout advances one target step at a time")
+        # bring the source's extra dims into the input variable's order, time first dropped
+        s_idx = np.transpose(s_idx, [s_extra.index(d) for d in extra])
+        ax = extra.index("time")
+        T = v.sizes["time"]
+        older = np.take(idx, range(1, T), axis=ax)                  # frames 1 .. T-1 move to 0 .. T-2
+        table[base + np.take(idx, range(0, T - 1), axis=ax).reshape(-1)] = (0 << 24) | (base + older.reshape(-1))
+        table[base + np.take(idx, [T - 1], axis=ax).reshape(-1)] = (src_id << 24) | (src_base + s_idx.reshape(-1))
+    return table.astype(np.int32)
+
+
+def device_chunked_prediction_generator(model, inputs: Dataset, targets_template: Dataset, forcings: Dataset,
+                                        verbose: bool = False) -> Iterator[Dataset]:
+    """`chunked_prediction_generator` (common/rollout.py:245-376) for a `gencast.GenCast` model with one target
+    step per chunk, keeping the autoregressive input window on the GPU: the inputs go host -> device once,
+    each step uploads only its forcings, the next window is assembled on the device from the previous window,
+    the prediction and the forcings (`window_update_table`, gc_select_columns), and only the prediction comes
+    back to the host.  Step for step it yields what
+    `chunked_prediction_generator(lambda rng, inputs, targets_template, forcings: model.full_sampling(inputs,
+    targets_template, forcings), ...)` yields with the same `model.rngs` state."""
+    import torch
+    from . import ops
+    if model._sampler is None:
+        raise ValueError("Sampler config must be specified to run inference.")
+    times = np.asarray(targets_template.coords["time"])
+    if len(np.unique(np.diff(times))) > 1:
+        raise ValueError("The targets time coordinates must be evenly spaced")
+    den, sampler = model.denoiser, model._sampler
+    chunk_time = times[:1]
+    window = None
+    table = None
+    for step in range(targets_template.sizes["time"]):
+        if verbose:
+            print(f"Chunk {step}/{targets_template.sizes['time']}", flush=True)
+        sl = slice(step, step + 1)
+        cur_t = _with_time(targets_template.isel(time=sl), chunk_time)
+        cur_f = _with_time(forcings.isel(time=sl), chunk_time)
+        engine = den._maybe_init(inputs, cur_t, cur_f)
+        sizes = dict(cur_t.sizes)
+        sizes.setdefault("batch", 1)
+        with torch.cuda.device(engine.device):
+            if window is None:
+                window = den.member_major(den.stacker.to_nodes("inputs", inputs, sizes)).clone()      # [B*G, C_in] fp32
+                nxt = torch.empty_like(window)
+                table = torch.from_numpy(window_update_table(inputs, cur_t, cur_f)).to(engine.device)
+            frc = den.member_major(den.stacker.to_nodes("forcings", cur_f, sizes))
+            engine.set_constant_features(window, frc)
+            res = sampler.sample_on_device(cur_t, model.rngs.noise())
+            out = res.reshape(sizes["batch"], engine.G, engine.n_out).permute(1, 0, 2)
+            pred = den.stacker.from_nodes(out, cur_t)
+            ops.select_columns([window, res, frc], table, nxt)
+            window, nxt = nxt, window
+        yield _with_time(pred, times[sl])
+
+
+def device_chunked_prediction(model, inputs: Dataset, targets_template: Dataset, forcings: Dataset,
+                              verbose: bool = False) -> Dataset:
+    return concat_time(list(device_chunked_prediction_generator(model, inputs, targets_template, forcings, verbose)))

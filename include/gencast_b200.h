@@ -215,6 +215,18 @@ GC_API int gc_cast_pad(void* stream, const void* src, int32_t src_dtype, int64_t
                 const float* scale_dev, int64_t rows);
 
 /*
+ * Column selection from up to three fp32 matrices: out[r, j] = src_k[r, c] with
+ * (k, c) = (table[j] >> 24, table[j] & 0xffffff).  This is the autoregressive window
+ * update of the reference's rollout on device -- common/rollout.py:362-368 and
+ * _get_next_inputs :379-401: the next step's stacked inputs are columns of the
+ * previous inputs (older frames shift), of the prediction and of the step's forcings.
+ * src1 / src2 may be NULL if the table does not reference them; out must not alias a source.
+ */
+GC_API int gc_select_columns(void* stream, const float* src0, int64_t ld0, const float* src1, int64_t ld1,
+                      const float* src2, int64_t ld2, const int32_t* table, float* out, int64_t ldo,
+                      int64_t rows, int32_t cols_out);
+
+/*
  * Ensemble statistics accumulation (no reference implementation exists; defined
  * in DESIGN.md): sum[i] += x[i]; sumsq[i] += x[i]^2 over n elements.
  */

@@ -214,3 +214,28 @@ def test_device_stacker_pinned_inputs_and_leased_outputs(cuda_device):
     gc.collect()
     assert st._out_leased < leased_before            # dropped results hand their buffers back
     assert sum(len(v) for v in st._out_pool.values()) >= 1
+
+
+def test_device_rollout_equals_host_rollout(cuda_device):
+    """rollout.device_chunked_prediction (window kept on the GPU, gc_select_columns) yields, step for step,
+    exactly what the reference-shaped host driver yields around GenCast.full_sampling."""
+    from gencast_flax_nnx_b200 import configs, gencast, graph, rollout, synthetic
+    from gencast_flax_nnx_b200.rngs import Rngs
+    case = make_case("tiny")
+    res, arch = configs.named_config("tiny")
+    lat, lon = graph.regular_grid(res)
+    inputs, targets, forcings = synthetic.make_example(lat, lon, batch=2, seed=1, num_target_steps=3)
+    sc = configs.SamplerConfig(num_noise_levels=3, stochastic_churn_rate=0.0)
+
+    def model():
+        return gencast.GenCast(configs.TASK, arch, sampler_config=sc, rngs=Rngs(7), params=case.params,
+                               compute_dtype="bf16")
+    host = rollout.chunked_prediction(
+        lambda rng, inputs, targets_template, forcings: m1.full_sampling(inputs, targets_template, forcings),
+        0, inputs, targets, forcings) if (m1 := model()) else None
+    dev = rollout.device_chunked_prediction(model(), inputs, targets, forcings)
+    assert dev.coords["time"].tolist() == host.coords["time"].tolist() == [12, 24, 36]
+    for k in host.keys():
+        assert dev[k].dims == host[k].dims
+        np.testing.assert_array_equal(dev[k].data, host[k].data)
+    assert not np.array_equal(host["2m_temperature"].data[:, 0], host["2m_temperature"].data[:, 1])

@@ -267,3 +267,24 @@ def test_param_interchange_round_trip(tmp_path):
     ref = params.init_reference_like(shapes)
     # at the reference initialisation every transformer block is the identity
     assert not ref["denoiser/predictor/mesh_gnn/batch_first_transformer/blocks/0/attn_module/final_linear/kernel"].any()
+
+
+def test_window_update_table_matches_host_window_roll():
+    """The column table of the on-device rollout (gc_select_columns) reproduces _get_next_inputs
+    (common/rollout.py:379-401) on the stacked layout, for the full GenCast task variable set."""
+    from gencast_flax_nnx_b200 import graph, rollout, stacking, synthetic
+    from gencast_flax_nnx_b200.xarray_lite import merge
+    lat, lon = graph.regular_grid(30.0)
+    inputs, targets, forcings = synthetic.make_example(lat, lon, batch=2, seed=3)
+    sizes = dict(targets.sizes)
+    rng = np.random.default_rng(0)
+    pred = targets.map(lambda v: DataArray(rng.standard_normal(v.shape).astype(np.float32), v.dims))
+    table = rollout.window_update_table(inputs, pred, forcings)
+    srcs = [stacking.dataset_to_nodes(d, sizes)[0] for d in (inputs, pred, forcings)]
+    new = np.stack([srcs[t >> 24][:, :, t & 0xffffff] for t in table], axis=-1)
+    ref, _ = stacking.dataset_to_nodes(rollout._get_next_inputs(inputs, merge([pred, forcings])), sizes)
+    np.testing.assert_array_equal(new, ref)
+    assert (table >> 24).max() == 2 and ((table >> 24) == 1).sum() == 82
+    # an input with a time axis that is neither predicted nor forced is rejected, as in the reference
+    with pytest.raises(ValueError):
+        rollout.window_update_table(inputs, pred.drop_vars(["2m_temperature"]), forcings)
