@@ -32,6 +32,7 @@ How it is computed differs where the B200 rewards it:
 from __future__ import annotations
 
 import dataclasses
+import os
 import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -332,8 +333,10 @@ class DenoiserEngine:
         self.xin = b(G, self.KN)                 # c_in * noisy targets (network input operand)
         self.a_const = b(G, self.KC)             # struct | inputs | forcings, constant over a sampling step
         self.g_h, self.g_y = b(G, L), b(G, L)    # MLP hidden / pre-norm output scratch on grid nodes
+        self.g_h2, self.g_y2 = b(G, L), b(G, L)  # the same for the grid branch (runs beside the mesh side)
         self.g0, self.g_lat, self.g2 = b(G, L), b(G, L), b(G, L)
-        self.g_p = b(G, L)                       # per-grid-node partial product for the edge MLPs
+        self.g_p = b(G, L)                       # per-grid-node partial product for the edge MLPs (encoder)
+        self.g_p2 = b(G, L)                      # same for the decoder (may be produced on the branch stream)
         self.m0, self.m_h, self.m_y, self.m_p, self.m_agg = b(V, L), b(V, L), b(V, L), b(V, L), b(V, L)
         self.m_out = b(V, L)
         self.x = b(V, L, torch.float32)          # transformer residual stream, fp32
@@ -448,16 +451,32 @@ class DenoiserEngine:
         ops.gemm([(h, w2)], y, bias=b2)
         ops.ln_cond(y, out, so, residual=residual)
 
-    def forward(self, ctx: SigmaContext) -> torch.Tensor:
+    def _grid_branch(self, ctx: SigmaContext) -> None:
+        """Grid-node update of the encoder and the decoder's per-grid-node partial product: they depend on
+        the embedded grid nodes only, and nothing needs them before the decoder."""
+        w, T = self.w, ctx.table
+        self._mlp_ln([(self.g0, w["gu_w1"])], w["gu_b1"], w["gu_w2"], w["gu_b2"],
+                     self.g_h2, self.g_y2, self.g_lat, T[self.C_G2M_GU], residual=self.g0)
+        ops.gemm([(self.g_lat, w["du_w1r"])], self.g_p2)
+
+    def forward(self, ctx: SigmaContext, branch_stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
         """One network evaluation F(xin, sigma) -> self.f_out [G, NO] fp32 (first n_out columns valid).
 
-        Enqueues on torch's current stream; reads self.xin and self.a_const.
+        Enqueues on torch's current stream; reads self.xin and self.a_const.  With `branch_stream` the
+        grid-side work that nothing on the mesh side depends on (`_grid_branch`) is enqueued there,
+        forked after the grid embedding and joined before the decoder: inside the captured step it becomes
+        a parallel branch of the graph whose CTAs fill the ramp / drain gaps between the mesh-side kernels.
         """
         w, T = self.w, ctx.table
         E1, E2 = self.E1t, self.E2t
         # ---- encoder (gencast/denoiser.py:602-688)
         self._mlp_ln([(self.xin, w["ge_w1n"]), (self.a_const, w["ge_w1c"])], w["ge_b1"], w["ge_w2"], w["ge_b2"],
                      self.g_h, self.g_y, self.g0, T[self.C_G2M_GE])
+        if branch_stream is not None:
+            main = torch.cuda.current_stream(self.device)
+            branch_stream.wait_stream(main)
+            with torch.cuda.stream(branch_stream):
+                self._grid_branch(ctx)
         ops.ln_cond(self.m0_ln, self.m0, T[self.C_G2M_ME], layer_norm=False)
         ops.gemm([(self.g0, w["eu_w1s"])], self.g_p)
         ops.gemm([(self.m0, w["eu_w1r"])], self.m_p)
@@ -468,8 +487,8 @@ class DenoiserEngine:
         ops.ln_cond_segment_sum(e_y, self.m_agg, T[self.C_G2M_EU], self.g2m_row_ptr, self.g2m_perm)
         self._mlp_ln([(self.m0, w["mu_w1a"]), (self.m_agg, w["mu_w1b"])], w["mu_b1"], w["mu_w2"], w["mu_b2"],
                      self.m_h, self.m_y, self.x, T[self.C_G2M_MU], residual=self.m0)
-        self._mlp_ln([(self.g0, w["gu_w1"])], w["gu_b1"], w["gu_w2"], w["gu_b2"],
-                     self.g_h, self.g_y, self.g_lat, T[self.C_G2M_GU], residual=self.g0)
+        if branch_stream is None:
+            self._grid_branch(ctx)
         # ---- processor (gencast/sparse_transformer.py:486-525, :624-634)
         for i in range(self.NL):
             ops.ln_cond(self.x, self.t_h, T[self.C_T0 + 2 * i])
@@ -482,10 +501,11 @@ class DenoiserEngine:
         ops.ln_cond(self.x, self.m_out, T[self.C_TFINAL])
         # ---- decoder (gencast/denoiser.py:730-768)
         ops.gemm([(self.m_out, w["du_w1s"])], self.m_p)
-        ops.gemm([(self.g_lat, w["du_w1r"])], self.g_p)
+        if branch_stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(branch_stream)
         e_h, e_y = self.e_h[:E2], self.e_y[:E2]
         ops.gemm([(self.m2g_e_ln, ctx.m2g_w1e)], e_h, bias=ctx.m2g_b1, act="swish",
-                 gathers=[(self.m_p, self.m2g_s), (self.g_p, self.m2g_r)])
+                 gathers=[(self.m_p, self.m2g_s), (self.g_p2, self.m2g_r)])
         ops.gemm([(e_h, w["du_w2"])], e_y, bias=w["du_b2"])
         ops.ln_cond_segment_sum(e_y, self.g_agg, T[self.C_M2G_EU], self.m2g_row_ptr, self.m2g_perm)
         self._mlp_ln([(self.g_lat, w["dg_w1a"]), (self.g_agg, w["dg_w1b"])], w["dg_b1"], w["dg_w2"], w["dg_b2"],
@@ -574,6 +594,7 @@ class SamplerEngine:
         self.x_mid = torch.zeros(G, C, dtype=torch.float32, device=e.device)
         self.result = torch.zeros(G, C, dtype=torch.float32, device=e.device)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._branch = torch.cuda.Stream(device=e.device)      # parallel graph branch for the grid-side work
         torch.cuda.synchronize(e.device)
 
     @property
@@ -586,14 +607,15 @@ class SamplerEngine:
         n_disc = sum(1 for p in self.plan if p[1] == "discard")
         return 2 + len(self.plan) * (self.engine.launches_per_forward + 1) - n_disc
 
-    def _enqueue(self):
+    def _enqueue(self, branch: bool = False):
         e = self.engine
+        bs = self._branch if (branch and os.environ.get("GENCAST_GRAPH_BRANCH", "1") != "0") else None
         C = e.n_out
         # x0 = sigma_0 * noise (:78); first network input = c_in(sigma_0) * x0
         ops.cast_pad(self.noise, self.x, scale=self.init_scale[0:1])
         ops.cast_pad(self.noise, e.xin[:, :C], scale=self.init_scale[1:2])
         for j, (sigma, kind, _) in enumerate(self.plan):
-            f = e.forward(self.ctx[j])
+            f = e.forward(self.ctx[j], bs)
             if kind == "first":
                 last = j + 1 == len(self.plan) or self.plan[j + 1][1] == "discard"
                 dst = self.result if last else self.x_mid
@@ -624,7 +646,7 @@ class SamplerEngine:
                 torch.cuda.synchronize(e.device)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    self._enqueue()
+                    self._enqueue(branch=True)
                 self._graph = graph
             self._graph.replay()
         return self.result
