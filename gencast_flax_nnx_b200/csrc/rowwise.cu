@@ -109,8 +109,12 @@ constexpr int HEAVY = 32;
 constexpr int SEG_UNROLL = 3;
 constexpr int SEG_HEAVY_PER_WARP = 64;   // heavy receivers a warp can defer to the block (beyond: it sums them itself)
 
-template <int NV, bool BF16>
-__global__ void __launch_bounds__(SEG_WARPS * 32, 2) ln_cond_segment_sum_kernel(
+// OCC = resident blocks per SM the register budget is cut for.  Regular low-degree graphs (mesh2grid: three
+// rows per receiver, no permutation) run best with the full budget (2 blocks, no spills: 305 us vs 365 us
+// at 1 deg x 4); irregular ones (grid2mesh: degrees 3 .. 594 through edge_perm) gain more from a third
+// block of warps than they lose to a few spilled registers (205 us vs 246 us).
+template <int NV, bool BF16, int OCC>
+__global__ void __launch_bounds__(SEG_WARPS * 32, OCC) ln_cond_segment_sum_kernel(
     const void* __restrict__ y, int64_t ldy, const float* __restrict__ scale_offset, int do_ln,
     const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ edge_perm, void* __restrict__ out,
     int out_dtype, int64_t ldo, int64_t num_segments) {
@@ -519,18 +523,19 @@ int gc_ln_cond_segment_sum(void* stream, const void* y, int32_t y_dtype, int64_t
   if (num_segments <= 0) return GC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const unsigned grid = grid_for(num_segments, SEG_WARPS, 8);
-#define GC_LAUNCH_SEG(NV, BF)                                                                                  \
-  GC_CHECK_CUDA(launch_kernel(ln_cond_segment_sum_kernel<NV, BF>, dim3(grid), dim3(SEG_WARPS * 32), 0, st, y, ldy,     \
+#define GC_LAUNCH_SEG(NV, BF, OCC)                                                                             \
+  GC_CHECK_CUDA(launch_kernel(ln_cond_segment_sum_kernel<NV, BF, OCC>, dim3(grid), dim3(SEG_WARPS * 32), 0, st, y, ldy, \
                               scale_offset, do_layer_norm, row_ptr, edge_perm, out, out_dtype, ldo, num_segments),      \
                 "ln_cond_segment_sum_kernel")
   if (y_dtype == GC_BF16) {
-    if (cols == 128) GC_LAUNCH_SEG(4, true);
-    else if (cols == 256) GC_LAUNCH_SEG(8, true);
-    else GC_LAUNCH_SEG(16, true);
+    if (cols == 128) GC_LAUNCH_SEG(4, true, 2);
+    else if (cols == 256) GC_LAUNCH_SEG(8, true, 2);
+    else if (edge_perm != nullptr) GC_LAUNCH_SEG(16, true, 3);
+    else GC_LAUNCH_SEG(16, true, 2);
   } else {
-    if (cols == 128) GC_LAUNCH_SEG(4, false);
-    else if (cols == 256) GC_LAUNCH_SEG(8, false);
-    else GC_LAUNCH_SEG(16, false);
+    if (cols == 128) GC_LAUNCH_SEG(4, false, 2);
+    else if (cols == 256) GC_LAUNCH_SEG(8, false, 2);
+    else GC_LAUNCH_SEG(16, false, 2);
   }
 #undef GC_LAUNCH_SEG
   GC_CHECK_LAUNCH("ln_cond_segment_sum_kernel");
