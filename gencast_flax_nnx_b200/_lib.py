@@ -16,6 +16,7 @@ GC_ACT_NONE = 0
 GC_ACT_SWISH = 1
 GC_ACT_GELU_TANH = 2
 GC_MAX_SEGMENTS = 3
+GC_GEMM_STATIC_WEIGHTS = 1
 
 LIB_PATH = Path(__file__).resolve().parent / "libgencast_b200.so"
 
@@ -48,7 +49,7 @@ class GemmArgs(Structure):
         ("out", c_void_p),
         ("ldo", c_int64),
         ("out_dtype", c_int32),
-        ("reserved", c_int32),
+        ("flags", c_int32),
     ]
 
 

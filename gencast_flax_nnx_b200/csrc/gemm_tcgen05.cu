@@ -73,6 +73,7 @@ struct GemmShape {
   int n_tiles;
   int store_mode;
   int gather_staged;               // row gathers go through the shared-memory transposition (staged store modes only)
+  int early_w;                     // W tiles of the first stages may be fetched before griddepcontrol.wait
 };
 
 // Epilogue of one warp for one accumulator buffer: 32 rows (its TMEM lane quarter) x HALF columns.
@@ -310,15 +311,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmShape 
 
   if (warp == 0) {
     if (lane == 0) {
+      // Weights first: with static W (shape.early_w) the W tiles of the first ring pass are requested before
+      // waiting for the predecessor grid, so their HBM latency overlaps its tail.
+      int pre = 0;
+      if (shape.early_w) {
+        for (int s = 0; s < shape.num_segments && pre < STAGES; ++s)
+          for (int kb = 0; kb < shape.kblocks[s] && pre < STAGES; ++kb, ++pre) {
+            mbar_arrive_expect_tx(full_bar(pre), C::STAGE_BYTES);
+            tma_load_2d(smem_b + pre * C::B_STAGE_BYTES, &maps.w[s], full_bar(pre), kb * BK, n_blk * BN);
+          }
+      }
       pdl_wait();            // first touch of operands a predecessor may have produced
-      int stage = 0;
+      int stage = 0, issued = 0;
       uint32_t phase = 0;
       for (int s = 0; s < shape.num_segments; ++s) {
-        for (int kb = 0; kb < shape.kblocks[s]; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+        for (int kb = 0; kb < shape.kblocks[s]; ++kb, ++issued) {
+          if (issued >= pre) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            tma_load_2d(smem_b + stage * C::B_STAGE_BYTES, &maps.w[s], full_bar(stage), kb * BK, n_blk * BN);
+          }
           tma_load_2d(smem_a + stage * A_STAGE_BYTES, &maps.a[s], full_bar(stage), kb * BK, m_blk * BM);
-          tma_load_2d(smem_b + stage * C::B_STAGE_BYTES, &maps.w[s], full_bar(stage), kb * BK, n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -456,23 +469,38 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const
 
   if (warp == 0) {
     if (lane == 0) {
+      auto load_w = [&](int st, int s, int kb, int n_blk) {
+        // W box is 128 rows: two boxes for a 256-wide tile
+#pragma unroll
+        for (int h = 0; h < PBN / 128; ++h)
+          tma_load_2d(smem_b + st * C::B_STAGE_BYTES + h * (128 * BK * 2), &maps.w[s], full_bar(st), kb * BK,
+                      n_blk * PBN + h * 128);
+      };
+      // weights of the first ring pass before the wait for the predecessor grid (see the one-tile kernel)
+      int pre = 0;
+      if (shape.early_w && static_cast<int>(blockIdx.x) < num_tiles) {
+        const int n_blk0 = static_cast<int>(blockIdx.x) % shape.n_tiles;
+        for (int s = 0; s < shape.num_segments && pre < PSTAGES; ++s)
+          for (int kb = 0; kb < shape.kblocks[s] && pre < PSTAGES; ++kb, ++pre) {
+            mbar_arrive_expect_tx(full_bar(pre), C::STAGE_BYTES);
+            load_w(pre, s, kb, n_blk0);
+          }
+      }
       pdl_wait();
-      int stage = 0;
+      int stage = 0, issued = 0;
       uint32_t phase = 0;
       int ev = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_blk = tile % shape.n_tiles, m_blk = tile / shape.n_tiles;
         for (int s = 0; s < shape.num_segments; ++s) {
-          for (int kb = 0; kb < shape.kblocks[s]; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            GC_GTRACE(0, ev); ++ev;
-            mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          for (int kb = 0; kb < shape.kblocks[s]; ++kb, ++issued) {
+            if (issued >= pre) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              GC_GTRACE(0, ev); ++ev;
+              mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+              load_w(stage, s, kb, n_blk);
+            }
             tma_load_2d(smem_a + stage * A_STAGE_BYTES, &maps.a[s], full_bar(stage), kb * BK, m_blk * BM);
-            // W box is 128 rows: two boxes for a 256-wide tile
-#pragma unroll
-            for (int h = 0; h < PBN / 128; ++h)
-              tma_load_2d(smem_b + stage * C::B_STAGE_BYTES + h * (128 * BK * 2), &maps.w[s], full_bar(stage), kb * BK,
-                          n_blk * PBN + h * 128);
             if (++stage == PSTAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -619,8 +647,18 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmS
 
   if (warp == 0) {
     if (lane == 0) {
+      // weights of the first ring pass before the wait for the predecessor grid (see the one-tile kernel)
+      int pre = 0;
+      if (shape.early_w && pair_id < num_tiles) {
+        const int n_row0 = (pair_id % shape.n_tiles) * QBN + static_cast<int>(rank) * 128;
+        for (int s = 0; s < shape.num_segments && pre < Q_STAGES; ++s)
+          for (int kb = 0; kb < shape.kblocks[s] && pre < Q_STAGES; ++kb, ++pre) {
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(pre), 2 * Q_STAGE_BYTES);
+            tma_load_2d_pair(smem_b + pre * Q_B_STAGE_BYTES, &maps.w[s], full_bar(pre), kb * BK, n_row0);
+          }
+      }
       pdl_wait();
-      int stage = 0;
+      int stage = 0, issued = 0;
       uint32_t phase = 0;
       int ev = 0;
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
@@ -628,13 +666,15 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmS
         const int m_row = m_pair * 256 + static_cast<int>(rank) * 128;
         const int n_row = n_blk * QBN + static_cast<int>(rank) * 128;
         for (int s = 0; s < shape.num_segments; ++s) {
-          for (int kb = 0; kb < shape.kblocks[s]; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            GC_GTRACE(0, ev); ++ev;
-            // the leader arms its barrier for the bytes of both CTAs
-            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Q_STAGE_BYTES);
+          for (int kb = 0; kb < shape.kblocks[s]; ++kb, ++issued) {
+            if (issued >= pre) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              GC_GTRACE(0, ev); ++ev;
+              // the leader arms its barrier for the bytes of both CTAs
+              if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Q_STAGE_BYTES);
+              tma_load_2d_pair(smem_b + stage * Q_B_STAGE_BYTES, &maps.w[s], full_bar(stage), kb * BK, n_row);
+            }
             tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &maps.a[s], full_bar(stage), kb * BK, m_row);
-            tma_load_2d_pair(smem_b + stage * Q_B_STAGE_BYTES, &maps.w[s], full_bar(stage), kb * BK, n_row);
             if (++stage == Q_STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -936,12 +976,21 @@ int make_tmap_out_2d(CUtensorMap* out, void* base, int dtype, uint64_t rows, uin
   return GC_OK;
 }
 
+bool early_w_enabled() {
+  static const bool on = []() {
+    const char* v = getenv("GENCAST_EARLY_W");
+    return !(v != nullptr && v[0] == '0');
+  }();
+  return on;
+}
+
 template <int BN, int NSTAGES>
 int launch_cfg(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
   using C = GemmCfg<BN, NSTAGES>;
   GemmMaps maps;
   GemmShape shape;
   shape.num_segments = a.num_segments;
+  shape.early_w = ((a.flags & GC_GEMM_STATIC_WEIGHTS) && early_w_enabled()) ? 1 : 0;
   shape.store_mode = STORE_DIRECT;
   shape.gather_staged = 0;
   shape.n_tiles = a.n / BN;
@@ -978,6 +1027,7 @@ int launch_persistent(cudaStream_t stream, const gc_gemm_args& a, const Epilogue
   GemmMaps maps;
   GemmShape shape;
   shape.num_segments = a.num_segments;
+  shape.early_w = ((a.flags & GC_GEMM_STATIC_WEIGHTS) && early_w_enabled()) ? 1 : 0;
   shape.n_tiles = a.n / PBN;
   for (int s = 0; s < GC_MAX_SEGMENTS; ++s) shape.kblocks[s] = 0;
   for (int s = 0; s < a.num_segments; ++s) {
@@ -1022,6 +1072,7 @@ int launch_pair(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams
   GemmMaps maps;
   GemmShape shape;
   shape.num_segments = a.num_segments;
+  shape.early_w = ((a.flags & GC_GEMM_STATIC_WEIGHTS) && early_w_enabled()) ? 1 : 0;
   shape.n_tiles = a.n / QBN;
   for (int s = 0; s < GC_MAX_SEGMENTS; ++s) shape.kblocks[s] = 0;
   for (int s = 0; s < a.num_segments; ++s) {
@@ -1078,6 +1129,7 @@ int launch_pair_resident(cudaStream_t stream, const gc_gemm_args& a, const Epilo
   GemmMaps maps;
   GemmShape shape;
   shape.num_segments = 1;
+  shape.early_w = 0;
   shape.n_tiles = a.n / QBN;
   for (int s = 0; s < GC_MAX_SEGMENTS; ++s) shape.kblocks[s] = 0;
   shape.kblocks[0] = a.k[0] / BK;

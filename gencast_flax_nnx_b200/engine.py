@@ -47,6 +47,12 @@ from .params import COND_DIM, mlp_prefixes
 _DTYPES = {"bf16": torch.bfloat16, "f32": torch.float32}
 
 
+def _gemm(*args, **kw):
+    """ops.gemm for model weights: they are never written by work queued on the stream, so the kernels may
+    fetch their first W tiles before the preceding kernel has finished (GC_GEMM_STATIC_WEIGHTS)."""
+    return ops.gemm(*args, static_weights=True, **kw)
+
+
 def _pad_to(n: int, mult: int) -> int:
     return (n + mult - 1) // mult * mult
 
@@ -359,8 +365,8 @@ class DenoiserEngine:
         a = self._dev(a, self.cd)
         w1 = self._wt(k1, w_rows, kp)
         h, y, out = self._buf(n, self.L), self._buf(n, self.L), self._buf(n, self.L)
-        ops.gemm([(a, w1)], h, bias=self._bias(b1), act="swish")
-        ops.gemm([(h, self._wt(k2))], y, bias=self._bias(b2))
+        _gemm([(a, w1)], h, bias=self._bias(b1), act="swish")
+        _gemm([(h, self._wt(k2))], y, bias=self._bias(b2))
         ops.ln_cond(y, out, None)
         return out
 
@@ -447,8 +453,8 @@ class DenoiserEngine:
 
     # ------------------------------------------------------------------ forward
     def _mlp_ln(self, segs, w1b, w2, b2, h, y, out, so, residual=None, gathers=(), act="swish"):
-        ops.gemm(segs, h, bias=w1b, act=act, gathers=gathers)
-        ops.gemm([(h, w2)], y, bias=b2)
+        _gemm(segs, h, bias=w1b, act=act, gathers=gathers)
+        _gemm([(h, w2)], y, bias=b2)
         ops.ln_cond(y, out, so, residual=residual)
 
     def _grid_branch(self, ctx: SigmaContext) -> None:
@@ -457,7 +463,7 @@ class DenoiserEngine:
         w, T = self.w, ctx.table
         self._mlp_ln([(self.g0, w["gu_w1"])], w["gu_b1"], w["gu_w2"], w["gu_b2"],
                      self.g_h2, self.g_y2, self.g_lat, T[self.C_G2M_GU], residual=self.g0)
-        ops.gemm([(self.g_lat, w["du_w1r"])], self.g_p2)
+        _gemm([(self.g_lat, w["du_w1r"])], self.g_p2)
 
     def forward(self, ctx: SigmaContext, branch_stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
         """One network evaluation F(xin, sigma) -> self.f_out [G, NO] fp32 (first n_out columns valid).
@@ -478,12 +484,12 @@ class DenoiserEngine:
             with torch.cuda.stream(branch_stream):
                 self._grid_branch(ctx)
         ops.ln_cond(self.m0_ln, self.m0, T[self.C_G2M_ME], layer_norm=False)
-        ops.gemm([(self.g0, w["eu_w1s"])], self.g_p)
-        ops.gemm([(self.m0, w["eu_w1r"])], self.m_p)
+        _gemm([(self.g0, w["eu_w1s"])], self.g_p)
+        _gemm([(self.m0, w["eu_w1r"])], self.m_p)
         e_h, e_y = self.e_h[:E1], self.e_y[:E1]
-        ops.gemm([(self.g2m_e_ln, ctx.g2m_w1e)], e_h, bias=ctx.g2m_b1, act="swish",
+        _gemm([(self.g2m_e_ln, ctx.g2m_w1e)], e_h, bias=ctx.g2m_b1, act="swish",
                  gathers=[(self.g_p, self.g2m_s), (self.m_p, self.g2m_r)])
-        ops.gemm([(e_h, w["eu_w2"])], e_y, bias=w["eu_b2"])
+        _gemm([(e_h, w["eu_w2"])], e_y, bias=w["eu_b2"])
         ops.ln_cond_segment_sum(e_y, self.m_agg, T[self.C_G2M_EU], self.g2m_row_ptr, self.g2m_perm)
         self._mlp_ln([(self.m0, w["mu_w1a"]), (self.m_agg, w["mu_w1b"])], w["mu_b1"], w["mu_w2"], w["mu_b2"],
                      self.m_h, self.m_y, self.x, T[self.C_G2M_MU], residual=self.m0)
@@ -492,26 +498,26 @@ class DenoiserEngine:
         # ---- processor (gencast/sparse_transformer.py:486-525, :624-634)
         for i in range(self.NL):
             ops.ln_cond(self.x, self.t_h, T[self.C_T0 + 2 * i])
-            ops.gemm([(self.t_h, w[f"t{i}_qkv"])], self.t_qkv)
+            _gemm([(self.t_h, w[f"t{i}_qkv"])], self.t_qkv)
             self._attention()
-            ops.gemm([(self.t_o, w[f"t{i}_wo"])], self.x, bias=w[f"t{i}_bo"], residual=self.x)
+            _gemm([(self.t_o, w[f"t{i}_wo"])], self.x, bias=w[f"t{i}_bo"], residual=self.x)
             ops.ln_cond(self.x, self.t_h, T[self.C_T0 + 2 * i + 1])
-            ops.gemm([(self.t_h, w[f"t{i}_w1"])], self.t_f, bias=w[f"t{i}_b1"], act="gelu_tanh")
-            ops.gemm([(self.t_f, w[f"t{i}_w2"])], self.x, bias=w[f"t{i}_b2"], residual=self.x)
+            _gemm([(self.t_h, w[f"t{i}_w1"])], self.t_f, bias=w[f"t{i}_b1"], act="gelu_tanh")
+            _gemm([(self.t_f, w[f"t{i}_w2"])], self.x, bias=w[f"t{i}_b2"], residual=self.x)
         ops.ln_cond(self.x, self.m_out, T[self.C_TFINAL])
         # ---- decoder (gencast/denoiser.py:730-768)
-        ops.gemm([(self.m_out, w["du_w1s"])], self.m_p)
+        _gemm([(self.m_out, w["du_w1s"])], self.m_p)
         if branch_stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(branch_stream)
         e_h, e_y = self.e_h[:E2], self.e_y[:E2]
-        ops.gemm([(self.m2g_e_ln, ctx.m2g_w1e)], e_h, bias=ctx.m2g_b1, act="swish",
+        _gemm([(self.m2g_e_ln, ctx.m2g_w1e)], e_h, bias=ctx.m2g_b1, act="swish",
                  gathers=[(self.m_p, self.m2g_s), (self.g_p2, self.m2g_r)])
-        ops.gemm([(e_h, w["du_w2"])], e_y, bias=w["du_b2"])
+        _gemm([(e_h, w["du_w2"])], e_y, bias=w["du_b2"])
         ops.ln_cond_segment_sum(e_y, self.g_agg, T[self.C_M2G_EU], self.m2g_row_ptr, self.m2g_perm)
         self._mlp_ln([(self.g_lat, w["dg_w1a"]), (self.g_agg, w["dg_w1b"])], w["dg_b1"], w["dg_w2"], w["dg_b2"],
                      self.g_h, self.g_y, self.g2, T[self.C_M2G_GU], residual=self.g_lat)
-        ops.gemm([(self.g2, w["out_w1"])], self.g_h, bias=w["out_b1"], act="swish")
-        ops.gemm([(self.g_h, w["out_w2"])], self.f_out, bias=w["out_b2"])
+        _gemm([(self.g2, w["out_w1"])], self.g_h, bias=w["out_b1"], act="swish")
+        _gemm([(self.g_h, w["out_w2"])], self.f_out, bias=w["out_b2"])
         return self.f_out
 
     def _attention(self):

@@ -61,7 +61,8 @@ def _nbytes(*ts):
     return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
 
 
-def _gemm_cost(segments, out, *, bias=None, act=None, addend=None, gathers=(), residual=None, alpha=None):
+def _gemm_cost(segments, out, *, bias=None, act=None, addend=None, gathers=(), residual=None, alpha=None,
+               static_weights=False):
     m, n = out.shape
     flops = 2.0 * m * n * sum(a.shape[1] for a, _ in segments)
     by = sum(_nbytes(a, w) for a, w in segments) + _nbytes(out, addend, residual)
@@ -106,7 +107,8 @@ def gemm(segments: Sequence[Tuple[torch.Tensor, torch.Tensor]], out: torch.Tenso
          bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
          addend: Optional[torch.Tensor] = None,
          gathers: Sequence[Tuple[torch.Tensor, torch.Tensor]] = (),
-         residual: Optional[torch.Tensor] = None, alpha: Optional[torch.Tensor] = None) -> torch.Tensor:
+         residual: Optional[torch.Tensor] = None, alpha: Optional[torch.Tensor] = None,
+         static_weights: bool = False) -> torch.Tensor:
     """out = act(alpha * sum_s A_s @ W_s^T + bias + addend + sum_j G_j[idx_j]) + residual.
 
     segments: [(A_s [m, k_s], W_s [n, k_s])], all of one dtype (bf16 -> tcgen05, f32 -> FFMA).
@@ -141,6 +143,9 @@ def gemm(segments: Sequence[Tuple[torch.Tensor, torch.Tensor]], out: torch.Tenso
     if residual is not None:
         args.residual = residual.data_ptr(); args.ld_res = _row_major(residual, "residual"); args.res_dtype = _dt(residual)
     args.out = out.data_ptr(); args.ldo = _row_major(out, "out"); args.out_dtype = _dt(out)
+    # static_weights: the W matrices are not produced by earlier work on this stream (model weights), so the
+    # kernel may fetch their first tiles while the preceding kernel is still draining
+    args.flags = _lib.GC_GEMM_STATIC_WEIGHTS if static_weights else 0
     _lib.check(lib.gc_gemm(_stream(), ctypes.byref(args)), "gc_gemm")
     return out
 

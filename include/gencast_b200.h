@@ -45,6 +45,7 @@ extern "C" {
 #define GC_ERR_CUDA (-2)
 #define GC_ERR_UNSUPPORTED (-3)
 
+#define GC_GEMM_STATIC_WEIGHTS 1
 #define GC_MAX_SEGMENTS 3
 
 /* Library / device introspection. */
@@ -97,7 +98,9 @@ typedef struct gc_gemm_args {
   void* out;                /* [m, n] */
   int64_t ldo;
   int32_t out_dtype;
-  int32_t reserved;
+  int32_t flags;                 /* GC_GEMM_STATIC_WEIGHTS: the W matrices are not written by earlier work on this
+                                    stream, so their first tiles may be fetched before the preceding kernel has
+                                    finished (under programmatic dependent launch); 0 = no assumption */
 } gc_gemm_args;
 
 GC_API int gc_gemm(void* stream, const gc_gemm_args* args);
