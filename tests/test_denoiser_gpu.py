@@ -239,3 +239,35 @@ def test_device_rollout_equals_host_rollout(cuda_device):
         assert dev[k].dims == host[k].dims
         np.testing.assert_array_equal(dev[k].data, host[k].data)
     assert not np.array_equal(host["2m_temperature"].data[:, 0], host["2m_temperature"].data[:, 1])
+
+
+def test_benched_workload_1deg_four_members_equal_single_member_runs(cuda_device):
+    """The default bench.py workload (GenCast 1 deg, 4 members evaluated together in bf16: CTA-pair GEMMs with
+    staged gathers, TS-form attention over 4 x 81 query tiles, pipelined segment sums) gives every member what
+    the one-member engine gives it, which test_full_size_1deg_properties ties to the fp32 path and, through
+    it, to the oracle."""
+    from gencast_flax_nnx_b200.engine import DenoiserEngine
+    case = make_case("1deg")
+    B, G = 4, case.graphs.num_grid_nodes
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((B, G, 82)).astype(np.float32)
+    inp = np.stack([case.inp_nodes[:, 0] * (1 + 0.05 * b) for b in range(B)])
+    frc = np.stack([case.frc_nodes[:, 0]] * B)
+    e1 = DenoiserEngine(case.graphs, case.arch, case.params, case.layout, compute_dtype="bf16")
+    single = []
+    for b in (0, 3):
+        e1.set_constant_features(inp[b], frc[b])
+        e1.set_network_input(x[b])
+        single.append(e1.read_output(e1.forward(e1.sigma_context(1.0))))
+    del e1
+    torch.cuda.empty_cache()
+    eb = DenoiserEngine(case.graphs, case.arch, case.params, case.layout, compute_dtype="bf16", members=B)
+    eb.set_constant_features(inp.reshape(B * G, -1), frc.reshape(B * G, -1))
+    eb.set_network_input(x.reshape(B * G, 82))
+    got = eb.read_output(eb.forward(eb.sigma_context(1.0))).reshape(B, G, 82)
+    assert np.isfinite(got).all()
+    for ref, b in zip(single, (0, 3)):
+        err = np.abs(got[b] - ref).max() / np.abs(ref).max()
+        print(f"1deg x 4 members, member {b}: max relative difference to the one-member engine {err:.2e}")
+        assert err <= 1e-6
+    assert not np.array_equal(got[0], got[3])
