@@ -55,7 +55,7 @@ struct AttCfg {
   static constexpr int Q_BYTES = TQ * D * 2;
   // K / V tile ring: a K tile and the V tile listed with it are consumed back to back (PV(t), S(t+2))
   static constexpr int NSLOT = D == 64 ? 10 : 6;
-  static constexpr int SMEM = Q_BYTES + NSLOT * SLOT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM = Q_BYTES + NSLOT * SLOT_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 64 /*tile_kv ring*/;
 };
 
 struct AttParams {
@@ -98,6 +98,9 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
   auto p_full = [&](int b) { return b2 + 8u * (2 + b); };
   const uint32_t o_full = b2 + 8u * 4;
   const uint32_t tmem_ptr_smem = b2 + 8u * 5;
+  // tile_kv entries of the tiles in flight, written by the TMA producer before it requests K_t and read by
+  // the MMA issuer after the tile has landed (the mbarrier orders them): no global load on the issuer's path
+  volatile uint32_t* kv_ring = reinterpret_cast<volatile uint32_t*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -152,17 +155,27 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
         if (++slot == C::NSLOT) { slot = 0; phase ^= 1u; }
       };
       // consumption order: K_0, K_1, then per tile t: V_t, K_{t+2}
-      for (int t = 0; t < 2 && t < T; ++t) load_tile(k_col, __ldg(p.tile_kv + t_beg + t));
+      auto load_k = [&](int t) {
+        const uint32_t kv = static_cast<uint32_t>(__ldg(p.tile_kv + t_beg + t));
+        kv_ring[t & 15] = kv;
+        load_tile(k_col, static_cast<int>(kv & 0xffffffu));
+      };
+      for (int t = 0; t < 2 && t < T; ++t) load_k(t);
       for (int t = 0; t < T; ++t) {
-        load_tile(v_col, __ldg(p.tile_kv + t_beg + t));
-        if (t + 2 < T) load_tile(k_col, __ldg(p.tile_kv + t_beg + t + 2));
+        load_tile(v_col, static_cast<int>(kv_ring[t & 15] & 0xffffffu));
+        if (t + 2 < T) load_k(t + 2);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer
-      constexpr uint32_t idesc_s = idesc_bf16_f32(TQ, TK, 0, 0);
       constexpr uint32_t idesc_o = idesc_bf16_f32(TQ, D, 0, 1);     // B = V tile, MN-major
+      // live key range of a pair, in 32-key sub-blocks: [lo, lo + cnt)
+      auto key_range = [&](int t, int& lo, int& cnt) {       // call after K_t has landed
+        const uint32_t kv = kv_ring[t & 15];
+        lo = static_cast<int>((kv >> 24) & 3u);
+        cnt = 4 - lo - static_cast<int>((kv >> 26) & 3u);
+      };
       int slot = 0;
       uint32_t slot_phase = 0;
       int g = 0;     // S iterations issued so far (buffer g & 1, use count g >> 1)
@@ -170,14 +183,19 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
       auto issue_s = [&]() {
         const int b = g & 1;
         mbar_wait(slot_full(slot), slot_phase);
+        int lo, cnt;
+        key_range(g, lo, cnt);
+        // N = 32 cnt keys starting at key 32 lo: K rows 32 lo .. of the tile (4 KB per 32 rows and 64-wide d
+        // chunk), S columns 32 lo .. of the group's buffer, so that column = key as the softmax expects
+        const uint32_t idesc_s = idesc_bf16_f32(TQ, 32 * cnt, 0, 0);
         GC_TRACE(1, 2 * mma_ev);
         GC_TRACE(1, 2 * mma_ev + 1); ++mma_ev;
         tc_fence_after();
-        const uint32_t k_base = slot_smem + slot * C::SLOT_BYTES;
+        const uint32_t k_base = slot_smem + slot * C::SLOT_BYTES + static_cast<uint32_t>(lo) * 4096u;
 #pragma unroll
         for (int j = 0; j < D / 16; ++j) {
           const uint32_t off = (j >> 2) * (TQ * 128) + (j & 3) * 32;
-          umma_f16(tmem_s0 + b * 128, desc_kmajor_sw128(q_smem + off), desc_kmajor_sw128(k_base + off), idesc_s, j > 0);
+          umma_f16(tmem_s0 + b * 128 + 32 * lo, desc_kmajor_sw128(q_smem + off), desc_kmajor_sw128(k_base + off), idesc_s, j > 0);
         }
         umma_commit(slot_empty(slot));
         umma_commit(s_full(b));
@@ -194,13 +212,15 @@ khop_attention_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttP
         GC_TRACE(2, 2 * t + 1);
         tc_fence_after();
         const uint32_t v_base = slot_smem + slot * C::SLOT_BYTES;
-#pragma unroll
-        for (int j = 0; j < TK / 16; ++j) {
+        int lo, cnt;
+        key_range(t, lo, cnt);
+        // two 16-key MMA steps per live 32-key sub-block
+        for (int j = 2 * lo; j < 2 * (lo + cnt); ++j) {
           // A: P[128 x 16 keys] from tensor memory: lane = query row, 8 columns of two bf16 each.
           // B: V[16 keys x D], MN-major: 16 key rows of 128 B start at j * 2048; 64-wide d chunks are
           // TK * 128 bytes apart.
           const uint64_t db = desc_mnmajor_sw128(v_base + j * 2048, TK * 128, 1024);
-          umma_f16_ts(tmem_o + (t & 1) * D, tmem_s0 + pb * 128 + 8 * j, db, idesc_o, (t > 1 || j > 0) ? 1u : 0u);
+          umma_f16_ts(tmem_o + (t & 1) * D, tmem_s0 + pb * 128 + 8 * j, db, idesc_o, (t > 1 || j > 2 * lo) ? 1u : 0u);
         }
         umma_commit(slot_empty(slot));
         if (++slot == C::NSLOT) { slot = 0; slot_phase ^= 1u; }

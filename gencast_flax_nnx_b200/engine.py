@@ -41,7 +41,7 @@ import torch
 
 from . import ops
 from .configs import DenoiserArchitectureConfig, NoiseEncoderConfig
-from .graph import DenoiserGraphs, csr_by_receiver, khop_tiles, patch_order
+from .graph import DenoiserGraphs, csr_by_receiver, khop_tiles, pack_key_ranges, patch_order
 from .params import COND_DIM, mlp_prefixes
 
 _DTYPES = {"bf16": torch.bfloat16, "f32": torch.float32}
@@ -257,6 +257,7 @@ class DenoiserEngine:
                 tp = np.concatenate([tp[:-1].astype(np.int64) + b * len(tk) for b in range(B)] + [[B * len(tk)]]).astype(np.int32)
                 tk = blocks(tk, nq)
                 tm = np.tile(tm, (B, 1, 1))
+            tk = pack_key_ranges(tk, tm)
             self.tile_ptr, self.tile_kv = self._dev(tp), self._dev(tk)
             self.tile_mask = self._dev(tm.view(np.int32)).view(torch.int32)
             self.num_attention_tiles = int(len(tk))

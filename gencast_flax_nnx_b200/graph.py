@@ -379,6 +379,23 @@ def khop_tiles(khop: sparse.spmatrix, tile: int = 128):
     return tile_ptr, tile_kv, np.ascontiguousarray(mask)
 
 
+def pack_key_ranges(tile_kv: np.ndarray, tile_mask: np.ndarray) -> np.ndarray:
+    """Annotates every listed (query tile, key tile) pair with the 32-key sub-blocks no query of the pair
+    attends to at either end of the key tile: bits 24-25 of tile_kv = number of leading dead sub-blocks,
+    bits 26-27 = trailing ones (0 = the whole tile is used, which is what an unannotated list says).
+    The tensor-core attention kernel then forms S and P V over the live key range only (N = 32 .. 128):
+    with the hierarchical patch order the range is 2.86 of 4 sub-blocks on average at 1 deg."""
+    kv = np.asarray(tile_kv, np.int64)
+    if kv.size and kv.max() >= (1 << 24):
+        raise ValueError("pack_key_ranges: key tile index does not fit 24 bits")
+    m = np.asarray(tile_mask).view(np.uint32).reshape(len(kv), -1, 4)
+    live = (m != 0).any(axis=1)                                   # [tiles, 4]
+    any_live = live.any(axis=1)
+    first = np.where(any_live, live.argmax(axis=1), 0)
+    last = np.where(any_live, 3 - live[:, ::-1].argmax(axis=1), 3)
+    return (kv | (first.astype(np.int64) << 24) | ((3 - last).astype(np.int64) << 26)).astype(np.int32)
+
+
 def patch_order(xyz: np.ndarray, leaf: int = 128, sub_leaf: int = 32) -> np.ndarray:
     """Permutation that groups mesh nodes into spatially compact patches of `leaf` nodes, each of
     which is itself ordered into compact sub-patches of `sub_leaf` nodes.

@@ -159,6 +159,9 @@ GC_API int gc_khop_attention(void* stream, const void* qkv, int32_t dtype, int64
  * least one neighbour, and tile_mask holds one 128 x 128 bit mask per pair
  * ([pair][row][4] uint32, bit (j % 32) of word (j / 32) = key tile_kv * 128 + j is a
  * neighbour of query t * 128 + row).  Same reference operator as gc_khop_attention.
+ * tile_kv[p]: bits 0-23 the key tile index; optionally bits 24-25 / 26-27 the number of
+ * leading / trailing 32-key sub-blocks of the pair that no query attends to (their mask bits
+ * must be zero): S and P V are then formed over the live key range only.  0 = whole tile.
  * head_dim 64 or 128.
  */
 GC_API int gc_khop_attention_tiles(void* stream, const void* qkv, int64_t ld_qkv, const int32_t* tile_ptr,
