@@ -456,6 +456,53 @@ __global__ void __launch_bounds__(256) select_columns_kernel(const float* __rest
   }
 }
 
+// One thread per (grid point, channel): its M member values sit in a shared-memory column
+// ([M][256] floats, conflict free), are insertion-sorted there, and the two CRPS terms are summed
+// in member / rank order (deterministic).
+constexpr int CRPS_MAX_MEMBERS = 64;
+__global__ void __launch_bounds__(256) fair_crps_kernel(const float* __restrict__ members, int64_t ldm, int M,
+                                                        const float* __restrict__ truth,
+                                                        const float* __restrict__ weights, int channels,
+                                                        float* __restrict__ out, int64_t n) {
+  extern __shared__ float col[];                 // [M][256]
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tid = threadIdx.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + tid; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float y = __ldg(truth + i);
+    float skill = 0.0f;
+    for (int m = 0; m < M; ++m) {
+      const float x = __ldg(members + m * ldm + i);
+      skill += fabsf(x - y);
+      int k = m;                                  // insertion into the sorted prefix
+      while (k > 0 && col[(k - 1) * 256 + tid] > x) { col[k * 256 + tid] = col[(k - 1) * 256 + tid]; --k; }
+      col[k * 256 + tid] = x;
+    }
+    float pair = 0.0f;
+    for (int k = 0; k < M; ++k) pair = fmaf(static_cast<float>(2 * k - M + 1), col[k * 256 + tid], pair);
+    const float crps = skill / static_cast<float>(M) - pair / (static_cast<float>(M) * static_cast<float>(M - 1));
+    out[i] = (weights != nullptr ? __ldg(weights + i / channels) : 1.0f) * crps;
+  }
+}
+
+// One block per column: strided partial sums per thread, then a fixed tree.
+__global__ void __launch_bounds__(256) column_sums_kernel(const float* __restrict__ x, int64_t rows, int cols,
+                                                          float* __restrict__ sums) {
+  __shared__ float red[256];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c = blockIdx.x;
+  float acc = 0.0f;
+  for (int64_t r = threadIdx.x; r < rows; r += blockDim.x) acc += __ldg(x + r * cols + c);
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sums[c] = red[0];
+}
+
 __global__ void __launch_bounds__(256) ensemble_accumulate_kernel(const float* __restrict__ x, float* __restrict__ sum,
                                                                   float* __restrict__ sumsq, int64_t n) {
   pdl_launch_dependents();
@@ -604,6 +651,32 @@ int gc_select_columns(void* stream, const float* src0, int64_t ld0, const float*
   GC_CHECK_CUDA(launch_kernel(select_columns_kernel, dim3(grid_for(rows * cols_out, 256 * 4, 8)), dim3(256), 0, st, src0, ld0,
                               src1, ld1, src2, ld2, table, out, ldo, rows, cols_out), "select_columns_kernel");
   GC_CHECK_LAUNCH("select_columns_kernel");
+  return GC_OK;
+}
+
+int gc_fair_crps(void* stream, const float* members, int64_t ld_members, int32_t num_members, const float* truth,
+                 const float* weights, int32_t channels, float* out, int64_t n) {
+  GC_REQUIRE(members && truth && out, "gc_fair_crps: null buffer");
+  GC_REQUIRE(num_members >= 2 && num_members <= CRPS_MAX_MEMBERS, "gc_fair_crps: num_members=%d (2 .. %d)", num_members,
+             CRPS_MAX_MEMBERS);
+  GC_REQUIRE(channels >= 1 && ld_members >= n, "gc_fair_crps: bad sizes");
+  if (n <= 0) return GC_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t smem = static_cast<size_t>(num_members) * 256 * sizeof(float);
+  GC_CHECK_CUDA(cudaFuncSetAttribute(fair_crps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                "cudaFuncSetAttribute(fair_crps_kernel)");
+  GC_CHECK_CUDA(launch_kernel(fair_crps_kernel, dim3(grid_for(n, 256, 2)), dim3(256), smem, st, members, ld_members,
+                              (int)num_members, truth, weights, (int)channels, out, n), "fair_crps_kernel");
+  GC_CHECK_LAUNCH("fair_crps_kernel");
+  return GC_OK;
+}
+
+int gc_column_sums(void* stream, const float* x, int64_t rows, int32_t cols, float* sums) {
+  GC_REQUIRE(x && sums, "gc_column_sums: null buffer");
+  GC_REQUIRE(cols >= 1 && rows >= 0, "gc_column_sums: bad sizes");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GC_CHECK_CUDA(launch_kernel(column_sums_kernel, dim3(cols), dim3(256), 0, st, x, rows, (int)cols, sums), "column_sums_kernel");
+  GC_CHECK_LAUNCH("column_sums_kernel");
   return GC_OK;
 }
 

@@ -260,6 +260,30 @@ def select_columns(sources: Sequence[Optional[torch.Tensor]], table: torch.Tenso
     return out
 
 
+def fair_crps(members: torch.Tensor, truth: torch.Tensor, weights: Optional[torch.Tensor], channels: int) -> torch.Tensor:
+    """members [M, n] fp32, truth [n], weights [n / channels] or None -> weighted fair CRPS per point, [n] fp32."""
+    lib = _lib.load()
+    M, n = members.shape
+    if members.dtype != torch.float32 or truth.dtype != torch.float32 or truth.numel() != n:
+        raise TypeError("fair_crps: members [M, n] and truth [n] must be fp32")
+    if weights is not None and (weights.dtype != torch.float32 or weights.numel() * channels != n):
+        raise TypeError("fair_crps: weights must be fp32 [n / channels]")
+    out = torch.empty(n, dtype=torch.float32, device=members.device)
+    _lib.check(lib.gc_fair_crps(_stream(), members.data_ptr(), _row_major(members, "members"), M, truth.data_ptr(),
+                                _p(weights), channels, out.data_ptr(), n), "gc_fair_crps")
+    return out
+
+
+def column_sums(x: torch.Tensor) -> torch.Tensor:
+    """[rows, cols] fp32 -> [cols] sums over rows in a fixed order."""
+    lib = _lib.load()
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise TypeError("column_sums: contiguous fp32 matrix expected")
+    out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
+    _lib.check(lib.gc_column_sums(_stream(), x.data_ptr(), x.shape[0], x.shape[1], out.data_ptr()), "gc_column_sums")
+    return out
+
+
 def ensemble_accumulate(x: torch.Tensor, total: torch.Tensor, total_sq: torch.Tensor):
     lib = _lib.load()
     _lib.check(lib.gc_ensemble_accumulate(_stream(), x.data_ptr(), total.data_ptr(), total_sq.data_ptr(), x.numel()),

@@ -91,6 +91,19 @@ def fair_crps(local_members: torch.Tensor, truth: torch.Tensor, weights: Optiona
         members = local_members
     M, G, C = members.shape
     lo, hi = (G * rank) // world, (G * (rank + 1)) // world      # this rank's grid slice
+    if members.is_cuda and members.dtype == torch.float32 and 2 <= M <= 64:
+        # on the GPU: gc_fair_crps (per point, sorted-sample identity in shared memory) + gc_column_sums
+        from . import ops
+        xs = members[:, lo:hi].reshape(M, -1).contiguous()
+        w = None if weights is None else weights[lo:hi].to(torch.float32).contiguous()
+        per_point = ops.fair_crps(xs, truth[lo:hi].to(torch.float32).reshape(-1).contiguous(), w, C)
+        num = ops.column_sums(per_point.reshape(hi - lo, C)).to(torch.float64)
+        den = (torch.full((C,), float(hi - lo), dtype=torch.float64, device=members.device) if w is None
+               else w.to(torch.float64).sum().expand(C).clone())
+        both = torch.stack([num, den])
+        if world > 1:
+            dist.all_reduce(both, group=group)
+        return (both[0] / both[1]).to(torch.float32)
     x = members[:, lo:hi].to(torch.float64)
     y = truth[lo:hi].to(torch.float64)
     w = torch.ones(hi - lo, dtype=torch.float64, device=x.device) if weights is None else weights[lo:hi].to(torch.float64)

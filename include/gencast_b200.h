@@ -233,6 +233,19 @@ GC_API int gc_select_columns(void* stream, const float* src0, int64_t ld0, const
                       int64_t rows, int32_t cols_out);
 
 /*
+ * Fair CRPS of an M-member ensemble per grid point and channel (no reference implementation
+ * exists; defined in DESIGN.md / parallel.py):
+ *   crps[i] = mean_m |x_m[i] - y[i]|  -  sum_{j<k} |x_j[i] - x_k[i]| / (M (M - 1))
+ * evaluated with the sorted-sample identity sum_{j<k} |x_j - x_k| = sum_k (2k - M + 1) x_(k).
+ * members: [M, n] fp32 (row stride ld_members), truth: [n]; out[i] = weight[i / channels] * crps[i]
+ * (weights may be NULL = 1).  2 <= M <= 64.  gc_column_sums then reduces out over grid points in a
+ * fixed order: sums[c] = sum_g x[g * channels + c].
+ */
+GC_API int gc_fair_crps(void* stream, const float* members, int64_t ld_members, int32_t num_members,
+                 const float* truth, const float* weights, int32_t channels, float* out, int64_t n);
+GC_API int gc_column_sums(void* stream, const float* x, int64_t rows, int32_t cols, float* sums);
+
+/*
  * Ensemble statistics accumulation (no reference implementation exists; defined
  * in DESIGN.md): sum[i] += x[i]; sumsq[i] += x[i]^2 over n elements.
  */

@@ -324,3 +324,30 @@ def test_errors_are_reported(cuda_device):
         ops.gemm([(a[:, :96], w[:, :96])], out)
     with pytest.raises(ValueError):
         ops.gemm([(a.cpu(), w.cpu())], out)
+
+
+@pytest.mark.parametrize("M", [2, 5, 32])
+def test_fair_crps_kernel(cuda_device, M):
+    """gc_fair_crps + gc_column_sums against the defining formula (parallel.py docstring) in fp64, through the
+    same entry point the ensemble code uses (parallel.fair_crps on one rank)."""
+    from gencast_flax_nnx_b200 import ops, parallel
+    g = torch.Generator(device="cpu").manual_seed(M)
+    G, C = 777, 5
+    x = torch.randn(M, G, C, generator=g)
+    x[:, 10] = x[0, 10]                                   # ties
+    y = torch.randn(G, C, generator=g)
+    w = torch.rand(G, generator=g) + 0.1
+    xd, yd = x.double(), y.double()
+    skill = (xd - yd[None]).abs().mean(0)
+    pair = (xd[:, None] - xd[None, :]).abs().sum((0, 1)) / 2 / (M * (M - 1))
+    ref_pt = skill - pair
+    d = cuda_device
+    got_pt = ops.fair_crps(x.reshape(M, -1).to(d), y.reshape(-1).to(d), None, C).cpu().reshape(G, C)
+    assert float((got_pt.double() - ref_pt).abs().max()) < 2e-5
+    ref = (ref_pt * w.double()[:, None]).sum(0) / w.double().sum()
+    got = parallel.fair_crps(x.to(d), y.to(d), w.to(d)).cpu()
+    assert float((got.double() - ref).abs().max() / ref.abs().max()) < 1e-5
+    again = parallel.fair_crps(x.to(d), y.to(d), w.to(d)).cpu()
+    assert torch.equal(got, again)                       # fixed summation order
+    host = parallel.fair_crps(x, y, w)                   # the torch formula used without a GPU
+    assert float((host.double() - ref).abs().max() / ref.abs().max()) < 1e-5
