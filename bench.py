@@ -294,6 +294,28 @@ def measure(args, config: str, MB: int, steps: int, warmup: int, dev, rank: int,
                   "host_buffers": "inputs / forcings Datasets in page-locked host memory (H2D every step); the "
                                   "prediction Dataset is host arrays (one D2H per step into page-locked memory)"}
     res["case"] = case
+    if args.rollout_steps > 0 and detailed:
+        # autoregressive rollout with the input window resident on the GPU (rollout.device_chunked_prediction):
+        # inputs uploaded once, forcings per step, predictions downloaded per step
+        from gencast_flax_nnx_b200 import rollout, synthetic
+        R = args.rollout_steps
+        _, tgt_r, frc_r = synthetic.make_example(case["lat"], case["lon"], batch=MB, seed=0, num_target_steps=R)
+        frc_r = pin_dataset(frc_r)
+        for _ in rollout.device_chunked_prediction_generator(model, inputs_h, tgt_r.isel(time=slice(0, 1)), frc_r.isel(time=slice(0, 1))):
+            pass
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for pred in rollout.device_chunked_prediction_generator(model, inputs_h, tgt_r, frc_r):
+            pass
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res["rollout"] = {"steps": R, "value": world * MB * R / float(t.item()), "unit": UNIT,
+                          "api": "rollout.device_chunked_prediction_generator (window on the GPU; forcings H2D and "
+                                 "prediction D2H every step)"}
     if not detailed or rank != 0:
         del model, se, eng, stats, flush, noises
         torch.cuda.empty_cache()
@@ -441,6 +463,8 @@ def run_gpu(args):
             "clocks": main["clocks"], "roofline": main["roofline"], "kernels": main["kernels"],
             "kernels_note": "per-launch device durations from CUDA-event pairs around each launch of 3 eagerly "
                             "replayed denoiser evaluations (queued behind a device delay); shares are of their sum"}
+    if "rollout" in main:
+        line["rollout"] = main["rollout"]
     if also is not None:
         line["also"] = also
     if cpu is not None:
@@ -482,6 +506,8 @@ def main():
                     help="ensemble members evaluated together on each GPU (default: 4 for 1deg = BASELINE configs[3]'s "
                          "32 members / 8 GPUs, 1 otherwise)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the nano (configs[1]) measurement in the 1deg run")
+    ap.add_argument("--rollout-steps", type=int, default=0,
+                    help="also time an autoregressive rollout of this many 12 h steps (configs[1] / [3] name 30)")
     args = ap.parse_args()
     if args.members_per_gpu is None:
         args.members_per_gpu = DEFAULT_MEMBERS_PER_GPU.get(args.config, 1)
