@@ -456,6 +456,58 @@ __global__ void __launch_bounds__(256) select_columns_kernel(const float* __rest
   }
 }
 
+// One warp per base row e0 < period: the base row is read once and combined, member by member, with the
+// gathered rows of that member's edge e0 + m * period.  16-byte accesses, fp32 sums, MUFU activations (the same
+// swish_fast / gelu_tanh_fast as the GEMM epilogues this replaces).
+template <int NV>
+__global__ void __launch_bounds__(256) edge_hidden_kernel(const __nv_bfloat16* __restrict__ base, int64_t ldb, int64_t period,
+                                                          const __nv_bfloat16* __restrict__ g0, const int32_t* __restrict__ idx0, int64_t ld0,
+                                                          const __nv_bfloat16* __restrict__ g1, const int32_t* __restrict__ idx1, int64_t ld1,
+                                                          int act, __nv_bfloat16* __restrict__ out, int64_t ldo, int64_t rows) {
+  constexpr int W = NV % 8 == 0 ? 8 : 4;
+  constexpr int NCH = NV / W;
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int members = static_cast<int>(rows / period);
+  pdl_wait();
+  auto load = [&](const __nv_bfloat16* p, float (&v)[NV]) {
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      float t[W];
+      load_as_float<W>(p, GC_BF16, (j * 32 + lane) * W, t);
+#pragma unroll
+      for (int i = 0; i < W; ++i) v[j * W + i] = t[i];
+    }
+  };
+  for (int64_t e0 = warp0; e0 < period; e0 += nwarps) {
+    float b[NV];
+    load(base + e0 * ldb, b);
+    for (int m = 0; m < members; ++m) {
+      const int64_t e = e0 + static_cast<int64_t>(m) * period;
+      float a[NV], v[NV];
+      load(g0 + static_cast<int64_t>(__ldg(idx0 + e)) * ld0, a);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = b[i] + a[i];
+      if (g1 != nullptr) {
+        load(g1 + static_cast<int64_t>(__ldg(idx1 + e)) * ld1, a);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] += a[i];
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = apply_act<true>(v[i], act);
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        float t[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) t[i] = v[j * W + i];
+        store_from_float<W>(out, GC_BF16, e * ldo + (j * 32 + lane) * W, t);
+      }
+    }
+  }
+}
+
 // One thread per (grid point, channel): its M member values sit in a shared-memory column
 // ([M][256] floats, conflict free), are insertion-sorted there, and the two CRPS terms are summed
 // in member / rank order (deterministic).
@@ -651,6 +703,34 @@ int gc_select_columns(void* stream, const float* src0, int64_t ld0, const float*
   GC_CHECK_CUDA(launch_kernel(select_columns_kernel, dim3(grid_for(rows * cols_out, 256 * 4, 8)), dim3(256), 0, st, src0, ld0,
                               src1, ld1, src2, ld2, table, out, ldo, rows, cols_out), "select_columns_kernel");
   GC_CHECK_LAUNCH("select_columns_kernel");
+  return GC_OK;
+}
+
+int gc_edge_hidden(void* stream, const void* base, int64_t ld_base, int64_t period, const void* g0, const int32_t* idx0,
+                   int64_t ld0, const void* g1, const int32_t* idx1, int64_t ld1, int32_t act, void* out, int64_t ldo,
+                   int64_t rows, int32_t cols) {
+  GC_REQUIRE(base && g0 && idx0 && out, "gc_edge_hidden: null buffer");
+  GC_REQUIRE((g1 == nullptr) == (idx1 == nullptr), "gc_edge_hidden: g1 and idx1 go together");
+  GC_REQUIRE(cols == 128 || cols == 256 || cols == 512, "gc_edge_hidden: cols=%d (supported: 128, 256, 512)", cols);
+  GC_REQUIRE(period > 0 && rows >= 0 && rows % period == 0, "gc_edge_hidden: rows must be a multiple of period");
+  GC_REQUIRE(ld_base % 8 == 0 && ld0 % 8 == 0 && ldo % 8 == 0 && (g1 == nullptr || ld1 % 8 == 0) && aligned16(base) &&
+                 aligned16(g0) && aligned16(out) && (g1 == nullptr || aligned16(g1)),
+             "gc_edge_hidden: alignment");
+  GC_REQUIRE(act == GC_ACT_NONE || act == GC_ACT_SWISH || act == GC_ACT_GELU_TANH, "gc_edge_hidden: act=%d", act);
+  if (rows == 0) return GC_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned grid = grid_for(period, 8, 8);
+#define GC_LAUNCH_EH(NV)                                                                                            \
+  GC_CHECK_CUDA(launch_kernel(edge_hidden_kernel<NV>, dim3(grid), dim3(256), 0, st,                                  \
+                              reinterpret_cast<const __nv_bfloat16*>(base), ld_base, period,                         \
+                              reinterpret_cast<const __nv_bfloat16*>(g0), idx0, ld0,                                 \
+                              reinterpret_cast<const __nv_bfloat16*>(g1), idx1, ld1, (int)act,                       \
+                              reinterpret_cast<__nv_bfloat16*>(out), ldo, rows), "edge_hidden_kernel")
+  if (cols == 128) GC_LAUNCH_EH(4);
+  else if (cols == 256) GC_LAUNCH_EH(8);
+  else GC_LAUNCH_EH(16);
+#undef GC_LAUNCH_EH
+  GC_CHECK_LAUNCH("edge_hidden_kernel");
   return GC_OK;
 }
 

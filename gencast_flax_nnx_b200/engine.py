@@ -110,6 +110,8 @@ class SigmaContext:
     g2m_b1: torch.Tensor           # [L] fp32
     m2g_w1e: torch.Tensor
     m2g_b1: torch.Tensor
+    g2m_base: Optional[torch.Tensor] = None   # [E1, L] e' @ W1e' + b1 of one member (bf16), or None (computed per call)
+    m2g_base: Optional[torch.Tensor] = None   # [E2, L]
 
 
 class DenoiserEngine:
@@ -160,6 +162,7 @@ class DenoiserEngine:
         self.mesh_order = mesh_order
         self.use_tc_attention = (attention == "auto" and compute_dtype == "bf16" and self.head_dim in (64, 128))
         self._sigma_cache: Dict[float, SigmaContext] = {}
+        self.edge_table_budget_bytes = int(float(os.environ.get("GENCAST_EDGE_TABLE_GB", "24")) * 2 ** 30)
         with torch.cuda.device(self.device):
             self._upload_graph()
             self._upload_weights()
@@ -400,7 +403,18 @@ class DenoiserEngine:
             ops.fold_affine_into_linear(self.w["eu_w1e"], self.w["eu_b1"], table[self.C_G2M_EE], g_w, g_b)
             d_w, d_b = torch.empty_like(g_w), torch.empty_like(g_b)
             ops.fold_affine_into_linear(self.w["du_w1e"], self.w["du_b1"], table[self.C_M2G_EE], d_w, d_b)
-        ctx = SigmaContext(sigma, table, g_w, g_b, d_w, d_b)
+            ctx = SigmaContext(sigma, table, g_w, g_b, d_w, d_b)
+            # The edge-feature part of the first edge-MLP layer, e' @ W1e' + b1, depends on the noise level only
+            # (static structural embeddings, conditioning folded into W1e'): one [E, L] table per level, shared by
+            # all members.  The per-call work is then a gather-add-activation (gc_edge_hidden) instead of an edge
+            # GEMM with gathers.  Kept while the tables of all cached levels fit the budget (12 GB at 1 deg for
+            # the 40 levels of the schedule; at 0.25 deg they would not, and the GEMM path is used).
+            need = 2 * (self.E1 + self.E2) * L * (len(self._sigma_cache) + 1)
+            if self.cd == torch.bfloat16 and need <= self.edge_table_budget_bytes:
+                ctx.g2m_base = torch.empty(self.E1, L, dtype=self.cd, device=self.device)
+                _gemm([(self.g2m_e_ln[:self.E1], g_w)], ctx.g2m_base, bias=g_b)
+                ctx.m2g_base = torch.empty(self.E2, L, dtype=self.cd, device=self.device)
+                _gemm([(self.m2g_e_ln[:self.E2], d_w)], ctx.m2g_base, bias=d_b)
         self._sigma_cache[sigma] = ctx
         return ctx
 
@@ -488,8 +502,11 @@ class DenoiserEngine:
         _gemm([(self.g0, w["eu_w1s"])], self.g_p)
         _gemm([(self.m0, w["eu_w1r"])], self.m_p)
         e_h, e_y = self.e_h[:E1], self.e_y[:E1]
-        _gemm([(self.g2m_e_ln, ctx.g2m_w1e)], e_h, bias=ctx.g2m_b1, act="swish",
-                 gathers=[(self.g_p, self.g2m_s), (self.m_p, self.g2m_r)])
+        if ctx.g2m_base is not None:
+            ops.edge_hidden(ctx.g2m_base, [(self.g_p, self.g2m_s), (self.m_p, self.g2m_r)], e_h, act="swish")
+        else:
+            _gemm([(self.g2m_e_ln, ctx.g2m_w1e)], e_h, bias=ctx.g2m_b1, act="swish",
+                  gathers=[(self.g_p, self.g2m_s), (self.m_p, self.g2m_r)])
         _gemm([(e_h, w["eu_w2"])], e_y, bias=w["eu_b2"])
         ops.ln_cond_segment_sum(e_y, self.m_agg, T[self.C_G2M_EU], self.g2m_row_ptr, self.g2m_perm)
         self._mlp_ln([(self.m0, w["mu_w1a"]), (self.m_agg, w["mu_w1b"])], w["mu_b1"], w["mu_w2"], w["mu_b2"],
@@ -511,8 +528,11 @@ class DenoiserEngine:
         if branch_stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(branch_stream)
         e_h, e_y = self.e_h[:E2], self.e_y[:E2]
-        _gemm([(self.m2g_e_ln, ctx.m2g_w1e)], e_h, bias=ctx.m2g_b1, act="swish",
-                 gathers=[(self.m_p, self.m2g_s), (self.g_p2, self.m2g_r)])
+        if ctx.m2g_base is not None:
+            ops.edge_hidden(ctx.m2g_base, [(self.m_p, self.m2g_s), (self.g_p2, self.m2g_r)], e_h, act="swish")
+        else:
+            _gemm([(self.m2g_e_ln, ctx.m2g_w1e)], e_h, bias=ctx.m2g_b1, act="swish",
+                  gathers=[(self.m_p, self.m2g_s), (self.g_p2, self.m2g_r)])
         _gemm([(e_h, w["du_w2"])], e_y, bias=w["du_b2"])
         ops.ln_cond_segment_sum(e_y, self.g_agg, T[self.C_M2G_EU], self.m2g_row_ptr, self.m2g_perm)
         self._mlp_ln([(self.g_lat, w["dg_w1a"]), (self.g_agg, w["dg_w1b"])], w["dg_b1"], w["dg_w2"], w["dg_b2"],

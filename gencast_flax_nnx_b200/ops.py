@@ -260,6 +260,23 @@ def select_columns(sources: Sequence[Optional[torch.Tensor]], table: torch.Tenso
     return out
 
 
+@_recorded("edge_hidden", lambda base, gathers, out, **kw: (0.0, _nbytes(base, out) + sum(out.shape[0] * out.shape[1] * 2.0 + 4.0 * out.shape[0] for _ in gathers)))
+def edge_hidden(base: torch.Tensor, gathers: Sequence[Tuple[torch.Tensor, torch.Tensor]], out: torch.Tensor, *,
+                act: Optional[str] = "swish") -> torch.Tensor:
+    """out[e] = act(base[e % len(base)] + sum_j gathers[j][0][gathers[j][1][e]]) (bf16); see gc_edge_hidden."""
+    lib = _lib.load()
+    if base.dtype != torch.bfloat16 or out.dtype != torch.bfloat16 or any(g.dtype != torch.bfloat16 for g, _ in gathers):
+        raise TypeError("edge_hidden: bf16 tensors expected")
+    if not 1 <= len(gathers) <= 2 or any(i.dtype != torch.int32 or i.numel() != out.shape[0] for _, i in gathers):
+        raise ValueError("edge_hidden: one or two (table, int32 index [rows]) pairs expected")
+    g = list(gathers) + [(None, None)]
+    _lib.check(lib.gc_edge_hidden(_stream(), base.data_ptr(), _row_major(base, "base"), base.shape[0],
+                                  g[0][0].data_ptr(), g[0][1].data_ptr(), _row_major(g[0][0], "gather source"),
+                                  _p(g[1][0]), _p(g[1][1]), _row_major(g[1][0], "gather source") if g[1][0] is not None else 0,
+                                  ACT[act], out.data_ptr(), _row_major(out, "out"), out.shape[0], out.shape[1]), "gc_edge_hidden")
+    return out
+
+
 def fair_crps(members: torch.Tensor, truth: torch.Tensor, weights: Optional[torch.Tensor], channels: int) -> torch.Tensor:
     """members [M, n] fp32, truth [n], weights [n / channels] or None -> weighted fair CRPS per point, [n] fp32."""
     lib = _lib.load()

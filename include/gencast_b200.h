@@ -233,6 +233,20 @@ GC_API int gc_select_columns(void* stream, const float* src0, int64_t ld0, const
                       int64_t rows, int32_t cols_out);
 
 /*
+ * Hidden layer of an edge MLP whose edge-feature part is known in advance:
+ *   out[e, :] = act( base[e % period, :] + g0[idx0[e], :] + g1[idx1[e], :] )        (bf16 in / out, fp32 sum)
+ * The reference's edge update is MLP([e | n_s | n_r]) (common/typed_graph_net.py:134-159, :301-305); its first
+ * layer splits into e @ W1e + n_s @ W1s + n_r @ W1r, and in GenCast's encoder / decoder the edge features e are
+ * static structural embeddings (gencast/denoiser.py:662-675, :753-755) whose only run-time dependence is the
+ * noise-level conditioning, so base = e' @ W1e' + b1 is a table per noise level, shared by all ensemble members
+ * (period = edges of one member; rows = members * period, member-major).  g1 / idx1 may be NULL.
+ * cols in {128, 256, 512}; act as in gc_gemm.
+ */
+GC_API int gc_edge_hidden(void* stream, const void* base, int64_t ld_base, int64_t period, const void* g0,
+                   const int32_t* idx0, int64_t ld0, const void* g1, const int32_t* idx1, int64_t ld1,
+                   int32_t act, void* out, int64_t ldo, int64_t rows, int32_t cols);
+
+/*
  * Fair CRPS of an M-member ensemble per grid point and channel (no reference implementation
  * exists; defined in DESIGN.md / parallel.py):
  *   crps[i] = mean_m |x_m[i] - y[i]|  -  sum_{j<k} |x_j[i] - x_k[i]| / (M (M - 1))

@@ -351,3 +351,28 @@ def test_fair_crps_kernel(cuda_device, M):
     assert torch.equal(got, again)                       # fixed summation order
     host = parallel.fair_crps(x, y, w)                   # the torch formula used without a GPU
     assert float((host.double() - ref).abs().max() / ref.abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("cols", [128, 256, 512])
+@pytest.mark.parametrize("act", ["swish", None])
+def test_edge_hidden(cuda_device, cols, act):
+    """gc_edge_hidden: act(base[e % period] + g0[idx0[e]] + g1[idx1[e]]) -- the first edge-MLP layer
+    (common/typed_graph_net.py:134-159) once its edge-feature part is tabulated per noise level."""
+    from gencast_flax_nnx_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(cols)
+    period, members, ns, nr = 1003, 3, 400, 77
+    rows = period * members
+    base = torch.randn(period, cols, generator=g).to(torch.bfloat16)
+    g0 = torch.randn(ns, cols, generator=g).to(torch.bfloat16)
+    g1 = torch.randn(nr, cols, generator=g).to(torch.bfloat16)
+    i0 = torch.randint(0, ns, (rows,), generator=g, dtype=torch.int32)
+    i1 = torch.randint(0, nr, (rows,), generator=g, dtype=torch.int32)
+    d = cuda_device
+    fn = _swish if act == "swish" else (lambda x: x)
+    pre = base.double().repeat(members, 1) + g0.double()[i0.long()] + g1.double()[i1.long()]
+    out = torch.full((rows, cols), float("nan"), dtype=torch.bfloat16, device=d)
+    ops.edge_hidden(base.to(d), [(g0.to(d), i0.to(d)), (g1.to(d), i1.to(d))], out, act=act)
+    assert _rel(out.cpu(), fn(pre)) < 1e-2
+    out1 = torch.full((rows, cols), float("nan"), dtype=torch.bfloat16, device=d)
+    ops.edge_hidden(base.to(d), [(g0.to(d), i0.to(d))], out1, act=act)
+    assert _rel(out1.cpu(), fn(base.double().repeat(members, 1) + g0.double()[i0.long()])) < 1e-2
