@@ -409,7 +409,7 @@ class DenoiserEngine:
             # all members.  The per-call work is then a gather-add-activation (gc_edge_hidden) instead of an edge
             # GEMM with gathers.  Kept while the tables of all cached levels fit the budget (12 GB at 1 deg for
             # the 40 levels of the schedule; at 0.25 deg they would not, and the GEMM path is used).
-            need = 2 * (self.E1 + self.E2) * L * (len(self._sigma_cache) + 1)
+            need = 2 * (self.E1 + self.E2) * L * max(40, len(self._sigma_cache) + 1)     # 40 = levels of a 20-step 2S schedule
             if self.cd == torch.bfloat16 and need <= self.edge_table_budget_bytes:
                 ctx.g2m_base = torch.empty(self.E1, L, dtype=self.cd, device=self.device)
                 _gemm([(self.g2m_e_ln[:self.E1], g_w)], ctx.g2m_base, bias=g_b)
