@@ -112,6 +112,8 @@ class SigmaContext:
     m2g_b1: torch.Tensor
     g2m_base: Optional[torch.Tensor] = None   # [E1, L] e' @ W1e' + b1 of one member (bf16), or None (computed per call)
     m2g_base: Optional[torch.Tensor] = None   # [E2, L]
+    m0: Optional[torch.Tensor] = None         # [Vt, L] embedded mesh nodes (static features, this level's affine)
+    m_p: Optional[torch.Tensor] = None        # [Vt, L] m0 @ W1r: receiver part of the grid2mesh edge MLP's first layer
 
 
 class DenoiserEngine:
@@ -347,7 +349,7 @@ class DenoiserEngine:
         self.g0, self.g_lat, self.g2 = b(G, L), b(G, L), b(G, L)
         self.g_p = b(G, L)                       # per-grid-node partial product for the edge MLPs (encoder)
         self.g_p2 = b(G, L)                      # same for the decoder (may be produced on the branch stream)
-        self.m0, self.m_h, self.m_y, self.m_p, self.m_agg = b(V, L), b(V, L), b(V, L), b(V, L), b(V, L)
+        self.m_h, self.m_y, self.m_p, self.m_agg = b(V, L), b(V, L), b(V, L), b(V, L)
         self.m_out = b(V, L)
         self.x = b(V, L, torch.float32)          # transformer residual stream, fp32
         self.t_h = b(V, L)
@@ -404,6 +406,12 @@ class DenoiserEngine:
             d_w, d_b = torch.empty_like(g_w), torch.empty_like(g_b)
             ops.fold_affine_into_linear(self.w["du_w1e"], self.w["du_b1"], table[self.C_M2G_EE], d_w, d_b)
             ctx = SigmaContext(sigma, table, g_w, g_b, d_w, d_b)
+            # mesh-node embedding and its product with the receiver block of the edge MLP: static features and this
+            # level's conditional affine only
+            ctx.m0 = torch.empty(self.Vt, L, dtype=self.cd, device=self.device)
+            ops.ln_cond(self.m0_ln, ctx.m0, table[self.C_G2M_ME], layer_norm=False)
+            ctx.m_p = torch.empty(self.Vt, L, dtype=self.cd, device=self.device)
+            _gemm([(ctx.m0, self.w["eu_w1r"])], ctx.m_p)
             # The edge-feature part of the first edge-MLP layer, e' @ W1e' + b1, depends on the noise level only
             # (static structural embeddings, conditioning folded into W1e'): one [E, L] table per level, shared by
             # all members.  The per-call work is then a gather-add-activation (gc_edge_hidden) instead of an edge
@@ -498,19 +506,17 @@ class DenoiserEngine:
             branch_stream.wait_stream(main)
             with torch.cuda.stream(branch_stream):
                 self._grid_branch(ctx)
-        ops.ln_cond(self.m0_ln, self.m0, T[self.C_G2M_ME], layer_norm=False)
         _gemm([(self.g0, w["eu_w1s"])], self.g_p)
-        _gemm([(self.m0, w["eu_w1r"])], self.m_p)
         e_h, e_y = self.e_h[:E1], self.e_y[:E1]
         if ctx.g2m_base is not None:
-            ops.edge_hidden(ctx.g2m_base, [(self.g_p, self.g2m_s), (self.m_p, self.g2m_r)], e_h, act="swish")
+            ops.edge_hidden(ctx.g2m_base, [(self.g_p, self.g2m_s), (ctx.m_p, self.g2m_r)], e_h, act="swish")
         else:
             _gemm([(self.g2m_e_ln, ctx.g2m_w1e)], e_h, bias=ctx.g2m_b1, act="swish",
-                  gathers=[(self.g_p, self.g2m_s), (self.m_p, self.g2m_r)])
+                  gathers=[(self.g_p, self.g2m_s), (ctx.m_p, self.g2m_r)])
         _gemm([(e_h, w["eu_w2"])], e_y, bias=w["eu_b2"])
         ops.ln_cond_segment_sum(e_y, self.m_agg, T[self.C_G2M_EU], self.g2m_row_ptr, self.g2m_perm)
-        self._mlp_ln([(self.m0, w["mu_w1a"]), (self.m_agg, w["mu_w1b"])], w["mu_b1"], w["mu_w2"], w["mu_b2"],
-                     self.m_h, self.m_y, self.x, T[self.C_G2M_MU], residual=self.m0)
+        self._mlp_ln([(ctx.m0, w["mu_w1a"]), (self.m_agg, w["mu_w1b"])], w["mu_b1"], w["mu_w2"], w["mu_b2"],
+                     self.m_h, self.m_y, self.x, T[self.C_G2M_MU], residual=ctx.m0)
         if branch_stream is None:
             self._grid_branch(ctx)
         # ---- processor (gencast/sparse_transformer.py:486-525, :624-634)
@@ -548,7 +554,7 @@ class DenoiserEngine:
         else:
             ops.khop_attention(self.t_qkv, self.t_o, self.nbr_ptr, self.nbr_idx, self.H, self.head_dim, self.max_degree)
 
-    LAUNCHES_PER_FORWARD_FIXED = 15 + 1 + 10   # encoder + final norm + decoder
+    LAUNCHES_PER_FORWARD_FIXED = 13 + 1 + 10   # encoder + final norm + decoder
 
     @property
     def launches_per_forward(self) -> int:
