@@ -68,6 +68,8 @@ SIGNATURES = {
                                     c_int64, c_int64, c_int32, c_int32]),
     "gc_khop_attention_tiles": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_int64, c_int64, c_int32, c_int32]),
+    "gc_khop_attention_gather": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                           c_int32, c_void_p, c_int64, c_int64, c_int32, c_int32]),
     "gc_cond_tables": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                  c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "gc_fold_affine_into_linear": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p,

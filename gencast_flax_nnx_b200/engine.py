@@ -41,7 +41,7 @@ import torch
 
 from . import ops
 from .configs import DenoiserArchitectureConfig, NoiseEncoderConfig
-from .graph import DenoiserGraphs, csr_by_receiver, khop_tiles, pack_key_ranges, patch_order
+from .graph import DenoiserGraphs, csr_by_receiver, khop_compact_steps, khop_tiles, pack_key_ranges, patch_order
 from .params import COND_DIM, mlp_prefixes
 
 _DTYPES = {"bf16": torch.bfloat16, "f32": torch.float32}
@@ -254,7 +254,25 @@ class DenoiserEngine:
         khop.sort_indices()
         self.khop_nnz = int(khop.nnz) * B
         self.max_degree = int(np.diff(khop.indptr).max())
-        if self.use_tc_attention:
+        # tensor-core attention: 'gather' = per-query-tile compacted key lists (default), 'tiles' = (query tile, key
+        # tile) pairs with TMA-loaded key tiles (round-1 kernel, kept for A/B: GENCAST_ATTENTION=tiles)
+        self.attention_kind = os.environ.get("GENCAST_ATTENTION", "gather") if self.use_tc_attention else "csr"
+        if self.attention_kind not in ("gather", "tiles", "csr"):
+            raise ValueError(f"GENCAST_ATTENTION={self.attention_kind!r} (gather | tiles)")
+        if self.attention_kind == "gather":
+            sp, keys, cm, work = khop_compact_steps(khop, 128, 64)
+            nq, ns = len(sp) - 1, int(sp[-1])               # query tiles / steps per member
+            if B > 1:
+                assert nq * 128 == Vp
+                sp = np.concatenate([sp[:-1].astype(np.int64) + b * ns for b in range(B)] + [[B * ns]]).astype(np.int32)
+                keys = blocks(keys, Vp)
+                counts = np.diff(sp)
+                work = np.argsort(-counts, kind="stable").astype(np.int32)
+            self.att_step_ptr, self.att_keys, self.att_work = self._dev(sp), self._dev(keys), self._dev(work)
+            self.att_mask = self._dev(cm.view(np.int32).reshape(-1))      # one copy, shared by the members
+            self.att_mask_period = ns if B > 1 else 0
+            self.num_attention_steps = int(sp[-1])
+        elif self.attention_kind == "tiles":
             tp, tk, tm = khop_tiles(khop, 128)
             nq = len(tp) - 1                                   # query / key tiles per member (= ceil(V / 128))
             if B > 1:
@@ -420,9 +438,10 @@ class DenoiserEngine:
             need = 2 * (self.E1 + self.E2) * L * max(40, len(self._sigma_cache) + 1)     # 40 = levels of a 20-step 2S schedule
             if self.cd == torch.bfloat16 and need <= self.edge_table_budget_bytes:
                 ctx.g2m_base = torch.empty(self.E1, L, dtype=self.cd, device=self.device)
-                _gemm([(self.g2m_e_ln[:self.E1], g_w)], ctx.g2m_base, bias=g_b)
+                # g_w / d_w were written by the fold kernels queued just above: not static weights (no early W fetch)
+                ops.gemm([(self.g2m_e_ln[:self.E1], g_w)], ctx.g2m_base, bias=g_b)
                 ctx.m2g_base = torch.empty(self.E2, L, dtype=self.cd, device=self.device)
-                _gemm([(self.m2g_e_ln[:self.E2], d_w)], ctx.m2g_base, bias=d_b)
+                ops.gemm([(self.m2g_e_ln[:self.E2], d_w)], ctx.m2g_base, bias=d_b)
         self._sigma_cache[sigma] = ctx
         return ctx
 
@@ -511,8 +530,9 @@ class DenoiserEngine:
         if ctx.g2m_base is not None:
             ops.edge_hidden(ctx.g2m_base, [(self.g_p, self.g2m_s), (ctx.m_p, self.g2m_r)], e_h, act="swish")
         else:
-            _gemm([(self.g2m_e_ln, ctx.g2m_w1e)], e_h, bias=ctx.g2m_b1, act="swish",
-                  gathers=[(self.g_p, self.g2m_s), (ctx.m_p, self.g2m_r)])
+            # folded per-level weight: produced by queued work (sigma_context), so no early W fetch
+            ops.gemm([(self.g2m_e_ln, ctx.g2m_w1e)], e_h, bias=ctx.g2m_b1, act="swish",
+                     gathers=[(self.g_p, self.g2m_s), (ctx.m_p, self.g2m_r)])
         _gemm([(e_h, w["eu_w2"])], e_y, bias=w["eu_b2"])
         ops.ln_cond_segment_sum(e_y, self.m_agg, T[self.C_G2M_EU], self.g2m_row_ptr, self.g2m_perm)
         self._mlp_ln([(ctx.m0, w["mu_w1a"]), (self.m_agg, w["mu_w1b"])], w["mu_b1"], w["mu_w2"], w["mu_b2"],
@@ -537,8 +557,8 @@ class DenoiserEngine:
         if ctx.m2g_base is not None:
             ops.edge_hidden(ctx.m2g_base, [(self.m_p, self.m2g_s), (self.g_p2, self.m2g_r)], e_h, act="swish")
         else:
-            _gemm([(self.m2g_e_ln, ctx.m2g_w1e)], e_h, bias=ctx.m2g_b1, act="swish",
-                  gathers=[(self.m_p, self.m2g_s), (self.g_p2, self.m2g_r)])
+            ops.gemm([(self.m2g_e_ln, ctx.m2g_w1e)], e_h, bias=ctx.m2g_b1, act="swish",
+                     gathers=[(self.m_p, self.m2g_s), (self.g_p2, self.m2g_r)])
         _gemm([(e_h, w["du_w2"])], e_y, bias=w["du_b2"])
         ops.ln_cond_segment_sum(e_y, self.g_agg, T[self.C_M2G_EU], self.m2g_row_ptr, self.m2g_perm)
         self._mlp_ln([(self.g_lat, w["dg_w1a"]), (self.g_agg, w["dg_w1b"])], w["dg_b1"], w["dg_w2"], w["dg_b2"],
@@ -548,7 +568,10 @@ class DenoiserEngine:
         return self.f_out
 
     def _attention(self):
-        if self.use_tc_attention:
+        if self.attention_kind == "gather":
+            ops.khop_attention_gather(self.t_qkv, self.t_o, self.att_step_ptr, self.att_keys, self.att_mask, self.att_work,
+                                      self.H, self.head_dim, self.att_mask_period, self.khop_nnz)
+        elif self.attention_kind == "tiles":
             ops.khop_attention_tiles(self.t_qkv, self.t_o, self.tile_ptr, self.tile_kv, self.tile_mask, self.H,
                                      self.head_dim, self.khop_nnz)
         else:

@@ -396,6 +396,51 @@ def pack_key_ranges(tile_kv: np.ndarray, tile_mask: np.ndarray) -> np.ndarray:
     return (kv | (first.astype(np.int64) << 24) | ((3 - last).astype(np.int64) << 26)).astype(np.int32)
 
 
+def khop_compact_steps(khop: sparse.spmatrix, tile_q: int = 128, step: int = 64):
+    """Per-query-tile compacted key lists for the gather form of the tensor-core attention kernel.
+
+    For each tile of `tile_q` consecutive queries the sorted union of the keys any of them attends to is
+    cut into steps of `step` keys (the last step is padded by repeating its last key; padded columns have
+    no mask bit).  A 128-query patch of the 1 deg mesh attends to 690 distinct keys on average, which the
+    plain (query tile, key tile) list spreads over 11.3 key tiles of 128 (1 446 keys): compacted it is 5.6
+    tiles' worth.  The kernel gathers the listed K / V rows into dense operand tiles itself.
+
+    Returns (step_ptr[nq+1] i32, keys[ns*step] i32, mask[ns, tile_q, step//32] u32, work[nq] i32):
+    steps step_ptr[t] .. step_ptr[t+1]-1 belong to query tile t; bit j%32 of word j//32 of mask[s, r] says
+    that key keys[s*step + j] is a neighbour of query t*tile_q + r; `work` lists the query tiles by
+    decreasing step count (longest first, stable) for the launch order.
+    """
+    csr = khop.tocsr()
+    csr.sort_indices()
+    n = csr.shape[0]
+    nq = -(-n // tile_q)
+    words = step // 32
+    step_ptr = np.zeros(nq + 1, np.int64)
+    keys_all, mask_all = [], []
+    for t in range(nq):
+        r0, r1 = t * tile_q, min((t + 1) * tile_q, n)
+        lo, hi = csr.indptr[r0], csr.indptr[r1]
+        cols = csr.indices[lo:hi]
+        uniq = np.unique(cols)
+        ns = -(-len(uniq) // step)
+        step_ptr[t + 1] = step_ptr[t] + ns
+        if ns == 0:
+            continue
+        padded = np.full(ns * step, uniq[-1], np.int32)
+        padded[:len(uniq)] = uniq
+        keys_all.append(padded)
+        rows = np.repeat(np.arange(r0, r1), np.diff(csr.indptr[r0:r1 + 1])) - r0
+        pos = np.searchsorted(uniq, cols)
+        bits = np.zeros((ns, tile_q, step), dtype=bool)
+        bits[pos // step, rows, pos % step] = True
+        mask_all.append(np.packbits(bits, axis=-1, bitorder="little").view(np.uint32).reshape(ns, tile_q, words))
+    keys = np.concatenate(keys_all) if keys_all else np.zeros(0, np.int32)
+    mask = np.concatenate(mask_all) if mask_all else np.zeros((0, tile_q, words), np.uint32)
+    counts = np.diff(step_ptr)
+    work = np.argsort(-counts, kind="stable").astype(np.int32)
+    return step_ptr.astype(np.int32), keys.astype(np.int32), np.ascontiguousarray(mask), work
+
+
 def patch_order(xyz: np.ndarray, leaf: int = 128, sub_leaf: int = 32) -> np.ndarray:
     """Permutation that groups mesh nodes into spatially compact patches of `leaf` nodes, each of
     which is itself ordered into compact sub-patches of `sub_leaf` nodes.

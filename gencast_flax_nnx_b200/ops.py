@@ -202,6 +202,28 @@ def khop_attention_tiles(qkv: torch.Tensor, out: torch.Tensor, tile_ptr: torch.T
     return out
 
 
+@_recorded("khop_attention_gather", lambda qkv, out, sp, keys, mask, work, heads, head_dim, mask_period=0, nnz=0: (4.0 * nnz * heads * head_dim, _nbytes(qkv, out, mask, keys)))
+def khop_attention_gather(qkv: torch.Tensor, out: torch.Tensor, step_ptr: torch.Tensor, keys: torch.Tensor,
+                          mask: torch.Tensor, work: torch.Tensor, heads: int, head_dim: int, mask_period: int = 0,
+                          nnz: int = 0) -> torch.Tensor:
+    """Tensor-core k-hop attention over per-query-tile compacted key lists (graph.khop_compact_steps); bf16.
+    `nnz` (pattern size) is only used by the timing recorder to report algorithmic FLOPs."""
+    lib = _lib.load()
+    if qkv.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
+        raise TypeError("khop_attention_gather: bf16 only")
+    for t, name in ((step_ptr, "step_ptr"), (keys, "keys"), (mask, "mask"), (work, "work")):
+        if t.dtype != torch.int32 or not t.is_cuda or not t.is_contiguous():
+            raise TypeError(f"khop_attention_gather: {name} must be a contiguous int32 CUDA tensor")
+    nq = work.numel()
+    if step_ptr.numel() != nq + 1:
+        raise ValueError("khop_attention_gather: step_ptr must have one entry per query tile plus one")
+    _lib.check(lib.gc_khop_attention_gather(_stream(), qkv.data_ptr(), _row_major(qkv, "qkv"), step_ptr.data_ptr(),
+                                            keys.data_ptr(), mask.data_ptr(), work.data_ptr(), nq, int(mask_period),
+                                            out.data_ptr(), _row_major(out, "out"), qkv.shape[0], heads, head_dim),
+               "gc_khop_attention_gather")
+    return out
+
+
 def cond_tables(sigma: torch.Tensor, w0, b0, w1, b1, base_period: float, num_frequencies: int,
                 wc: torch.Tensor, bc: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()

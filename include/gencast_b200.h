@@ -169,6 +169,21 @@ GC_API int gc_khop_attention_tiles(void* stream, const void* qkv, int64_t ld_qkv
                                    int64_t nodes, int32_t heads, int32_t head_dim);
 
 /*
+ * The same attention over per-query-tile COMPACTED key lists (bf16, head_dim 64 or 128): for query tile t (128
+ * consecutive nodes) steps step_ptr[t] .. step_ptr[t+1]-1 each name 64 rows of qkv (keys[step * 64 + j]; the sorted
+ * union of the tile's neighbours, the last step padded with any valid row) and mask[step][row] holds 64 bits: bit j
+ * set = keys[step * 64 + j] is a neighbour of query t * 128 + row (padded columns: clear).  The kernel gathers the
+ * K / V rows into dense tensor-core tiles itself, so a 128-query patch of the 1 deg mesh costs 11 steps of 64 keys
+ * instead of 11.3 key tiles of 128.  mask_period > 0: mask index = step % mask_period (ensemble members evaluated
+ * together share the masks; their key lists differ by a row offset).  work[num_q_tiles]: launch order of the query
+ * tiles.  Same reference operator as gc_khop_attention (gencast/sparse_transformer.py:309-354).
+ */
+GC_API int gc_khop_attention_gather(void* stream, const void* qkv, int64_t ld_qkv, const int32_t* step_ptr,
+                                    const int32_t* keys, const uint32_t* mask, const int32_t* work,
+                                    int32_t num_q_tiles, int32_t mask_period, void* out, int64_t ldo, int64_t nodes,
+                                    int32_t heads, int32_t head_dim);
+
+/*
  * Noise-level conditioning for a batch of noise levels, all layers at once:
  *   cond      = Linear1(gelu_tanh(Linear0(fourier(log sigma))))     [16]
  *   table[i, l] = (1 + s_l | o_l),  [s_l | o_l] = cond . Wc_l + bc_l   [2*width]

@@ -288,3 +288,35 @@ def test_window_update_table_matches_host_window_roll():
     # an input with a time axis that is neither predicted nor forced is rejected, as in the reference
     with pytest.raises(ValueError):
         rollout.window_update_table(inputs, pred.drop_vars(["2m_temperature"]), forcings)
+
+
+def test_khop_compact_steps_reconstruct_the_pattern():
+    """graph.khop_compact_steps: keys of a query tile are the sorted union of its rows' neighbours, padded columns
+    carry no mask bit, and (keys, mask) reproduce the pattern exactly."""
+    from scipy import sparse
+    from gencast_flax_nnx_b200 import graph
+    rng = np.random.default_rng(3)
+    n = 300
+    dense = rng.random((n, n)) < 0.07
+    dense[np.arange(n), np.arange(n)] = True
+    dense[:, 40:90] = False
+    dense[np.arange(40, 90), np.arange(40, 90)] = True
+    sp, keys, cm, work = graph.khop_compact_steps(sparse.csr_matrix(dense), 128, 64)
+    nq = -(-n // 128)
+    assert len(sp) == nq + 1 and len(keys) == sp[-1] * 64 and cm.shape == (sp[-1], 128, 2)
+    assert sorted(work.tolist()) == list(range(nq)) and np.all(np.diff(np.diff(sp)[work]) <= 0)
+    rebuilt = np.zeros_like(dense)
+    bits = np.unpackbits(cm.view(np.uint8), axis=-1, bitorder="little").reshape(sp[-1], 128, 64).astype(bool)
+    for t in range(nq):
+        union = np.unique(np.nonzero(dense[t * 128:(t + 1) * 128])[1])
+        k = keys[sp[t] * 64: sp[t + 1] * 64]
+        assert sp[t + 1] - sp[t] == -(-len(union) // 64)
+        np.testing.assert_array_equal(k[:len(union)], union)
+        assert np.all(k[len(union):] == union[-1])
+        b = bits[sp[t]:sp[t + 1]].transpose(1, 0, 2).reshape(128, -1)       # [row, compacted column]
+        assert not b[:, len(union):].any()
+        rows = min(128, n - t * 128)
+        assert not b[rows:].any()
+        for r in range(rows):
+            rebuilt[t * 128 + r, k[b[r]]] = True
+    np.testing.assert_array_equal(rebuilt, dense)

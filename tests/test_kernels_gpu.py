@@ -259,6 +259,80 @@ def test_khop_attention_tensor_core(cuda_device, heads, head_dim, n, density, qk
     assert _rel(outs[1], outs[0].double()) < 1e-2
 
 
+@pytest.mark.parametrize("heads,head_dim", [(4, 64), (2, 128), (4, 128)])
+@pytest.mark.parametrize("n,density,qk_scale", [(300, 0.2, 1.5), (1000, 0.05, 1.5), (128, 1.0, 1.5), (1000, 0.3, 5.0),
+                                                (2300, 0.4, 1.5), (700, 0.1, 12.0)])
+def test_khop_attention_gather(cuda_device, heads, head_dim, n, density, qk_scale):
+    """tcgen05 attention over per-query-tile compacted key lists (gathered K / V tiles, single-pass online softmax)
+    against dense masked softmax attention in fp64; bitwise repeatable."""
+    from scipy import sparse
+    from gencast_flax_nnx_b200 import ops
+    from gencast_flax_nnx_b200.graph import khop_compact_steps
+    rng = np.random.default_rng(head_dim + n)
+    hd = heads * head_dim
+    g = torch.Generator(device="cpu").manual_seed(4)
+    # qk_scale 5 / 12 give logits of order +-50 / +-300 (x log2 e / sqrt d): row maxima jump between steps by far more
+    # than 2^40, which exercises the overflow guard, the offset raise and the rescaling of O in tensor memory
+    qkv = torch.randn(n, 3 * hd, generator=g)
+    qkv[:, :2 * hd] *= qk_scale
+    qkv[:, 2 * hd:] *= 1.5
+    qkv = qkv.to(torch.bfloat16)
+    mask = rng.random((n, n)) < density
+    if n == 1000 and density < 0.1:
+        mask[:, 300:700] = False         # keys nobody attends to: absent from every compacted list
+        mask[400:, :200] = False
+    if n == 700:
+        mask[:, :] = np.triu(mask, 0)    # rows meet their first neighbour at different steps
+        mask[100:200, :] = False         # rows with the diagonal only
+    if n == 2300:
+        mask[:128, :] = True             # one query tile attends to everything: 36 steps (> the staged key list)
+    mask[np.arange(n), np.arange(n)] = True
+    sp, keys, cm, work = khop_compact_steps(sparse.csr_matrix(mask))
+    d = cuda_device
+    q, k, v = [t.double().reshape(n, heads, head_dim) for t in qkv.split(hd, dim=1)]
+    logits = torch.einsum("qhd,khd->hqk", q, k) / math.sqrt(head_dim)
+    logits = logits.masked_fill(~torch.from_numpy(mask)[None], float("-inf"))
+    ref = torch.einsum("hqk,khd->qhd", torch.softmax(logits, -1), v).reshape(n, hd)
+    args = [torch.from_numpy(a.view(np.int32).reshape(-1) if a.dtype == np.uint32 else a).to(d) for a in (sp, keys, cm, work)]
+    outs = []
+    for _ in range(2):
+        out = torch.full((n, hd), float("nan"), dtype=torch.bfloat16, device=d)
+        ops.khop_attention_gather(qkv.to(d), out, *args, heads, head_dim)
+        torch.cuda.synchronize()
+        assert _rel(out.cpu(), ref) < 1.5e-2
+        outs.append(out.cpu())
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_khop_attention_gather_members_share_masks(cuda_device):
+    """Two members evaluated together: key lists offset per member, one copy of the masks (mask_period)."""
+    from scipy import sparse
+    from gencast_flax_nnx_b200 import ops
+    from gencast_flax_nnx_b200.graph import khop_compact_steps
+    rng = np.random.default_rng(5)
+    n, heads, head_dim = 256, 4, 64
+    hd = heads * head_dim
+    mask = rng.random((n, n)) < 0.15
+    mask[np.arange(n), np.arange(n)] = True
+    sp, keys, cm, work = khop_compact_steps(sparse.csr_matrix(mask))
+    ns, nq = int(sp[-1]), len(sp) - 1
+    d = cuda_device
+    qkv = (torch.randn(2 * n, 3 * hd, generator=torch.Generator().manual_seed(1)) * 1.2).to(torch.bfloat16).to(d)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(d)
+    single = []
+    for b in range(2):
+        out = torch.empty(n, hd, dtype=torch.bfloat16, device=d)
+        ops.khop_attention_gather(qkv[b * n:(b + 1) * n], out, t(sp), t(keys), t(cm.view(np.int32).reshape(-1)), t(work), heads, head_dim)
+        single.append(out)
+    sp2 = np.concatenate([sp[:-1], sp[:-1] + ns, [2 * ns]]).astype(np.int32)
+    keys2 = np.concatenate([keys, keys + n]).astype(np.int32)
+    work2 = np.argsort(-np.diff(sp2), kind="stable").astype(np.int32)
+    out2 = torch.empty(2 * n, hd, dtype=torch.bfloat16, device=d)
+    ops.khop_attention_gather(qkv, out2, t(sp2), t(keys2), t(cm.view(np.int32).reshape(-1)), t(work2), heads, head_dim, mask_period=ns)
+    torch.cuda.synchronize()
+    assert torch.equal(out2[:n], single[0]) and torch.equal(out2[n:], single[1])
+
+
 def test_cond_tables_and_fold(cuda_device):
     from gencast_flax_nnx_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(9)
