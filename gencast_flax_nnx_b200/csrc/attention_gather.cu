@@ -30,11 +30,22 @@
 // 32-key half-steps in which none of a warp's 32 queries has a neighbour are neither read nor exponentiated.
 //
 // Warps (288 threads): 0 = MMA issuer / TMEM owner / Q load, 1-4 = softmax + epilogue, 5-8 = K / V row gather.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
 namespace gc {
+
+long long* g_attention_gather_trace = nullptr;   // debug: clock stamps of CTA 0 (null in normal use)
+
 namespace {
+
+// Debug timeline: CTA 0 records clock64() at pipeline events into trace[role * 512 + index].
+#define GC_GTR(role, index)                                                                                       \
+  do {                                                                                                            \
+    if (p.trace != nullptr && blockIdx.x == 0 && (index) < 512) p.trace[(role) * 512 + (index)] = clock64();      \
+  } while (0)
 
 constexpr int GQ = 128;            // queries per tile
 constexpr int GS = 64;             // keys per step
@@ -68,6 +79,8 @@ struct GatherAttParams {
   int heads;
   int hd;                      // heads * head_dim: column offset of K inside a qkv row (V at 2 * hd)
   float scale_log2e;           // head_dim^-0.5 * log2(e)
+  int prefetch_steps;          // K / V rows of the step this many steps ahead are prefetched into L2 (0 = off)
+  long long* trace;
 };
 
 __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src) {
@@ -105,6 +118,7 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
   using namespace sm100;
   using C = GCfg<D>;
   pdl_launch_dependents();
+  if (threadIdx.x == 0) GC_GTR(6, 0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t q_smem = base;
@@ -172,7 +186,9 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
       uint32_t kphase = 0, vphase = 0;
       auto issue_s = [&](int t) {
         const int b = t & 1;
+        GC_GTR(1, 2 * t);
         mbar_wait(k_full(kslot), kphase);
+        GC_GTR(1, 2 * t + 1);
         tc_fence_after();
         const uint32_t k_base = k_smem + kslot * C::SLOT_BYTES;
 #pragma unroll
@@ -189,8 +205,11 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
       for (int t = 0; t < 2 && t < T; ++t) issue_s(t);
       for (int t = 0; t < T; ++t) {
         const int b = t & 1;
+        GC_GTR(2, 3 * t);
         mbar_wait(v_full(vslot), vphase);
+        GC_GTR(2, 3 * t + 1);
         mbar_wait(p_full(b), (t >> 1) & 1);
+        GC_GTR(2, 3 * t + 2);
         tc_fence_after();
         const uint32_t v_base = v_smem + vslot * C::SLOT_BYTES;
 #pragma unroll
@@ -233,7 +252,9 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
 #pragma unroll
       for (int c = 0; c < 2; ++c) live[c] = __any_sync(0xffffffffu, mw[c] != 0u);
       const uint32_t s_addr = tmem_s + b * 64 + lane_addr;
+      if (threadIdx.x == 32) GC_GTR(3, 3 * t);
       mbar_wait(s_full(b), (t >> 1) & 1);
+      if (threadIdx.x == 32) GC_GTR(3, 3 * t + 1);
       tc_fence_after();
       uint32_t packed[2][16];
       float ls[2];
@@ -299,14 +320,17 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(b));
+      if (threadIdx.x == 32) GC_GTR(3, 3 * t + 2);
     }
     // ---- epilogue: O / l
     const float l = l0 + l1;
     const float inv_l = l > 0.0f ? 1.0f / l : 0.0f;
+    if (threadIdx.x == 32) GC_GTR(4, 0);
     if (T > 0) {
       mbar_wait(o_full, 0);
       tc_fence_after();
     }
+    if (threadIdx.x == 32) GC_GTR(4, 1);
     const int64_t row = static_cast<int64_t>(qt) * GQ + r;
 #pragma unroll
     for (int c = 0; c < D; c += 32) {
@@ -343,6 +367,7 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
     const uint32_t u8 = static_cast<uint32_t>(unit & 7);
     pdl_wait();                                  // qkv is the predecessor's output
     uint32_t pend_bar = 0;
+    int ld_ev = 0;
     auto key_of = [&](int t, int rl) -> int64_t {
       if (t < G_MAX_STAGED_STEPS) return keys_s[t * GS + rl];
       return __ldg(p.keys + (static_cast<int64_t>(s_beg) + t) * GS + rl);
@@ -353,7 +378,20 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(pend_bar);
+        if (threadIdx.x == 160) { GC_GTR(5, ld_ev - 1 - (all ? 0 : 1)); }
         pend_bar = 0u;
+      }
+    };
+    // L2 prefetch of the rows a later step will gather: the ring holds two steps per operand, so a tile has about
+    // one step time to arrive; with half of qkv coming from HBM (it is as large as the L2) that is not enough
+    // (trace: 2 700-3 500 clk from issue to landed), whereas an L2 hit takes a few hundred clk.
+    constexpr int LINES = D / 64;                // 128-byte lines per row
+    auto prefetch_rows = [&](int t, int col0) {
+      if (t >= T) return;
+      const int rl = lw * 16 + lane / LINES;
+      if (lane < 16 * LINES) {
+        const __nv_bfloat16* src = p.qkv + key_of(t, rl) * p.ld_qkv + col0 + (lane % LINES) * 64;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
       }
     };
     auto produce = [&](uint32_t empty_bar, uint32_t parity, uint32_t full_bar, uint32_t slot_base, int col0, int t) {
@@ -365,6 +403,7 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
         if (lane == 0) mbar_wait(empty_bar, parity);
         __syncwarp();
       }
+      if (threadIdx.x == 160) { GC_GTR(0, ld_ev); ++ld_ev; }
 #pragma unroll
       for (int i = 0; i < ITER; ++i) {
         const int rl = lw * 16 + i * RPI + row_in;
@@ -390,16 +429,23 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
       if (++vslot == C::NV) { vslot = 0; vphase ^= 1u; }
     };
     // consumption order: K_0, K_1, then per step t: V_t, K_{t+2}
+    const int pf = p.prefetch_steps;
+    if (pf > 0) {
+      for (int t = 0; t < pf; ++t) { prefetch_rows(2 + t, k_col); prefetch_rows(t, v_col); }
+    }
     for (int t = 0; t < 2 && t < T; ++t) load_k(t);
     for (int t = 0; t < T; ++t) {
+      if (pf > 0) { prefetch_rows(t + pf, v_col); prefetch_rows(t + 2 + pf, k_col); }
       load_v(t);
       if (t + 2 < T) load_k(t + 2);
     }
     flush_pending(true);
   }
+  if (threadIdx.x == 32) GC_GTR(4, 2);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (threadIdx.x == 0) GC_GTR(4, 3);
 }
 
 template <int D>
@@ -414,6 +460,11 @@ int launch_gather(cudaStream_t st, const CUtensorMap& map, const GatherAttParams
 
 }  // namespace
 }  // namespace gc
+
+// Debug hook (not part of the public header): clock-stamp buffer of at least 8 * 512 int64.
+extern "C" __attribute__((visibility("default"))) void gc_debug_set_attention_gather_trace(void* ptr) {
+  gc::g_attention_gather_trace = reinterpret_cast<long long*>(ptr);
+}
 
 extern "C" int gc_khop_attention_gather(void* stream, const void* qkv, int64_t ld_qkv, const int32_t* step_ptr,
                                         const int32_t* keys, const uint32_t* mask, const int32_t* work,
@@ -439,6 +490,11 @@ extern "C" int gc_khop_attention_gather(void* stream, const void* qkv, int64_t l
   p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ldo = ldo; p.nodes = (int)nodes; p.heads = heads;
   p.hd = heads * head_dim;
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)head_dim);
+  p.trace = g_attention_gather_trace;
+  {
+    static const int pf = []() { const char* v = getenv("GENCAST_ATT_PREFETCH"); return v != nullptr ? atoi(v) : 2; }();
+    p.prefetch_steps = pf < 0 ? 0 : (pf > 8 ? 8 : pf);
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (head_dim == 64) return launch_gather<64>(st, map, p, num_q_tiles);
   return launch_gather<128>(st, map, p, num_q_tiles);

@@ -266,8 +266,20 @@ class DenoiserEngine:
                 assert nq * 128 == Vp
                 sp = np.concatenate([sp[:-1].astype(np.int64) + b * ns for b in range(B)] + [[B * ns]]).astype(np.int32)
                 keys = blocks(keys, Vp)
-                counts = np.diff(sp)
-                work = np.argsort(-counts, kind="stable").astype(np.int32)
+            # Launch order of the query tiles.  'natural' = member by member along the patch order: the CTAs in flight
+            # then share one member's K / V rows (31 MB at 1 deg) instead of all members' (126 MB = the whole L2), which
+            # is what keeps the gathered rows L2 hits; 'reverse' walks the members backwards (the QKV GEMM wrote the last
+            # member's rows last); 'sorted' = longest tiles first (khop_compact_steps' own order).
+            order_kind = os.environ.get("GENCAST_ATT_ORDER", "natural")
+            nqt = len(sp) - 1
+            if order_kind == "natural":
+                work = np.arange(nqt, dtype=np.int32)
+            elif order_kind == "reverse":
+                work = np.arange(nqt, dtype=np.int32)[::-1].copy()
+            elif order_kind == "sorted":
+                work = np.argsort(-np.diff(sp), kind="stable").astype(np.int32)
+            else:
+                raise ValueError(f"GENCAST_ATT_ORDER={order_kind!r}")
             self.att_step_ptr, self.att_keys, self.att_work = self._dev(sp), self._dev(keys), self._dev(work)
             self.att_mask = self._dev(cm.view(np.int32).reshape(-1))      # one copy, shared by the members
             self.att_mask_period = ns if B > 1 else 0

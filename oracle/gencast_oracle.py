@@ -344,7 +344,7 @@ def assemble_features(inputs_stacked, forcings: Mapping[str, torch.Tensor],
 
 
 def preconditioned_denoiser(p, g, arch, inputs_stacked, forcings, noisy_targets: Mapping[str, torch.Tensor],
-                            sigma, dtype):
+                            sigma, dtype, network_fn=None):
     """D(x, sigma) = c_out F(c_in x, sigma) + c_skip x, per target variable.
 
     Reference: gencast/dpm_solver_plus_plus_2s.py:190-205.  noisy_targets maps
@@ -354,7 +354,10 @@ def preconditioned_denoiser(p, g, arch, inputs_stacked, forcings, noisy_targets:
     sig = sigma.to(dtype)
     scaled = {k: v.to(dtype) * c_in(sig)[None, :, None] for k, v in noisy_targets.items()}
     feats = assemble_features(inputs_stacked.to(dtype), {k: v.to(dtype) for k, v in forcings.items()}, scaled)
-    raw = denoiser_forward(p, g, arch, feats, sig, dtype)
+    # network_fn(features [G,B,C], sigma [B]) -> [G,B,n_out] replaces the GenCast network: used to pin this function
+    # and the solver loop against the reference's own sampler code run around a toy network
+    # (tools/make_sampler_golden.py)
+    raw = denoiser_forward(p, g, arch, feats, sig, dtype) if network_fn is None else network_fn(feats, sig)
     out, i = {}, 0
     for k in sorted(noisy_targets.keys()):
         c = noisy_targets[k].shape[-1]
@@ -376,7 +379,7 @@ def noise_schedule(max_noise_level=80.0, min_noise_level=0.03, num_noise_levels=
 
 def dpm_solver_2s(p, g, arch, inputs_stacked, forcings, init_x: Mapping[str, torch.Tensor],
                   sigmas: Sequence[float], dtype, num_steps: Optional[int] = None,
-                  trace: Optional[list] = None):
+                  trace: Optional[list] = None, network_fn=None):
     """Deterministic DPM-Solver++ 2S loop (stochastic churn = 0).
 
     Reference: gencast/dpm_solver_plus_plus_2s.py:120-158.  init_x already holds
@@ -391,7 +394,7 @@ def dpm_solver_2s(p, g, arch, inputs_stacked, forcings, init_x: Mapping[str, tor
     def D(state, s):
         s_safe = max(float(s), 1e-6)
         return preconditioned_denoiser(p, g, arch, inputs_stacked, forcings, state,
-                                       torch.full((B,), s_safe, dtype=dtype), dtype)
+                                       torch.full((B,), s_safe, dtype=dtype), dtype, network_fn)
     for i in range(n):
         sigma, sigma_next = float(sigmas[i]), float(sigmas[i + 1])
         sigma_mid = math.sqrt(sigma * sigma_next)

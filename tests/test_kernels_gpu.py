@@ -363,6 +363,26 @@ def test_cond_tables_and_fold(cuda_device):
         assert _rel(b_out.cpu(), bias.double() + w.double() @ so[k:].double()) < 1e-5
 
 
+def test_cond_tables_match_reference_fourier_features_mlp(cuda_device):
+    """gc_cond_tables against the output of the reference's own FourierFeaturesMLP code (common/mlp.py:255-265,
+    common/model_utils.py:728-757; fixture tests/golden/refshim_sampler.npz, tools/make_sampler_golden.py): with an
+    identity conditional linear the table rows are (1 + cond[:8] | cond[8:])."""
+    import os
+    from gencast_flax_nnx_b200 import ops
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refshim_sampler.npz"))
+    d = cuda_device
+    f32 = lambda k: torch.from_numpy(gold[k].astype(np.float32)).to(d)
+    sigma = f32("encoder/sigmas")
+    wc = torch.eye(16, device=d).reshape(1, 16, 16).contiguous()
+    bc = torch.zeros(1, 16, device=d)
+    table = torch.empty(len(sigma), 1, 16, device=d)
+    ops.cond_tables(sigma, f32("encoder/linear_0/kernel"), f32("encoder/linear_0/bias"), f32("encoder/linear_1/kernel"),
+                    f32("encoder/linear_1/bias"), 16.0, 32, wc, bc, table)
+    got = table[:, 0].cpu().double()
+    got[:, :8] -= 1.0
+    assert _rel(got, torch.from_numpy(gold["encoder/cond"])) < 2e-4      # fp32 sin / cos of |angle| up to ~170 rad
+
+
 def test_dpm_update_cast_pad_accumulate(cuda_device):
     from gencast_flax_nnx_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(2)

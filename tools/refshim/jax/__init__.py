@@ -20,3 +20,21 @@ def custom_vjp(fn=None, nondiff_argnums=()):
 
 def jit(fn=None, **k):
     return fn if fn is not None else (lambda f: f)
+
+
+class _Typing:
+    ArrayLike = object
+    DTypeLike = object
+
+
+typing = _Typing()
+
+
+class _Tree:
+    @staticmethod
+    def map(fn, *trees):
+        from .tree_util import tree_map
+        return tree_map(fn, *trees)
+
+
+tree = _Tree()
