@@ -82,6 +82,9 @@ SIGNATURES = {
                                     c_int64, c_int64, c_int32]),
     "gc_edge_hidden": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                  c_int64, c_int32, c_void_p, c_int64, c_int64, c_int32]),
+    "gc_edge_mlp_sum3": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                   c_int64, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_int32,
+                                   c_int64, c_int64, c_int32]),
     "gc_fair_crps": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_int64]),
     "gc_column_sums": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "gc_ensemble_accumulate": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),

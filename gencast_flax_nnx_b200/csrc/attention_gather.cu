@@ -30,8 +30,6 @@
 // 32-key half-steps in which none of a warp's 32 queries has a neighbour are neither read nor exponentiated.
 //
 // Warps (288 threads): 0 = MMA issuer / TMEM owner / Q load, 1-4 = softmax + epilogue, 5-8 = K / V row gather.
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -79,16 +77,17 @@ struct GatherAttParams {
   int heads;
   int hd;                      // heads * head_dim: column offset of K inside a qkv row (V at 2 * hd)
   float scale_log2e;           // head_dim^-0.5 * log2(e)
-  int prefetch_steps;          // K / V rows of the step this many steps ahead are prefetched into L2 (0 = off)
   long long* trace;
 };
 
 __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// The executing thread arrives on `bar` once all of its earlier cp.async copies have landed (asynchronously: the
+// thread itself does not wait; .noinc: the arrival is counted in the barrier's initial count).
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -150,8 +149,8 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&q_map);
     mbar_init(q_full, 1);
-    for (int s = 0; s < C::NK; ++s) { mbar_init(k_full(s), G_LOADERS); mbar_init(k_empty(s), 1); }
-    for (int s = 0; s < C::NV; ++s) { mbar_init(v_full(s), G_LOADERS); mbar_init(v_empty(s), 1); }
+    for (int s = 0; s < C::NK; ++s) { mbar_init(k_full(s), (G_LOADERS / 2) * 32); mbar_init(k_empty(s), 1); }
+    for (int s = 0; s < C::NV; ++s) { mbar_init(v_full(s), (G_LOADERS / 2) * 32); mbar_init(v_empty(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(p_full(b), 4); }
     mbar_init(pv_done, 1);
     mbar_init(o_full, 1);
@@ -175,58 +174,72 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
   const uint32_t tmem_o = tmem_base + 128;      // O at +128 .. +128 + D
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- Q load + MMA issuer
-      pdl_wait();
+    // ---------------- Q load + MMA issuer.  The whole warp runs this code and one elected lane issues the
+    // tcgen05 / TMA instructions: inside an `if (lane == 0)` region the compiler treats every operand as divergent
+    // and wraps each tcgen05.mma in an ELECT / R2UR.BROADCAST x5 / BRA.U.ANY loop (~15 dependent instructions, ~100 clk
+    // per MMA for an instruction that computes for 32-64 clk); warp-uniform control flow keeps descriptors in
+    // uniform registers.
+    pdl_wait();
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, C::Q_BYTES);
       for (int c = 0; c < C::CHUNKS; ++c) tma_load_2d(q_smem + c * (GQ * 128), &q_map, q_full, head * D + 64 * c, qt * GQ);
-      constexpr uint32_t idesc_s = idesc_bf16_f32(GQ, GS, 0, 0);
-      constexpr uint32_t idesc_o = idesc_bf16_f32(GQ, D, 0, 1);     // B = V tile, MN-major
-      int kslot = 0, vslot = 0;
-      uint32_t kphase = 0, vphase = 0;
-      auto issue_s = [&](int t) {
-        const int b = t & 1;
-        GC_GTR(1, 2 * t);
-        mbar_wait(k_full(kslot), kphase);
-        GC_GTR(1, 2 * t + 1);
-        tc_fence_after();
-        const uint32_t k_base = k_smem + kslot * C::SLOT_BYTES;
+    }
+    __syncwarp();
+    constexpr uint32_t idesc_s = idesc_bf16_f32(GQ, GS, 0, 0);
+    constexpr uint32_t idesc_o = idesc_bf16_f32(GQ, D, 0, 1);     // B = V tile, MN-major
+    const uint64_t dq0 = desc_kmajor_sw128(q_smem);
+    int kslot = 0, vslot = 0;
+    uint32_t kphase = 0, vphase = 0;
+    auto issue_s = [&](int t) {
+      const int b = t & 1;
+      GC_GTR(1, 2 * t);
+      mbar_wait(k_full(kslot), kphase);
+      GC_GTR(1, 2 * t + 1);
+      fence_proxy_async_smem();      // the gathered rows were written by cp.async (generic proxy), the MMA reads them
+      tc_fence_after();              // through the async proxy
+      const uint64_t dk0 = desc_kmajor_sw128(k_smem + kslot * C::SLOT_BYTES);
+      if (elect_one()) {
 #pragma unroll
         for (int j = 0; j < D / 16; ++j) {
-          const uint32_t off_q = (j >> 2) * (GQ * 128) + (j & 3) * 32;
-          const uint32_t off_k = (j >> 2) * (GS * 128) + (j & 3) * 32;
-          umma_f16(tmem_s + b * 64, desc_kmajor_sw128(q_smem + off_q), desc_kmajor_sw128(k_base + off_k), idesc_s, j > 0);
+          // descriptor start-address field is in 16-byte units: 64-wide d chunk j / 4, 32 bytes per K = 16 step inside it
+          const uint32_t off_q = ((j >> 2) * (GQ * 128) + (j & 3) * 32) >> 4;
+          const uint32_t off_k = ((j >> 2) * (GS * 128) + (j & 3) * 32) >> 4;
+          umma_f16(tmem_s + b * 64, dq0 + off_q, dk0 + off_k, idesc_s, j > 0);
         }
         umma_commit(k_empty(kslot));
         umma_commit(s_full(b));
-        if (++kslot == C::NK) { kslot = 0; kphase ^= 1u; }
-      };
-      mbar_wait(q_full, 0);
-      for (int t = 0; t < 2 && t < T; ++t) issue_s(t);
-      for (int t = 0; t < T; ++t) {
-        const int b = t & 1;
-        GC_GTR(2, 3 * t);
-        mbar_wait(v_full(vslot), vphase);
-        GC_GTR(2, 3 * t + 1);
-        mbar_wait(p_full(b), (t >> 1) & 1);
-        GC_GTR(2, 3 * t + 2);
-        tc_fence_after();
-        const uint32_t v_base = v_smem + vslot * C::SLOT_BYTES;
+      }
+      __syncwarp();
+      if (++kslot == C::NK) { kslot = 0; kphase ^= 1u; }
+    };
+    mbar_wait(q_full, 0);
+    for (int t = 0; t < 2 && t < T; ++t) issue_s(t);
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1;
+      GC_GTR(2, 3 * t);
+      mbar_wait(v_full(vslot), vphase);
+      GC_GTR(2, 3 * t + 1);
+      mbar_wait(p_full(b), (t >> 1) & 1);
+      GC_GTR(2, 3 * t + 2);
+      fence_proxy_async_smem();
+      tc_fence_after();
+      // A: P[128 x 16 keys] from tensor memory (lane = query row, 8 columns of two bf16 each);
+      // B: V[16 keys x D], MN-major: 16 key rows of 128 B start at j * 2048, 64-wide d chunks GS * 128 B apart
+      const uint64_t dv0 = desc_mnmajor_sw128(v_smem + vslot * C::SLOT_BYTES, GS * 128, 1024);
+      if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < GS / 16; ++j) {
-          // A: P[128 x 16 keys] from tensor memory (lane = query row, 8 columns of two bf16 each);
-          // B: V[16 keys x D], MN-major: 16 key rows of 128 B start at j * 2048, 64-wide d chunks GS * 128 B apart
-          const uint64_t db = desc_mnmajor_sw128(v_base + j * 2048, GS * 128, 1024);
-          umma_f16_ts(tmem_o, tmem_s + b * 64 + 8 * j, db, idesc_o, (t > 0 || j > 0) ? 1u : 0u);
-        }
+        for (int j = 0; j < GS / 16; ++j)
+          umma_f16_ts(tmem_o, tmem_s + b * 64 + 8 * j, dv0 + static_cast<uint32_t>(j * (2048 >> 4)), idesc_o, (t > 0 || j > 0) ? 1u : 0u);
         umma_commit(v_empty(vslot));
         umma_commit(pv_done);
-        if (++vslot == C::NV) { vslot = 0; vphase ^= 1u; }
-        // S_{t+2} overwrites the columns of S_t / P_t: in issue order behind P_t V_t, which read them
-        if (t + 2 < T) issue_s(t + 2);
       }
-      umma_commit(o_full);
+      __syncwarp();
+      if (++vslot == C::NV) { vslot = 0; vphase ^= 1u; }
+      // S_{t+2} overwrites the columns of S_t / P_t: in issue order behind P_t V_t, which read them
+      if (t + 2 < T) issue_s(t + 2);
     }
+    if (elect_one()) umma_commit(o_full);
+    __syncwarp();
   } else if (warp <= 4) {
     // ---------------- softmax + epilogue: warp w owns TMEM lanes 32 (w % 4) .. + 31 = query rows of the tile
     const int q = warp & 3;
@@ -356,65 +369,41 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
       }
     }
   } else {
-    // ---------------- K / V row gather: warp lw copies rows 16 lw .. 16 lw + 15 of every step tile
+    // ---------------- K / V row gather.  Warps 5, 6 fetch the K tiles (32 rows each), warps 7, 8 the V tiles: two
+    // independent streams, so a K tile is requested the moment its slot frees (S_t formed) and never queues behind a
+    // V tile whose slot only frees when P_{t-2} V_{t-2} has completed.
     constexpr int UNITS = D / 8;                 // 16-byte units per row
     constexpr int RPI = 32 / UNITS;              // rows per warp instruction
-    constexpr int ITER = 16 / RPI;
-    const int lw = warp - 5;
+    constexpr int ITER = 32 / RPI;
+    const int lw = (warp - 5) & 1;               // which half of the tile's rows
+    const bool v_stream = warp >= 7;
     const int unit = lane % UNITS;
     const int row_in = lane / UNITS;
     const uint32_t dst_unit = static_cast<uint32_t>(unit >> 3) * (GS * 128);   // 64-wide d chunk of this unit
     const uint32_t u8 = static_cast<uint32_t>(unit & 7);
     pdl_wait();                                  // qkv is the predecessor's output
-    uint32_t pend_bar = 0;
     int ld_ev = 0;
     auto key_of = [&](int t, int rl) -> int64_t {
       if (t < G_MAX_STAGED_STEPS) return keys_s[t * GS + rl];
       return __ldg(p.keys + (static_cast<int64_t>(s_beg) + t) * GS + rl);
     };
-    auto flush_pending = [&](bool all) {
-      if (pend_bar != 0u) {
-        if (all) cp_async_wait<0>(); else cp_async_wait<1>();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(pend_bar);
-        if (threadIdx.x == 160) { GC_GTR(5, ld_ev - 1 - (all ? 0 : 1)); }
-        pend_bar = 0u;
-      }
-    };
-    // L2 prefetch of the rows a later step will gather: the ring holds two steps per operand, so a tile has about
-    // one step time to arrive; with half of qkv coming from HBM (it is as large as the L2) that is not enough
-    // (trace: 2 700-3 500 clk from issue to landed), whereas an L2 hit takes a few hundred clk.
-    constexpr int LINES = D / 64;                // 128-byte lines per row
-    auto prefetch_rows = [&](int t, int col0) {
-      if (t >= T) return;
-      const int rl = lw * 16 + lane / LINES;
-      if (lane < 16 * LINES) {
-        const __nv_bfloat16* src = p.qkv + key_of(t, rl) * p.ld_qkv + col0 + (lane % LINES) * 64;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
-      }
-    };
+    // A gather warp never waits for its own copies: every lane's cp.async.mbarrier.arrive.noinc makes the tile's
+    // "full" barrier count that lane's copies when they land.  (Waiting with cp.async.wait_group and arriving with a
+    // plain mbarrier.arrive costs a MEMBAR.ALL that also waits for the NEXT tile's copies issued just before: one tile
+    // in flight per warp and 2 700 clk from issue to signal, which made the softmax warps wait for S half of the time.)
     auto produce = [&](uint32_t empty_bar, uint32_t parity, uint32_t full_bar, uint32_t slot_base, int col0, int t) {
-      uint32_t ok = 0;
-      if (lane == 0) ok = mbar_test_wait(empty_bar, parity) ? 1u : 0u;
-      ok = __shfl_sync(0xffffffffu, ok, 0);
-      if (!ok) {
-        flush_pending(true);                      // never hold back a finished tile while waiting for a slot
-        if (lane == 0) mbar_wait(empty_bar, parity);
-        __syncwarp();
-      }
-      if (threadIdx.x == 160) { GC_GTR(0, ld_ev); ++ld_ev; }
+      if (lane == 0) mbar_wait(empty_bar, parity);
+      __syncwarp();
+      if (lane == 0 && lw == 0) { GC_GTR(v_stream ? 5 : 0, ld_ev); ++ld_ev; }
 #pragma unroll
       for (int i = 0; i < ITER; ++i) {
-        const int rl = lw * 16 + i * RPI + row_in;
+        const int rl = lw * 32 + i * RPI + row_in;
         const int64_t key = key_of(t, rl);
         const __nv_bfloat16* src = p.qkv + key * p.ld_qkv + col0 + unit * 8;
         const uint32_t dst = slot_base + dst_unit + static_cast<uint32_t>(rl) * 128u + ((u8 ^ (static_cast<uint32_t>(rl) & 7u)) << 4);
         cp_async_16(dst, src);
       }
-      cp_async_commit();
-      flush_pending(false);                       // the tile before this one has landed
-      pend_bar = full_bar;
+      cp_async_arrive_noinc(full_bar);
     };
     const int k_col = p.hd + head * D;
     const int v_col = 2 * p.hd + head * D;
@@ -428,18 +417,11 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
       produce(v_empty(vslot), vphase ^ 1u, v_full(vslot), v_smem + vslot * C::SLOT_BYTES, v_col, t);
       if (++vslot == C::NV) { vslot = 0; vphase ^= 1u; }
     };
-    // consumption order: K_0, K_1, then per step t: V_t, K_{t+2}
-    const int pf = p.prefetch_steps;
-    if (pf > 0) {
-      for (int t = 0; t < pf; ++t) { prefetch_rows(2 + t, k_col); prefetch_rows(t, v_col); }
+    if (v_stream) {
+      for (int t = 0; t < T; ++t) load_v(t);
+    } else {
+      for (int t = 0; t < T; ++t) load_k(t);
     }
-    for (int t = 0; t < 2 && t < T; ++t) load_k(t);
-    for (int t = 0; t < T; ++t) {
-      if (pf > 0) { prefetch_rows(t + pf, v_col); prefetch_rows(t + 2 + pf, k_col); }
-      load_v(t);
-      if (t + 2 < T) load_k(t + 2);
-    }
-    flush_pending(true);
   }
   if (threadIdx.x == 32) GC_GTR(4, 2);
   tc_fence_before();
@@ -491,10 +473,6 @@ extern "C" int gc_khop_attention_gather(void* stream, const void* qkv, int64_t l
   p.hd = heads * head_dim;
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)head_dim);
   p.trace = g_attention_gather_trace;
-  {
-    static const int pf = []() { const char* v = getenv("GENCAST_ATT_PREFETCH"); return v != nullptr ? atoi(v) : 2; }();
-    p.prefetch_steps = pf < 0 ? 0 : (pf > 8 ? 8 : pf);
-  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (head_dim == 64) return launch_gather<64>(st, map, p, num_q_tiles);
   return launch_gather<128>(st, map, p, num_q_tiles);

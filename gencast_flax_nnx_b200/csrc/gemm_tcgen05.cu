@@ -309,57 +309,68 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmShape 
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
+  // Producer and MMA warps run warp-uniform code and elect one lane for the TMA / tcgen05 instructions: inside an
+  // `if (lane == 0)` region the compiler treats the operands as divergent and wraps every UTCHMMA / UTMALDG in an
+  // ELECT + R2UR.BROADCAST x5 + BRA.U.ANY loop (~15 dependent instructions per MMA: the 590-650 clk k-block period
+  // measured in round 1 against 512 clk of tensor work); with uniform control flow the descriptors live in uniform
+  // registers and the four MMAs of a k-block issue back to back.
   if (warp == 0) {
-    if (lane == 0) {
-      // Weights first: with static W (shape.early_w) the W tiles of the first ring pass are requested before
-      // waiting for the predecessor grid, so their HBM latency overlaps its tail.
-      int pre = 0;
-      if (shape.early_w) {
-        for (int s = 0; s < shape.num_segments && pre < STAGES; ++s)
-          for (int kb = 0; kb < shape.kblocks[s] && pre < STAGES; ++kb, ++pre) {
+    // Weights first: with static W (shape.early_w) the W tiles of the first ring pass are requested before
+    // waiting for the predecessor grid, so their HBM latency overlaps its tail.
+    int pre = 0;
+    if (shape.early_w) {
+      for (int s = 0; s < shape.num_segments && pre < STAGES; ++s)
+        for (int kb = 0; kb < shape.kblocks[s] && pre < STAGES; ++kb, ++pre) {
+          if (elect_one()) {
             mbar_arrive_expect_tx(full_bar(pre), C::STAGE_BYTES);
             tma_load_2d(smem_b + pre * C::B_STAGE_BYTES, &maps.w[s], full_bar(pre), kb * BK, n_blk * BN);
           }
-      }
-      pdl_wait();            // first touch of operands a predecessor may have produced
-      int stage = 0, issued = 0;
-      uint32_t phase = 0;
-      for (int s = 0; s < shape.num_segments; ++s) {
-        for (int kb = 0; kb < shape.kblocks[s]; ++kb, ++issued) {
+          __syncwarp();
+        }
+    }
+    pdl_wait();            // first touch of operands a predecessor may have produced
+    int stage = 0, issued = 0;
+    uint32_t phase = 0;
+    for (int s = 0; s < shape.num_segments; ++s) {
+      for (int kb = 0; kb < shape.kblocks[s]; ++kb, ++issued) {
+        if (issued >= pre) mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
           if (issued >= pre) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
             tma_load_2d(smem_b + stage * C::B_STAGE_BYTES, &maps.w[s], full_bar(stage), kb * BK, n_blk * BN);
           }
           tma_load_2d(smem_a + stage * A_STAGE_BYTES, &maps.a[s], full_bar(stage), kb * BK, m_blk * BM);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16_f32(BM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t accumulate = 0;
-      for (int s = 0; s < shape.num_segments; ++s) {
-        for (int kb = 0; kb < shape.kblocks[s]; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint64_t da = desc_kmajor_sw128(smem_a + stage * A_STAGE_BYTES);
-          const uint64_t db = desc_kmajor_sw128(smem_b + stage * C::B_STAGE_BYTES);
+    constexpr uint32_t idesc = idesc_bf16_f32(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t accumulate = 0;
+    for (int s = 0; s < shape.num_segments; ++s) {
+      for (int kb = 0; kb < shape.kblocks[s]; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint64_t da = desc_kmajor_sw128(smem_a + stage * A_STAGE_BYTES);
+        const uint64_t db = desc_kmajor_sw128(smem_b + stage * C::B_STAGE_BYTES);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 16 bf16 = 32 bytes inside the 128-byte swizzle span: +2 in the (>>4) address field
-            umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, accumulate);
-            accumulate = 1;
+            umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, (accumulate | static_cast<uint32_t>(k)) != 0u ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        accumulate = 1;
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(tmem_full_bar);
     }
+    if (elect_one()) umma_commit(tmem_full_bar);
+    __syncwarp();
   } else {
     // Epilogue: TMEM lane quarter is fixed by warp id modulo 4.  32 columns per step, the next
     // step's tcgen05.ld is in flight while the current one is processed.
@@ -468,75 +479,82 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
   if (warp == 0) {
-    if (lane == 0) {
-      auto load_w = [&](int st, int s, int kb, int n_blk) {
-        // W box is 128 rows: two boxes for a 256-wide tile
+    auto load_w = [&](int st, int s, int kb, int n_blk) {
+      // W box is 128 rows: two boxes for a 256-wide tile
 #pragma unroll
-        for (int h = 0; h < PBN / 128; ++h)
-          tma_load_2d(smem_b + st * C::B_STAGE_BYTES + h * (128 * BK * 2), &maps.w[s], full_bar(st), kb * BK,
-                      n_blk * PBN + h * 128);
-      };
-      // weights of the first ring pass before the wait for the predecessor grid (see the one-tile kernel)
-      int pre = 0;
-      if (shape.early_w && static_cast<int>(blockIdx.x) < num_tiles) {
-        const int n_blk0 = static_cast<int>(blockIdx.x) % shape.n_tiles;
-        for (int s = 0; s < shape.num_segments && pre < PSTAGES; ++s)
-          for (int kb = 0; kb < shape.kblocks[s] && pre < PSTAGES; ++kb, ++pre) {
+      for (int h = 0; h < PBN / 128; ++h)
+        tma_load_2d(smem_b + st * C::B_STAGE_BYTES + h * (128 * BK * 2), &maps.w[s], full_bar(st), kb * BK,
+                    n_blk * PBN + h * 128);
+    };
+    // weights of the first ring pass before the wait for the predecessor grid (see the one-tile kernel)
+    int pre = 0;
+    if (shape.early_w && static_cast<int>(blockIdx.x) < num_tiles) {
+      const int n_blk0 = static_cast<int>(blockIdx.x) % shape.n_tiles;
+      for (int s = 0; s < shape.num_segments && pre < PSTAGES; ++s)
+        for (int kb = 0; kb < shape.kblocks[s] && pre < PSTAGES; ++kb, ++pre) {
+          if (elect_one()) {
             mbar_arrive_expect_tx(full_bar(pre), C::STAGE_BYTES);
             load_w(pre, s, kb, n_blk0);
           }
-      }
-      pdl_wait();
-      int stage = 0, issued = 0;
-      uint32_t phase = 0;
-      int ev = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_blk = tile % shape.n_tiles, m_blk = tile / shape.n_tiles;
-        for (int s = 0; s < shape.num_segments; ++s) {
-          for (int kb = 0; kb < shape.kblocks[s]; ++kb, ++issued) {
+          __syncwarp();
+        }
+    }
+    pdl_wait();
+    int stage = 0, issued = 0;
+    uint32_t phase = 0;
+    int ev = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_blk = tile % shape.n_tiles, m_blk = tile / shape.n_tiles;
+      for (int s = 0; s < shape.num_segments; ++s) {
+        for (int kb = 0; kb < shape.kblocks[s]; ++kb, ++issued) {
+          if (issued >= pre) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            GC_GTRACE(0, ev); ++ev;
+          }
+          if (elect_one()) {
             if (issued >= pre) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
-              GC_GTRACE(0, ev); ++ev;
               mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
               load_w(stage, s, kb, n_blk);
             }
             tma_load_2d(smem_a + stage * A_STAGE_BYTES, &maps.a[s], full_bar(stage), kb * BK, m_blk * BM);
-            if (++stage == PSTAGES) { stage = 0; phase ^= 1u; }
           }
+          __syncwarp();
+          if (++stage == PSTAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16_f32(BM, PBN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-        const int b = lt & 1;
-        GC_GTRACE(1, 4 * lt);
-        mbar_wait(acc_empty(b), ((lt >> 1) & 1) ^ 1u);      // epilogue has drained this accumulator buffer
-        GC_GTRACE(1, 4 * lt + 1);
-        tc_fence_after();
-        uint32_t accumulate = 0;
-        for (int s = 0; s < shape.num_segments; ++s) {
-          for (int kb = 0; kb < shape.kblocks[s]; ++kb) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-            const uint64_t da = desc_kmajor_sw128(smem_a + stage * A_STAGE_BYTES);
-            const uint64_t db = desc_kmajor_sw128(smem_b + stage * C::B_STAGE_BYTES);
+    constexpr uint32_t idesc = idesc_bf16_f32(BM, PBN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int b = lt & 1;
+      GC_GTRACE(1, 4 * lt);
+      mbar_wait(acc_empty(b), ((lt >> 1) & 1) ^ 1u);      // epilogue has drained this accumulator buffer
+      GC_GTRACE(1, 4 * lt + 1);
+      tc_fence_after();
+      uint32_t accumulate = 0;
+      for (int s = 0; s < shape.num_segments; ++s) {
+        for (int kb = 0; kb < shape.kblocks[s]; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t da = desc_kmajor_sw128(smem_a + stage * A_STAGE_BYTES);
+          const uint64_t db = desc_kmajor_sw128(smem_b + stage * C::B_STAGE_BYTES);
+          if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              umma_f16(tmem_base + b * PBN, da + 2u * k, db + 2u * k, idesc, accumulate);
-              accumulate = 1;
-            }
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_f16(tmem_base + b * PBN, da + 2u * k, db + 2u * k, idesc, (accumulate | static_cast<uint32_t>(k)) != 0u ? 1u : 0u);
             umma_commit(empty_bar(stage));
-            if (++stage == PSTAGES) { stage = 0; phase ^= 1u; }
           }
+          __syncwarp();
+          accumulate = 1;
+          if (++stage == PSTAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(acc_full(b));
-        GC_GTRACE(1, 4 * lt + 2);
       }
+      if (elect_one()) umma_commit(acc_full(b));
+      __syncwarp();
+      GC_GTRACE(1, 4 * lt + 2);
     }
   } else {
     const int q = warp & 3;
@@ -646,42 +664,48 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmS
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
   if (warp == 0) {
-    if (lane == 0) {
-      // weights of the first ring pass before the wait for the predecessor grid (see the one-tile kernel)
-      int pre = 0;
-      if (shape.early_w && pair_id < num_tiles) {
-        const int n_row0 = (pair_id % shape.n_tiles) * QBN + static_cast<int>(rank) * 128;
-        for (int s = 0; s < shape.num_segments && pre < Q_STAGES; ++s)
-          for (int kb = 0; kb < shape.kblocks[s] && pre < Q_STAGES; ++kb, ++pre) {
+    // weights of the first ring pass before the wait for the predecessor grid (see the one-tile kernel)
+    int pre = 0;
+    if (shape.early_w && pair_id < num_tiles) {
+      const int n_row0 = (pair_id % shape.n_tiles) * QBN + static_cast<int>(rank) * 128;
+      for (int s = 0; s < shape.num_segments && pre < Q_STAGES; ++s)
+        for (int kb = 0; kb < shape.kblocks[s] && pre < Q_STAGES; ++kb, ++pre) {
+          if (elect_one()) {
             if (rank == 0) mbar_arrive_expect_tx(full_bar(pre), 2 * Q_STAGE_BYTES);
             tma_load_2d_pair(smem_b + pre * Q_B_STAGE_BYTES, &maps.w[s], full_bar(pre), kb * BK, n_row0);
           }
-      }
-      pdl_wait();
-      int stage = 0, issued = 0;
-      uint32_t phase = 0;
-      int ev = 0;
-      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
-        const int n_blk = tile % shape.n_tiles, m_pair = tile / shape.n_tiles;
-        const int m_row = m_pair * 256 + static_cast<int>(rank) * 128;
-        const int n_row = n_blk * QBN + static_cast<int>(rank) * 128;
-        for (int s = 0; s < shape.num_segments; ++s) {
-          for (int kb = 0; kb < shape.kblocks[s]; ++kb, ++issued) {
+          __syncwarp();
+        }
+    }
+    pdl_wait();
+    int stage = 0, issued = 0;
+    uint32_t phase = 0;
+    int ev = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      const int n_blk = tile % shape.n_tiles, m_pair = tile / shape.n_tiles;
+      const int m_row = m_pair * 256 + static_cast<int>(rank) * 128;
+      const int n_row = n_blk * QBN + static_cast<int>(rank) * 128;
+      for (int s = 0; s < shape.num_segments; ++s) {
+        for (int kb = 0; kb < shape.kblocks[s]; ++kb, ++issued) {
+          if (issued >= pre) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            GC_GTRACE(0, ev); ++ev;
+          }
+          if (elect_one()) {
             if (issued >= pre) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
-              GC_GTRACE(0, ev); ++ev;
               // the leader arms its barrier for the bytes of both CTAs
               if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Q_STAGE_BYTES);
               tma_load_2d_pair(smem_b + stage * Q_B_STAGE_BYTES, &maps.w[s], full_bar(stage), kb * BK, n_row);
             }
             tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &maps.a[s], full_bar(stage), kb * BK, m_row);
-            if (++stage == Q_STAGES) { stage = 0; phase ^= 1u; }
           }
+          __syncwarp();
+          if (++stage == Q_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       constexpr uint32_t idesc = idesc_bf16_f32(256, QBN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -701,16 +725,19 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmS
             tc_fence_after();
             const uint64_t da = desc_kmajor_sw128(smem_a + stage * A_STAGE_BYTES);
             const uint64_t db = desc_kmajor_sw128(smem_b + stage * Q_B_STAGE_BYTES);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              umma_f16_pair(tmem_base + b * QBN, da + 2u * k, db + 2u * k, idesc, accumulate);
-              accumulate = 1;
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_f16_pair(tmem_base + b * QBN, da + 2u * k, db + 2u * k, idesc, (accumulate | static_cast<uint32_t>(k)) != 0u ? 1u : 0u);
+              umma_commit_pair(empty_bar(stage));               // frees the stage in both CTAs
             }
-            umma_commit_pair(empty_bar(stage));               // frees the stage in both CTAs
+            __syncwarp();
+            accumulate = 1;
             if (++stage == Q_STAGES) { stage = 0; phase ^= 1u; }
           }
         }
-        umma_commit_pair(acc_full(b));
+        if (elect_one()) umma_commit_pair(acc_full(b));
+        __syncwarp();
         GC_GTRACE(1, 4 * lt + 2);
       }
     }

@@ -165,6 +165,9 @@ class DenoiserEngine:
         self.use_tc_attention = (attention == "auto" and compute_dtype == "bf16" and self.head_dim in (64, 128))
         self._sigma_cache: Dict[float, SigmaContext] = {}
         self.edge_table_budget_bytes = int(float(os.environ.get("GENCAST_EDGE_TABLE_GB", "24")) * 2 ** 30)
+        # mesh2grid edge update + aggregation in one kernel (gc_edge_mlp_sum3); GENCAST_EDGE_FUSED=0 keeps the
+        # three-kernel path (gc_edge_hidden / edge GEMM with gathers -> second-layer GEMM -> gc_ln_cond_segment_sum)
+        self.fuse_m2g = compute_dtype == "bf16" and os.environ.get("GENCAST_EDGE_FUSED", "1") != "0"
         with torch.cuda.device(self.device):
             self._upload_graph()
             self._upload_weights()
@@ -566,13 +569,23 @@ class DenoiserEngine:
         if branch_stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(branch_stream)
         e_h, e_y = self.e_h[:E2], self.e_y[:E2]
-        if ctx.m2g_base is not None:
+        if self.fuse_m2g and self.m2g_perm is None:
+            # every grid node has exactly three incoming edges, stored grid-major: gather + first-layer sum + swish feed
+            # the second-layer GEMM from shared memory, LayerNorm + affine + the 3-row sums run in its epilogue
+            base = ctx.m2g_base
+            if base is None:
+                base = ops.gemm([(self.m2g_e_ln, ctx.m2g_w1e)], e_h, bias=ctx.m2g_b1)
+            ops.edge_mlp_sum3(base, [(self.m_p, self.m2g_s), (self.g_p2, self.m2g_r)], w["du_w2"], w["du_b2"],
+                              T[self.C_M2G_EU], self.g_agg, act="swish")
+        elif ctx.m2g_base is not None:
             ops.edge_hidden(ctx.m2g_base, [(self.m_p, self.m2g_s), (self.g_p2, self.m2g_r)], e_h, act="swish")
+            _gemm([(e_h, w["du_w2"])], e_y, bias=w["du_b2"])
+            ops.ln_cond_segment_sum(e_y, self.g_agg, T[self.C_M2G_EU], self.m2g_row_ptr, self.m2g_perm)
         else:
             ops.gemm([(self.m2g_e_ln, ctx.m2g_w1e)], e_h, bias=ctx.m2g_b1, act="swish",
                      gathers=[(self.m_p, self.m2g_s), (self.g_p2, self.m2g_r)])
-        _gemm([(e_h, w["du_w2"])], e_y, bias=w["du_b2"])
-        ops.ln_cond_segment_sum(e_y, self.g_agg, T[self.C_M2G_EU], self.m2g_row_ptr, self.m2g_perm)
+            _gemm([(e_h, w["du_w2"])], e_y, bias=w["du_b2"])
+            ops.ln_cond_segment_sum(e_y, self.g_agg, T[self.C_M2G_EU], self.m2g_row_ptr, self.m2g_perm)
         self._mlp_ln([(self.g_lat, w["dg_w1a"]), (self.g_agg, w["dg_w1b"])], w["dg_b1"], w["dg_w2"], w["dg_b2"],
                      self.g_h, self.g_y, self.g2, T[self.C_M2G_GU], residual=self.g_lat)
         _gemm([(self.g2, w["out_w1"])], self.g_h, bias=w["out_b1"], act="swish")
@@ -593,7 +606,12 @@ class DenoiserEngine:
 
     @property
     def launches_per_forward(self) -> int:
-        return self.LAUNCHES_PER_FORWARD_FIXED + 7 * self.NL
+        n = self.LAUNCHES_PER_FORWARD_FIXED + 7 * self.NL
+        if self.fuse_m2g and self.m2g_perm is None:
+            # fused mesh2grid edge path: 1 kernel instead of 3 with the per-level tables, 2 instead of 3 without
+            tables = bool(self._sigma_cache) and next(iter(self._sigma_cache.values())).m2g_base is not None
+            n -= 2 if tables else 1
+        return n
 
 
 # ----------------------------------------------------------------------------------

@@ -262,6 +262,25 @@ GC_API int gc_edge_hidden(void* stream, const void* base, int64_t ld_base, int64
                    int32_t act, void* out, int64_t ldo, int64_t rows, int32_t cols);
 
 /*
+ * Fused edge update + aggregation for a bipartite graph whose receivers have exactly three incoming edges each,
+ * stored receiver-major (edges 3v, 3v+1, 3v+2 -> receiver v; GenCast's mesh2grid decoder,
+ * common/grid_mesh_connectivity.py:104, :125-131).  One kernel, no [E, cols] tensor in HBM:
+ *   h_e   = act( base[e mod period] + gs[idx_s[e]] + gr[idx_r[e]] )         first edge-MLP layer, split by operand
+ *   y_e   = h_e . W2^T + b2                                                 second layer (tcgen05, fp32 accumulate)
+ *   out_v = scale * sum_{e in 3v..3v+2} LayerNorm(y_e) + 3 * offset         LN + conditional affine + segment sum
+ * Replaces EdgeWrapper / MLPWithNormConditioning of the edge update (common/typed_graph_net.py:134-159, :295-305;
+ * common/mlp.py:115-147) together with jraph.segment_sum (common/typed_graph_net.py:161-195,
+ * common/deep_typed_graph_net.py:396-410).  base / gs / gr / w2 are bf16; w2 is [cols, cols] stored [out, in];
+ * b2 [cols] and scale_offset [2 cols] = (1 + s | o) are fp32 (either may be NULL); out is bf16 or fp32,
+ * [num_receivers, cols]; idx_s / idx_r have 3 * num_receivers entries.  cols in {128, 256, 512}.
+ */
+GC_API int gc_edge_mlp_sum3(void* stream, const void* base, int64_t ld_base, int64_t period, const void* gs,
+                            const int32_t* idx_s, int64_t ld_gs, const void* gr, const int32_t* idx_r, int64_t ld_gr,
+                            int32_t act, const void* w2, int64_t ld_w2, const float* b2, const float* scale_offset,
+                            int32_t do_layer_norm, void* out, int32_t out_dtype, int64_t ldo, int64_t num_receivers,
+                            int32_t cols);
+
+/*
  * Fair CRPS of an M-member ensemble per grid point and channel (no reference implementation
  * exists; defined in DESIGN.md / parallel.py):
  *   crps[i] = mean_m |x_m[i] - y[i]|  -  sum_{j<k} |x_j[i] - x_k[i]| / (M (M - 1))

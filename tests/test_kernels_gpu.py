@@ -333,6 +333,50 @@ def test_khop_attention_gather_members_share_masks(cuda_device):
     assert torch.equal(out2[:n], single[0]) and torch.equal(out2[n:], single[1])
 
 
+@pytest.mark.parametrize("cols,nrecv,members", [(128, 37, 1), (256, 1000, 2), (512, 6000, 1), (512, 20000, 4)])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_edge_mlp_sum3_fused(cuda_device, cols, nrecv, members, out_dtype):
+    """Fused degree-3 edge update + aggregation (gather-add-swish -> tcgen05 GEMM -> LayerNorm -> 3-row segment sum ->
+    conditional affine) against the same chain in fp64 on the bf16-rounded operands; bitwise repeatable."""
+    from gencast_flax_nnx_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(cols + nrecv)
+    d = cuda_device
+    R = nrecv * members
+    E = 3 * R
+    period = 3 * nrecv                                        # base rows are shared by the members
+    n_s, n_r = 777, R
+    bf = lambda t: t.to(torch.bfloat16)
+    base = bf(torch.randn(period, cols, generator=g))
+    gs = bf(torch.randn(n_s, cols, generator=g))
+    gr = bf(torch.randn(n_r, cols, generator=g))
+    idx_s = torch.randint(0, n_s, (E,), generator=g, dtype=torch.int32)
+    idx_r = torch.arange(R, dtype=torch.int32).repeat_interleave(3)
+    w2 = bf(torch.randn(cols, cols, generator=g) / math.sqrt(cols))
+    b2 = torch.randn(cols, generator=g) * 0.1
+    so = torch.cat([1 + 0.1 * torch.randn(cols, generator=g), torch.randn(cols, generator=g)])
+    e = torch.arange(E)
+    h = base.double()[e % period] + gs.double()[idx_s.long()] + gr.double()[idx_r.long()]
+    h = bf((h * torch.sigmoid(h)).float()).double()
+    y = h @ w2.double().T + b2.double()
+    mean = y.mean(-1, keepdim=True)
+    var = ((y * y).mean(-1, keepdim=True) - mean * mean).clamp_min(0)
+    ln = (y - mean) / torch.sqrt(var + 1e-6)
+    ref = ln.reshape(R, 3, cols).sum(1) * so[:cols].double() + 3 * so[cols:].double()
+    outs = []
+    for _ in range(2):
+        out = torch.full((R, cols), float("nan"), dtype=out_dtype, device=d)
+        ops.edge_mlp_sum3(base.to(d), [(gs.to(d), idx_s.to(d)), (gr.to(d), idx_r.to(d))], w2.to(d), b2.to(d), so.to(d), out)
+        torch.cuda.synchronize()
+        outs.append(out.cpu())
+    # the hidden layer is rounded to bf16 on both sides; MUFU swish differs from the exact one by < 1 bf16 ulp
+    assert _rel(outs[0], ref) < (1.2e-2 if out_dtype == torch.bfloat16 else 8e-3)
+    assert torch.equal(outs[0], outs[1])
+    # without LayerNorm / affine / bias: plain sum of the three second-layer outputs
+    out = torch.empty(R, cols, dtype=torch.float32, device=d)
+    ops.edge_mlp_sum3(base.to(d), [(gs.to(d), idx_s.to(d)), (gr.to(d), idx_r.to(d))], w2.to(d), None, None, out, layer_norm=False)
+    assert _rel(out.cpu(), (h @ w2.double().T).reshape(R, 3, cols).sum(1)) < 8e-3
+
+
 def test_cond_tables_and_fold(cuda_device):
     from gencast_flax_nnx_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(9)

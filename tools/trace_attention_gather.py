@@ -55,7 +55,7 @@ t0 = tr[6][0]
 rel = lambda x: int(x - t0) if x > 0 else -1
 print(f"CTA 0: query tile {qt}, T={T} steps; cycles since kernel entry")
 print("loader warp 5: slot free -> copies issued at:", [rel(x) for x in tr[0][: 2 * T]])
-print("loader warp 5: tile signalled at            :", [rel(x) for x in tr[5][: 2 * T]])
+
 print("MMA S  (wait K start, K ready):", [(rel(tr[1][2 * i]), rel(tr[1][2 * i + 1])) for i in range(T)])
 print("MMA PV (start, V ready, P ready):", [(rel(tr[2][3 * i]), rel(tr[2][3 * i + 1]), rel(tr[2][3 * i + 2])) for i in range(T)])
 print("softmax warp 1 (wait S start, S arrived, P signalled):", [(rel(tr[3][3 * i]), rel(tr[3][3 * i + 1]), rel(tr[3][3 * i + 2])) for i in range(T)])
