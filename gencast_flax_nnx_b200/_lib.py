@@ -53,6 +53,59 @@ class GemmArgs(Structure):
     ]
 
 
+class Mlp2(Structure):
+    """Mirror of struct gc_mlp2."""
+    _fields_ = [("w1", c_void_p * GC_MAX_SEGMENTS), ("k1", c_int32 * GC_MAX_SEGMENTS), ("num_segments", c_int32),
+                ("b1", c_void_p), ("w2", c_void_p), ("b2", c_void_p)]
+
+
+class TransformerLayer(Structure):
+    """Mirror of struct gc_transformer_layer."""
+    _fields_ = [("wqkv", c_void_p), ("wo", c_void_p), ("bo", c_void_p), ("w1", c_void_p), ("b1", c_void_p),
+                ("w2", c_void_p), ("b2", c_void_p)]
+
+
+class DenoiserModel(Structure):
+    """Mirror of struct gc_denoiser_model."""
+    _fields_ = [("dtype", c_int32), ("latent", c_int32), ("heads", c_int32), ("head_dim", c_int32), ("ffw_hidden", c_int32),
+                ("num_layers", c_int32), ("n_out_padded", c_int32), ("reserved", c_int32),
+                ("grid_embed", Mlp2), ("g2m_w1s", c_void_p), ("g2m_w2", c_void_p), ("g2m_b2", c_void_p),
+                ("mesh_update", Mlp2), ("grid_update", Mlp2), ("layers", POINTER(TransformerLayer)),
+                ("m2g_w1s", c_void_p), ("m2g_w1r", c_void_p), ("m2g_w2", c_void_p), ("m2g_b2", c_void_p),
+                ("m2g_grid_update", Mlp2), ("output", Mlp2)]
+
+
+class DenoiserGraph(Structure):
+    """Mirror of struct gc_denoiser_graph."""
+    _fields_ = [("grid_rows", c_int64), ("mesh_rows", c_int64), ("g2m_edges", c_int64), ("m2g_edges", c_int64),
+                ("g2m_senders", c_void_p), ("g2m_receivers", c_void_p), ("g2m_row_ptr", c_void_p), ("g2m_perm", c_void_p),
+                ("m2g_senders", c_void_p), ("m2g_receivers", c_void_p), ("m2g_row_ptr", c_void_p), ("m2g_perm", c_void_p),
+                ("g2m_edge_ln", c_void_p), ("m2g_edge_ln", c_void_p),
+                ("attention_kind", c_int32), ("max_degree", c_int32), ("num_q_tiles", c_int32), ("mask_period", c_int32),
+                ("step_ptr", c_void_p), ("keys", c_void_p), ("step_mask", c_void_p), ("work", c_void_p),
+                ("tile_ptr", c_void_p), ("tile_kv", c_void_p), ("tile_mask", c_void_p),
+                ("nbr_ptr", c_void_p), ("nbr_idx", c_void_p)]
+
+
+class SigmaContextC(Structure):
+    """Mirror of struct gc_sigma_context."""
+    _fields_ = [("table", c_void_p), ("g2m_w1e", c_void_p), ("g2m_b1", c_void_p), ("m2g_w1e", c_void_p), ("m2g_b1", c_void_p),
+                ("g2m_base", c_void_p), ("m2g_base", c_void_p), ("g2m_base_rows", c_int64), ("m2g_base_rows", c_int64),
+                ("m0", c_void_p), ("m_p", c_void_p)]
+
+
+class DenoiserWorkspace(Structure):
+    """Mirror of struct gc_denoiser_workspace."""
+    _fields_ = [(n, c_void_p) for n in (
+        "xin", "a_const", "g_h", "g_y", "g_h2", "g_y2", "g0", "g_lat", "g2", "g_p", "g_p2", "g_agg",
+        "m_h", "m_y", "m_p", "m_agg", "m_out", "t_h", "t_o", "x", "t_qkv", "t_f", "e_h", "e_y", "f_out",
+        "branch_stream", "fork_event", "join_event")] + [("flags", c_int32), ("reserved", c_int32)]
+
+
+GC_ATTENTION_CSR, GC_ATTENTION_TILES, GC_ATTENTION_GATHER = 0, 1, 2
+GC_FORWARD_FUSE_M2G = 1
+FORWARD_STRUCTS = (DenoiserModel, DenoiserGraph, SigmaContextC, DenoiserWorkspace, Mlp2, TransformerLayer)
+
 # name -> (restype, argtypes); also the list of symbols tests check for.
 SIGNATURES = {
     "gc_last_error": (c_char_p, []),
@@ -85,6 +138,9 @@ SIGNATURES = {
     "gc_edge_mlp_sum3": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                    c_int64, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_int32,
                                    c_int64, c_int64, c_int32]),
+    "gc_denoiser_forward": (c_int32, [c_void_p, POINTER(DenoiserModel), POINTER(DenoiserGraph), POINTER(SigmaContextC),
+                                      POINTER(DenoiserWorkspace)]),
+    "gc_sizeof_forward_structs": (c_int32, [c_int32]),
     "gc_fair_crps": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_int64]),
     "gc_column_sums": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "gc_ensemble_accumulate": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),
@@ -113,6 +169,10 @@ def load() -> ctypes.CDLL:
         fn.argtypes = argtypes
     if lib.gc_sizeof_gemm_args() != ctypes.sizeof(GemmArgs):
         raise GencastKernelError("struct gc_gemm_args layout mismatch between the library and the ctypes binding")
+    for i, st in enumerate(FORWARD_STRUCTS):
+        if lib.gc_sizeof_forward_structs(i) != ctypes.sizeof(st):
+            raise GencastKernelError(f"struct layout mismatch between the library and the ctypes binding: {st.__name__} "
+                                     f"({lib.gc_sizeof_forward_structs(i)} vs {ctypes.sizeof(st)})")
     _lib = lib
     return lib
 

@@ -247,11 +247,12 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const float c2 = p.scale_log2e;
     const uint32_t o_addr = tmem_o + lane_addr;
-    auto mask_of = [&](int t) {
-      int gs = s_beg + t;
-      if (p.mask_period > 0) gs %= p.mask_period;
-      return __ldg(p.mask + static_cast<int64_t>(gs) * GQ + r);
-    };
+    // masks repeat with period p.mask_period over the global step index (members share one copy); a query tile's
+    // steps are contiguous inside one period, so the reduction is done once (a per-step modulo is a ~30-instruction
+    // sequence through the XU pipe on the softmax warps' critical path)
+    const int gs0 = p.mask_period > 0 ? s_beg % p.mask_period : s_beg;
+    const uint2* mask_row = p.mask + static_cast<int64_t>(gs0) * GQ + r;
+    auto mask_of = [&](int t) { return __ldg(mask_row + static_cast<int64_t>(t) * GQ); };
     float m = -INFINITY;                                 // the row's offset, in raw logit units
     float l0 = 0.0f, l1 = 0.0f;
     uint2 mk_next = make_uint2(0u, 0u);

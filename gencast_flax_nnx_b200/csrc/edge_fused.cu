@@ -70,7 +70,17 @@ struct EdgeFusedParams {
   void* out; int out_dtype; int64_t ldo;
   int64_t num_receivers;
   int num_tiles;
+  int members, tiles_per_member;   // tile order: see tile_of()
 };
+
+// Ensemble members evaluated together share the `base` table (period = one member's edges).  Walking the tiles member by
+// member streams the table from HBM once per member; interleaving the members (consecutive tile slots = the same base
+// rows for member 0, 1, ...) makes all but the first read of a base row an L2 hit.  Falls back to the plain order when
+// the member blocks are not a whole number of tiles.
+__device__ __forceinline__ int tile_of(const EdgeFusedParams& p, int slot) {
+  if (p.members <= 1) return slot;
+  return (slot % p.members) * p.tiles_per_member + slot / p.members;
+}
 
 template <int L>
 __global__ void __launch_bounds__(EF_THREADS, 1)
@@ -176,7 +186,8 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const EdgeFusedP
     pdl_wait();
     int sa = 0;
     uint32_t pa = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int slot = blockIdx.x; slot < p.num_tiles; slot += gridDim.x) {
+      const int tile = tile_of(p, slot);
       // rows of this thread: quarter j holds receivers 10 j .. 10 j + 9 of the tile
       const __nv_bfloat16* pb[4];
       const __nv_bfloat16* ps[4];
@@ -258,7 +269,8 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const EdgeFusedP
     const float* ofs = vec_s + 2 * L + half * CH;
     const float inv_n = 1.0f / static_cast<float>(L);
     int lt = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+    for (int slot = blockIdx.x; slot < p.num_tiles; slot += gridDim.x, ++lt) {
+      const int tile = tile_of(p, slot);
       mbar_wait(acc_full, static_cast<uint32_t>(lt) & 1u);
       tc_fence_after();
       // ---- pass 1: row statistics of y = acc + b2 over this warp's half of the columns
@@ -388,6 +400,14 @@ extern "C" int gc_edge_mlp_sum3(void* stream, const void* base, int64_t ld_base,
   p.act = act; p.b2 = b2; p.scale_offset = scale_offset; p.do_ln = do_layer_norm;
   p.out = out; p.out_dtype = out_dtype; p.ldo = ldo; p.num_receivers = num_receivers;
   p.num_tiles = (int)((num_receivers + EF_RECV_PER_TILE - 1) / EF_RECV_PER_TILE);
+  p.members = 1; p.tiles_per_member = p.num_tiles;
+  {
+    const int64_t edges = 3 * num_receivers, per_tile = 3 * EF_RECV_PER_TILE;
+    if (period < edges && edges % period == 0 && period % per_tile == 0) {
+      p.members = (int)(edges / period);
+      p.tiles_per_member = (int)(period / per_tile);
+    }
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (cols == 128) return launch_edge_fused<128>(st, w_map, p);
   if (cols == 256) return launch_edge_fused<256>(st, w_map, p);

@@ -329,6 +329,14 @@ def edge_mlp_sum3(base: torch.Tensor, gathers: Sequence[Tuple[torch.Tensor, torc
     return out
 
 
+def denoiser_forward(model, graph, sigma, workspace) -> None:
+    """One whole network evaluation through gc_denoiser_forward (descriptors: _lib.DenoiserModel, DenoiserGraph,
+    SigmaContextC, DenoiserWorkspace, filled by the engine)."""
+    lib = _lib.load()
+    _lib.check(lib.gc_denoiser_forward(_stream(), ctypes.byref(model), ctypes.byref(graph), ctypes.byref(sigma),
+                                       ctypes.byref(workspace)), "gc_denoiser_forward")
+
+
 def fair_crps(members: torch.Tensor, truth: torch.Tensor, weights: Optional[torch.Tensor], channels: int) -> torch.Tensor:
     """members [M, n] fp32, truth [n], weights [n / channels] or None -> weighted fair CRPS per point, [n] fp32."""
     lib = _lib.load()

@@ -299,6 +299,109 @@ GC_API int gc_column_sums(void* stream, const float* x, int64_t rows, int32_t co
  */
 GC_API int gc_ensemble_accumulate(void* stream, const float* x, float* sum, float* sumsq, int64_t n);
 
+/*
+ * ---------------------------------------------------------------------------------------------------------------
+ * One whole network evaluation in a single call.
+ *
+ * gc_denoiser_forward sequences the ~135 kernel launches of F(c_in x, sigma) -- DenoiserArchitecture.__call__,
+ * gencast/denoiser.py:303-341: grid2mesh GNN (:602-688), mesh transformer (:691-728; gencast/sparse_transformer.py:
+ * 486-525, :624-634), mesh2grid GNN (:730-768) -- on `stream`, from descriptors of device pointers that the host
+ * fills once.  This is the entry point an XLA FFI custom call (or any non-Python host) binds when it wants the
+ * denoiser as one operator; csrc/xla_ffi_shim.cc wraps it.  Enqueue-only, CUDA-graph capturable, no allocation.
+ * All matrices are row-major and contiguous (leading dimension = columns); weights are stored [out, in] (the
+ * Linear kernel transposed, K contiguous, K padded to a multiple of 64) in the operand dtype `dtype`.
+ * ---------------------------------------------------------------------------------------------------------------
+ */
+#define GC_ATTENTION_CSR 0
+#define GC_ATTENTION_TILES 1
+#define GC_ATTENTION_GATHER 2
+
+/* rows of gc_sigma_context.table (one (1 + s | o) vector of 2 * latent floats per conditional LayerNorm) */
+#define GC_COND_G2M_EDGE_EMBED 0
+#define GC_COND_G2M_GRID_EMBED 1
+#define GC_COND_G2M_MESH_EMBED 2
+#define GC_COND_G2M_EDGE_UPDATE 3
+#define GC_COND_G2M_GRID_UPDATE 4
+#define GC_COND_G2M_MESH_UPDATE 5
+#define GC_COND_TRANSFORMER0 6   /* + 2 i: attention norm of block i, + 2 i + 1: its FFW norm; then the final norm,
+                                    the mesh2grid edge embedding, edge update and grid update */
+
+#define GC_FORWARD_FUSE_M2G 1    /* mesh2grid edge update + aggregation through gc_edge_mlp_sum3 */
+
+/* Linear -> swish -> Linear (common/mlp.py:152-203); the first layer may be split in K-segments (concatenated
+ * operands of the reference, common/typed_graph_net.py:301-305, :315-326) */
+typedef struct gc_mlp2 {
+  const void* w1[GC_MAX_SEGMENTS];   /* [latent, k1[s]] */
+  int32_t k1[GC_MAX_SEGMENTS];
+  int32_t num_segments;
+  const float* b1;                   /* [latent] */
+  const void* w2;                    /* [n2, latent] */
+  const float* b2;                   /* [n2] */
+} gc_mlp2;
+
+/* one transformer block (gencast/sparse_transformer.py:252-307, :458-525) */
+typedef struct gc_transformer_layer {
+  const void* wqkv;                  /* [3 latent, latent]: q | k | v projections, no bias (:281) */
+  const void* wo; const float* bo;   /* [latent, latent] output projection with bias (:305) */
+  const void* w1; const float* b1;   /* [ffw_hidden, latent] */
+  const void* w2; const float* b2;   /* [latent, ffw_hidden] */
+} gc_transformer_layer;
+
+typedef struct gc_denoiser_model {
+  int32_t dtype;                     /* GC_BF16 (tensor cores) or GC_F32 */
+  int32_t latent, heads, head_dim, ffw_hidden, num_layers, n_out_padded, reserved;
+  gc_mlp2 grid_embed;                /* segments: c_in * noisy targets [KN], per-step constants [KC] */
+  const void* g2m_w1s;               /* sender block of the grid2mesh edge MLP's first layer, [latent, latent] */
+  const void* g2m_w2; const float* g2m_b2;
+  gc_mlp2 mesh_update;               /* segments: embedded mesh nodes, aggregated messages */
+  gc_mlp2 grid_update;
+  const gc_transformer_layer* layers;   /* host array [num_layers] */
+  const void* m2g_w1s; const void* m2g_w1r;   /* sender / receiver blocks of the mesh2grid edge MLP's first layer */
+  const void* m2g_w2; const float* m2g_b2;
+  gc_mlp2 m2g_grid_update;           /* segments: grid latents, aggregated messages */
+  gc_mlp2 output;                    /* latent -> latent -> n_out_padded, no LayerNorm (deep_typed_graph_net.py:469-485) */
+} gc_denoiser_model;
+
+typedef struct gc_denoiser_graph {
+  int64_t grid_rows, mesh_rows, g2m_edges, m2g_edges;    /* totals over the ensemble members evaluated together */
+  const int32_t* g2m_senders; const int32_t* g2m_receivers; const int32_t* g2m_row_ptr; const int32_t* g2m_perm;
+  const int32_t* m2g_senders; const int32_t* m2g_receivers; const int32_t* m2g_row_ptr;
+  const int32_t* m2g_perm;           /* NULL: edges receiver-major, three per grid node */
+  const void* g2m_edge_ln; const void* m2g_edge_ln;      /* LayerNorm'ed static edge embeddings [edges, latent] */
+  int32_t attention_kind, max_degree, num_q_tiles, mask_period;
+  const int32_t* step_ptr; const int32_t* keys; const uint32_t* step_mask; const int32_t* work;   /* GC_ATTENTION_GATHER */
+  const int32_t* tile_ptr; const int32_t* tile_kv; const uint32_t* tile_mask;                      /* GC_ATTENTION_TILES */
+  const int32_t* nbr_ptr; const int32_t* nbr_idx;                                                  /* GC_ATTENTION_CSR */
+} gc_denoiser_graph;
+
+/* everything that depends on the noise level (and the weights) only */
+typedef struct gc_sigma_context {
+  const float* table;                /* [num conditional norms, 2 latent], gc_cond_tables */
+  const void* g2m_w1e; const float* g2m_b1;   /* edge block of the edge MLPs' first layer with the edge embedding's */
+  const void* m2g_w1e; const float* m2g_b1;   /* conditional affine folded in (gc_fold_affine_into_linear) */
+  const void* g2m_base; const void* m2g_base; /* e' W1e' + b1 tabulated for this level, or NULL */
+  int64_t g2m_base_rows, m2g_base_rows;
+  const void* m0; const void* m_p;   /* embedded mesh nodes and their product with the receiver block, [mesh_rows, latent] */
+} gc_sigma_context;
+
+typedef struct gc_denoiser_workspace {
+  void* xin; void* a_const;          /* inputs: [grid_rows, KN], [grid_rows, KC] */
+  void* g_h; void* g_y; void* g_h2; void* g_y2; void* g0; void* g_lat; void* g2; void* g_p; void* g_p2; void* g_agg;
+  void* m_h; void* m_y; void* m_p; void* m_agg; void* m_out; void* t_h; void* t_o;   /* [mesh_rows, latent] */
+  float* x;                          /* [mesh_rows, latent] fp32 residual stream of the transformer */
+  void* t_qkv; void* t_f;            /* [mesh_rows, 3 latent], [mesh_rows, ffw_hidden] */
+  void* e_h; void* e_y;              /* [max(g2m_edges, m2g_edges), latent] */
+  float* f_out;                      /* output: raw network prediction [grid_rows, n_out_padded] fp32 */
+  void* branch_stream; void* fork_event; void* join_event;   /* optional parallel branch (cudaStream_t / cudaEvent_t) */
+  int32_t flags; int32_t reserved;
+} gc_denoiser_workspace;
+
+GC_API int gc_denoiser_forward(void* stream, const gc_denoiser_model* model, const gc_denoiser_graph* graph,
+                               const gc_sigma_context* sigma, const gc_denoiser_workspace* workspace);
+/* sizeof of the structs above as compiled into the library (0 model, 1 graph, 2 sigma context, 3 workspace,
+ * 4 gc_mlp2, 5 gc_transformer_layer), for binding-side layout checks */
+GC_API int gc_sizeof_forward_structs(int32_t which);
+
 #ifdef __cplusplus
 }
 #endif

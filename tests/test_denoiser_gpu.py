@@ -271,3 +271,31 @@ def test_benched_workload_1deg_four_members_equal_single_member_runs(cuda_device
         print(f"1deg x 4 members, member {b}: max relative difference to the one-member engine {err:.2e}")
         assert err <= 1e-6
     assert not np.array_equal(got[0], got[3])
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("name,members", [("tiny", 1), ("tiny", 3), ("nano", 2)])
+def test_c_forward_equals_python_sequencing(cuda_device, monkeypatch, name, members, dtype):
+    """gc_denoiser_forward (the whole evaluation sequenced in C++, one call through the C ABI) gives bitwise the result
+    of the same launches issued one by one from Python, eagerly and inside the sampler's CUDA graph (parallel branch)."""
+    from gencast_flax_nnx_b200.engine import DenoiserEngine, SamplerEngine, noise_schedule
+    case = make_case(name)
+    B, G = members, case.graphs.num_grid_nodes
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((B * G, 82)).astype(np.float32)
+    inp = np.concatenate([case.inp_nodes[:, 0] * (1 + 0.1 * b) for b in range(B)])
+    frc = np.concatenate([case.frc_nodes[:, 0]] * B)
+    sigmas = noise_schedule(80.0, 0.03, 3, 7.0)
+    outs = {}
+    for impl in ("py", "c"):
+        monkeypatch.setenv("GENCAST_FORWARD", impl)
+        eng = DenoiserEngine(case.graphs, case.arch, case.params, case.layout, compute_dtype=dtype, members=B)
+        assert eng.forward_impl == impl
+        eng.set_constant_features(inp, frc)
+        eng.set_network_input(x)
+        one = eng.read_output(eng.forward(eng.sigma_context(1.0)))
+        se = SamplerEngine(eng, sigmas)
+        outs[impl] = (one, se.sample(x, use_graph=True).cpu().numpy().copy(), se.sample(x, use_graph=False).cpu().numpy().copy())
+    for a, b in zip(outs["py"], outs["c"]):
+        assert np.isfinite(a).all() and np.array_equal(a, b)
+    assert np.array_equal(outs["c"][1], outs["c"][2])
