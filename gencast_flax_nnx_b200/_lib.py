@@ -141,6 +141,7 @@ SIGNATURES = {
     "gc_denoiser_forward": (c_int32, [c_void_p, POINTER(DenoiserModel), POINTER(DenoiserGraph), POINTER(SigmaContextC),
                                       POINTER(DenoiserWorkspace)]),
     "gc_sizeof_forward_structs": (c_int32, [c_int32]),
+    "gc_sh_synthesis": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32]),
     "gc_fair_crps": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_int64]),
     "gc_column_sums": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "gc_ensemble_accumulate": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),

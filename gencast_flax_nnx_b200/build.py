@@ -17,7 +17,7 @@ CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libgencast_b200.so"
 STAMP_PATH = PKG_DIR / "libgencast_b200.so.stamp"
 
-SOURCES = ["abi.cu", "gemm_tcgen05.cu", "gemm_ffma.cu", "rowwise.cu", "attention_csr.cu", "attention_tc.cu", "attention_gather.cu", "edge_fused.cu", "forward.cu"]
+SOURCES = ["abi.cu", "gemm_tcgen05.cu", "gemm_ffma.cu", "rowwise.cu", "attention_csr.cu", "attention_tc.cu", "attention_gather.cu", "edge_fused.cu", "forward.cu", "spherical.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

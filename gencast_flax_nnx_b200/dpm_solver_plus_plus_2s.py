@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import stacking
-from .engine import SamplerEngine, noise_schedule
+from .engine import SamplerEngine, noise_schedule, stochastic_churn_rate_schedule
 from .xarray_lite import Dataset
 
 
@@ -23,13 +23,13 @@ class Sampler:
                  initial_noise: str = "spherical"):
         self._noise_levels = noise_schedule(max_noise_level, min_noise_level, num_noise_levels, rho)
         self._stochastic_churn = stochastic_churn_rate > 0
-        if self._stochastic_churn:
-            # The reference's loop calls utils.apply_stochastic_churn_arr, which does not exist
-            # (gencast/dpm_solver_plus_plus_2s.py:131 vs gencast/samplers_utils.py:434); both of its
-            # drivers pass 0.0 (training/train.py:167, training/evaluation.py:69).
-            raise NotImplementedError("stochastic churn is not runnable in the reference either; pass "
-                                      "stochastic_churn_rate=0.0")
-        self._churn = (churn_min_noise_level, churn_max_noise_level, noise_level_inflation_factor)
+        # The reference's loop calls utils.apply_stochastic_churn_arr, which it does not define
+        # (gencast/dpm_solver_plus_plus_2s.py:131 vs gencast/samplers_utils.py:434), and both of its drivers pass
+        # 0.0 (training/train.py:167, training/evaluation.py:69).  Here churn runs with the semantics of the
+        # documented apply_stochastic_churn (samplers_utils.py:434-452) on the device state.
+        self._per_step_churn_rates = stochastic_churn_rate_schedule(self._noise_levels, stochastic_churn_rate,
+                                                                    churn_min_noise_level, churn_max_noise_level)
+        self._noise_level_inflation_factor = noise_level_inflation_factor
         self._denoiser = denoiser
         self.sigma_data = 1.0
         self._evaluate_discarded_call = evaluate_discarded_call
@@ -46,7 +46,9 @@ class Sampler:
 
     def sampler_engine(self) -> SamplerEngine:
         if self._engine is None:
-            self._engine = SamplerEngine(self._denoiser.engine, self._noise_levels, self._evaluate_discarded_call)
+            self._engine = SamplerEngine(self._denoiser.engine, self._noise_levels, self._evaluate_discarded_call,
+                                         churn_rates=self._per_step_churn_rates if self._stochastic_churn else None,
+                                         noise_level_inflation_factor=self._noise_level_inflation_factor)
         return self._engine
 
     def __call__(self, inputs: Dataset, targets_template: Dataset, forcings: Optional[Dataset] = None,
@@ -97,4 +99,25 @@ class Sampler:
                     noise = self._noise_gen.sample_nodes(engine.n_out, members=batch, generator=gen)
                 else:
                     noise = torch.randn(batch * engine.G, engine.n_out, generator=gen, device=engine.device)
-            return se.sample(noise, use_graph=self._use_graph)
+            churn_noise = None
+            if se.num_churn_steps > 0:
+                # one fresh unit-variance draw per churned step, like the reference's spherical_white_noise_like(x, rngs)
+                g2 = self._churn_generator(key, engine.device)
+                if self._initial_noise == "spherical":
+                    if self._noise_gen is None:
+                        from .spherical_noise import SphericalNoise
+                        self._noise_gen = SphericalNoise(targets_template.coords["lat"], targets_template.coords["lon"],
+                                                         engine.device)
+                    draws = [self._noise_gen.sample_nodes(engine.n_out, members=batch, generator=g2)
+                             for _ in range(se.num_churn_steps)]
+                else:
+                    draws = [torch.randn(batch * engine.G, engine.n_out, generator=g2, device=engine.device)
+                             for _ in range(se.num_churn_steps)]
+                churn_noise = torch.stack(draws)
+            return se.sample(noise, use_graph=self._use_graph, churn_noise=churn_noise)
+
+    @staticmethod
+    def _churn_generator(key: int, device) -> torch.Generator:
+        g = torch.Generator(device=device)
+        g.manual_seed((int(key) * 0x9E3779B1 + 1) & 0x7FFFFFFFFFFFFFFF)
+        return g

@@ -719,6 +719,16 @@ def noise_schedule(max_noise_level: float, min_noise_level: float, num_noise_lev
     return np.append(levels, 0.0)
 
 
+def stochastic_churn_rate_schedule(noise_levels, stochastic_churn_rate: float = 0.0, churn_min_noise_level: float = 0.05,
+                                   churn_max_noise_level: float = 50.0) -> np.ndarray:
+    """Churn rate of every solver step (reference: gencast/samplers_utils.py:414-431): rate / steps, clamped so the
+    variance grows by at most a factor 2, for the levels inside [min, max]."""
+    noise_levels = np.asarray(noise_levels, np.float64)
+    n = len(noise_levels) - 1
+    per_step = min(stochastic_churn_rate / n, math.sqrt(2.0) - 1.0)
+    return ((churn_min_noise_level <= noise_levels[:-1]) & (noise_levels[:-1] <= churn_max_noise_level)) * per_step
+
+
 def _c_in(s):
     return (s * s + 1.0) ** -0.5       # gencast/dpm_solver_plus_plus_2s.py:181-182 (sigma_data = 1)
 
@@ -742,14 +752,29 @@ class SamplerEngine:
     network evaluation for like-for-like timing (40 instead of 39 evaluations).
     """
 
-    def __init__(self, engine: DenoiserEngine, sigmas: Sequence[float], evaluate_discarded_call: bool = True):
+    def __init__(self, engine: DenoiserEngine, sigmas: Sequence[float], evaluate_discarded_call: bool = True,
+                 churn_rates: Optional[Sequence[float]] = None, noise_level_inflation_factor: float = 1.0):
+        """churn_rates: per-step stochastic churn (stochastic_churn_rate_schedule; None / zeros = deterministic sampler).
+        A churned step first moves the state from sigma_i to sigma_i (1 + rate) with fresh unit-variance noise scaled by
+        sqrt(sigma'^2 - sigma_i^2) * inflation (gencast/samplers_utils.py:434-452, dpm...2s.py:127-137) and then runs
+        the 2S update from sigma'; the noise of the k-th churned step is `churn_noise[k]` of sample()."""
         self.engine = e = engine
         self.sigmas = [float(s) for s in sigmas]
         self.evaluate_discarded_call = evaluate_discarded_call
         plan: List[Tuple[float, str, Tuple[float, float, float, float]]] = []
         n = len(self.sigmas) - 1
+        rates = [0.0] * n if churn_rates is None else [float(r) for r in churn_rates]
+        if len(rates) != n:
+            raise ValueError("churn_rates must have one entry per solver step")
+        self.num_churn_steps = sum(1 for r in rates if r > 0)
         for i in range(n):
             s, s_next = self.sigmas[i], self.sigmas[i + 1]
+            if rates[i] > 0:
+                s_new = s * (1.0 + rates[i])
+                extra = math.sqrt(max(s_new * s_new - s * s, 0.0)) * noise_level_inflation_factor
+                # x += extra * noise, next network input c_in(s_new) x: gc_dpm_update with (c_out, c_skip, a) = (extra, 1, 0)
+                plan.append((s_new, "churn", (extra, 1.0, 0.0, _c_in(max(s_new, 1e-6)))))
+                s = s_new
             s_mid = math.sqrt(s * s_next)
             s_safe, mid_safe = max(s, 1e-6), max(s_mid, 1e-6)
             if s_next == 0.0:
@@ -763,7 +788,7 @@ class SamplerEngine:
                 plan.append((s_safe, "first", (_c_out(s_safe), _c_skip(s_safe), a, _c_in(mid_safe))))
                 plan.append((mid_safe, "second", (_c_out(mid_safe), _c_skip(mid_safe), b, _c_in(nxt))))
         self.plan = plan
-        self.ctx = [e.sigma_context(p[0]) for p in plan]
+        self.ctx = [None if p[1] == "churn" else e.sigma_context(p[0]) for p in plan]
         sched = np.asarray([p[2] for p in plan], np.float32)
         self.sched = torch.from_numpy(sched).to(e.device)
         self.init_scale = torch.tensor([self.sigmas[0], self.sigmas[0] * _c_in(self.sigmas[0])], dtype=torch.float32,
@@ -773,19 +798,20 @@ class SamplerEngine:
         self.x = torch.zeros(G, C, dtype=torch.float32, device=e.device)
         self.x_mid = torch.zeros(G, C, dtype=torch.float32, device=e.device)
         self.result = torch.zeros(G, C, dtype=torch.float32, device=e.device)
+        self.churn_noise = torch.zeros(max(self.num_churn_steps, 1), G, C, dtype=torch.float32, device=e.device)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._branch = torch.cuda.Stream(device=e.device)      # parallel graph branch for the grid-side work
         torch.cuda.synchronize(e.device)
 
     @property
     def num_network_evaluations(self) -> int:
-        return len(self.plan)
+        return sum(1 for p in self.plan if p[1] != "churn")
 
     @property
     def launches_per_step(self) -> int:
         # 2 initial scalings + per evaluation (forward + update); the discarded call has no update
         n_disc = sum(1 for p in self.plan if p[1] == "discard")
-        return 2 + len(self.plan) * (self.engine.launches_per_forward + 1) - n_disc
+        return 2 + self.num_network_evaluations * (self.engine.launches_per_forward + 1) - n_disc + self.num_churn_steps
 
     def _enqueue(self, branch: bool = False):
         e = self.engine
@@ -794,7 +820,12 @@ class SamplerEngine:
         # x0 = sigma_0 * noise (:78); first network input = c_in(sigma_0) * x0
         ops.cast_pad(self.noise, self.x, scale=self.init_scale[0:1])
         ops.cast_pad(self.noise, e.xin[:, :C], scale=self.init_scale[1:2])
+        k_churn = 0
         for j, (sigma, kind, _) in enumerate(self.plan):
+            if kind == "churn":
+                ops.dpm_update(self.churn_noise[k_churn], self.x, self.x, self.sched[j], self.x, e.xin, C)
+                k_churn += 1
+                continue
             f = e.forward(self.ctx[j], bs)
             if kind == "first":
                 last = j + 1 == len(self.plan) or self.plan[j + 1][1] == "discard"
@@ -804,16 +835,23 @@ class SamplerEngine:
                 ops.dpm_update(f, self.x_mid, self.x, self.sched[j], self.x, e.xin, C)
             # "discard": evaluated, result unused (reference :148-153)
 
-    def sample(self, noise: Optional[torch.Tensor] = None, use_graph: bool = True) -> torch.Tensor:
+    def sample(self, noise: Optional[torch.Tensor] = None, use_graph: bool = True,
+               churn_noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Runs one 12 h sampling step; returns the device tensor [G, n_out] fp32 (valid until the next call).
 
         `noise` is the unit-variance initial noise in [grid node, channel] layout
-        (device or host); if None, self.noise is used as already filled.
+        (device or host); if None, self.noise is used as already filled.  `churn_noise`
+        ([num_churn_steps, G, n_out], device) are the unit-variance draws of the churned steps.
         """
         e = self.engine
         with torch.cuda.device(e.device):
             if noise is not None:
                 self.noise.copy_(e._to_device_f32("noise", [noise]), non_blocking=True)
+            if self.num_churn_steps > 0:
+                if churn_noise is None:
+                    raise ValueError(f"this sampler has {self.num_churn_steps} churned steps: pass churn_noise")
+                self.churn_noise.copy_(torch.as_tensor(churn_noise, device=e.device).reshape(self.churn_noise.shape),
+                                       non_blocking=True)
             if not use_graph:
                 self._enqueue()
                 return self.result

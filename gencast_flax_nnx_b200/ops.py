@@ -337,6 +337,23 @@ def denoiser_forward(model, graph, sigma, workspace) -> None:
                                        ctypes.byref(workspace)), "gc_denoiser_forward")
 
 
+def sh_synthesis(coef: torch.Tensor, table: torch.Tensor, spec: torch.Tensor, out: torch.Tensor, members: int,
+                 channels: int, n_lat: int, n_lon: int) -> torch.Tensor:
+    """Spherical-harmonic synthesis of random coefficients into [members * n_lat * n_lon, channels] noise (gc_sh_synthesis)."""
+    lib = _lib.load()
+    L = table.shape[0]
+    for t in (coef, table, spec, out):
+        if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+            raise TypeError("sh_synthesis: contiguous fp32 CUDA tensors expected")
+    if coef.shape != (2, L, members * channels, L) or table.shape != (L, L, n_lat):
+        raise ValueError("sh_synthesis: coef must be [2, L, members * channels, L] and table [L, L, n_lat]")
+    if spec.numel() < members * n_lat * channels * L * 2 or out.shape != (members * n_lat * n_lon, channels):
+        raise ValueError("sh_synthesis: scratch / output size")
+    _lib.check(lib.gc_sh_synthesis(_stream(), coef.data_ptr(), table.data_ptr(), spec.data_ptr(), out.data_ptr(), L, members,
+                                   channels, n_lat, n_lon), "gc_sh_synthesis")
+    return out
+
+
 def fair_crps(members: torch.Tensor, truth: torch.Tensor, weights: Optional[torch.Tensor], channels: int) -> torch.Tensor:
     """members [M, n] fp32, truth [n], weights [n / channels] or None -> weighted fair CRPS per point, [n] fp32."""
     lib = _lib.load()

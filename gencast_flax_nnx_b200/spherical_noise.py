@@ -1,4 +1,5 @@
-"""Isotropic white noise on the sphere for the sampler's initial state.
+"""Isotropic white noise on the sphere for the sampler's initial state and its stochastic churn
+(SURVEY.md §8f item 1).
 
 The reference draws its noise in spherical-harmonic space (gencast/samplers_utils.py:250-346):
 total wavenumbers l = 0 .. n_lon/2 - 1 carry equal power 1/(n_lon/2), split evenly over the 2l+1
@@ -6,13 +7,14 @@ real harmonics of each l, and the field is synthesised on the lat/lon grid with 
 spherical harmonics, so that every grid point has unit marginal variance and the field is
 rotation invariant (in particular single-valued at the poles, unlike white noise per grid cell).
 
-This module restates that construction: geodesy-normalised associated Legendre functions by the
-standard stable recurrence (float64, host, once), then per draw a Legendre synthesis (one batched
-matmul per zonal wavenumber m) and an inverse real FFT along longitude.  It is set-up work of a
-sampling step, not part of the 40-evaluation hot loop; the two transforms are torch library calls
-(cuBLAS / cuFFT), not hand-written kernels.  dinosaur is not installable here, so agreement with
-its exact coefficient ordering / random stream is unpinned; the statistical contract (zero mean, unit
-variance at every latitude, flat spectrum, isotropy) is tested.
+This module restates that construction on the GPU: geodesy-normalised associated Legendre functions
+by the standard stable recurrence (float64, host, once per grid), then per draw Gaussian coefficients
+(torch's device generator) and gc_sh_synthesis, the library's hand-written Legendre + longitude
+synthesis, which writes the sampler's [member * node, channel] state layout directly.  There is no
+CPU path; the float64 host restatement used by the tests is oracle/spherical_noise_oracle.py.
+dinosaur is not installable here, so agreement with its exact coefficient ordering / random stream is
+unpinned; what is tested is the synthesis against the float64 restatement on the same
+coefficients and the statistical contract (zero mean, unit variance at every latitude, isotropy).
 """
 from __future__ import annotations
 
@@ -21,6 +23,8 @@ from typing import Optional
 
 import numpy as np
 import torch
+
+from . import ops
 
 
 def legendre_table(n_wavenumbers: int, sin_lat: np.ndarray) -> np.ndarray:
@@ -46,32 +50,47 @@ def legendre_table(n_wavenumbers: int, sin_lat: np.ndarray) -> np.ndarray:
     return out
 
 
+def amplitude_table(grid_lat, n_lon: int) -> np.ndarray:
+    """table[m, l, lat] = Pbar[m, l, lat] * sqrt(power_l / (2 l + 1)) with the flat spectrum power_l = 1 / (n_lon / 2)
+    of the reference (gencast/samplers_utils.py:316-322, :336-344), float64."""
+    L = max(1, n_lon // 2)
+    table = legendre_table(L, np.sin(np.deg2rad(np.asarray(grid_lat, np.float64))))
+    amp = np.sqrt((1.0 / L) / (2.0 * np.arange(L) + 1.0))
+    return table * amp[None, :, None]
+
+
 class SphericalNoise:
-    """Unit-variance isotropic white noise fields on an equiangular lat/lon grid (poles included)."""
+    """Unit-variance isotropic white noise fields on an equiangular lat/lon grid (poles included), on the GPU."""
 
     def __init__(self, grid_lat, grid_lon, device=None):
-        lat = np.asarray(grid_lat, np.float64)
-        self.n_lat, self.n_lon = len(lat), len(grid_lon)
+        self.device = torch.device(device if device is not None else "cuda:0")
+        if self.device.type != "cuda":
+            raise RuntimeError("SphericalNoise runs on a CUDA device (gc_sh_synthesis); the float64 host restatement "
+                               "for tests is oracle/spherical_noise_oracle.py")
+        self.n_lat, self.n_lon = len(grid_lat), len(grid_lon)
         self.L = max(1, self.n_lon // 2)                     # gencast/samplers_utils.py:336
-        self.device = torch.device(device) if device is not None else torch.device("cpu")
-        table = legendre_table(self.L, np.sin(np.deg2rad(lat)))
-        # per-l amplitude: power 1/L per total wavenumber over 2l+1 harmonics (samplers_utils.py:316-322)
-        amp = np.sqrt((1.0 / self.L) / (2.0 * np.arange(self.L) + 1.0))
-        self.table = torch.from_numpy((table * amp[None, :, None]).astype(np.float32)).to(self.device)   # [m, l, lat]
+        self.table = torch.from_numpy(amplitude_table(grid_lat, self.n_lon).astype(np.float32)).to(self.device)   # [m, l, lat]
+        self._spec = None
+
+    def draw_coefficients(self, n_fields: int, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        """[2 (cos | sin), m, field, l] standard normal coefficients (entries with l < m are not used)."""
+        return torch.randn(2, self.L, n_fields, self.L, generator=generator, device=self.device)
+
+    def synthesize(self, coef: torch.Tensor, channels: int, members: int = 1) -> torch.Tensor:
+        """Coefficients [2, L, members * channels, L] -> [members * n_lat * n_lon, channels] fp32 (the sampler's state
+        layout: node index = lat * n_lon + lon, member-major blocks)."""
+        need = members * self.n_lat * channels * self.L * 2
+        if self._spec is None or self._spec.numel() < need:
+            self._spec = torch.empty(need, dtype=torch.float32, device=self.device)
+        out = torch.empty(members * self.n_lat * self.n_lon, channels, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            return ops.sh_synthesis(coef, self.table, self._spec, out, members, channels, self.n_lat, self.n_lon)
+
+    def sample_nodes(self, channels: int, members: int = 1, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        """[members * n_lat * n_lon, channels] unit-variance noise."""
+        return self.synthesize(self.draw_coefficients(members * channels, generator), channels, members)
 
     def sample(self, n_fields: int, generator: Optional[torch.Generator] = None) -> torch.Tensor:
         """[n_fields, n_lat, n_lon] fp32 on the device."""
-        L, n = self.L, self.n_lon
-        coef = torch.randn(2, L, n_fields, L, generator=generator, device=self.device)     # (cos|sin, m, field, l)
-        # Legendre synthesis per zonal wavenumber: [m, field, l] @ [m, l, lat] -> [m, field, lat]
-        a = torch.bmm(coef[0], self.table)
-        b = torch.bmm(coef[1], self.table)
-        spec = torch.zeros(n_fields, self.n_lat, n // 2 + 1, dtype=torch.complex64, device=self.device)
-        spec[:, :, :L] = torch.complex(a, -b).permute(1, 2, 0) * (0.5 * n)
-        spec[:, :, 0] = torch.complex(a[0], torch.zeros_like(a[0])) * float(n)
-        return torch.fft.irfft(spec, n=n, dim=-1)
-
-    def sample_nodes(self, channels: int, members: int = 1, generator: Optional[torch.Generator] = None) -> torch.Tensor:
-        """[members * n_lat * n_lon, channels]: the sampler state layout (node index = lat * n_lon + lon)."""
-        f = self.sample(members * channels, generator).reshape(members, channels, self.n_lat * self.n_lon)
-        return f.permute(0, 2, 1).reshape(members * self.n_lat * self.n_lon, channels).contiguous()
+        nodes = self.sample_nodes(n_fields, 1, generator)
+        return nodes.reshape(self.n_lat, self.n_lon, n_fields).permute(2, 0, 1).contiguous()

@@ -281,6 +281,21 @@ GC_API int gc_edge_mlp_sum3(void* stream, const void* base, int64_t ld_base, int
                             int32_t cols);
 
 /*
+ * Inverse real spherical-harmonic transform of random coefficients -> isotropic white noise fields in the sampler's
+ * state layout.  Replaces dinosaur's RealSphericalHarmonics.to_nodal as called by the reference's noise generator
+ * (gencast/samplers_utils.py:99-118, :250-346; the per-l amplitudes of :316-322 are folded into `table`):
+ *   out[(member * n_lat + lat) * n_lon + lon, ch] =
+ *       sum_m sum_{l >= m} table[m, l, lat] * ( coef[0, m, f, l] cos(2 pi m lon / n_lon) + coef[1, m, f, l] sin(...) ),
+ *   f = member * channels + ch.
+ * coef: [2, wavenumbers, members * channels, wavenumbers] fp32 (cos | sin coefficients; entries with l < m and the
+ * m = 0 sine row are ignored); table: [wavenumbers (m), wavenumbers (l), n_lat] fp32; spec: scratch
+ * [members * n_lat * channels * wavenumbers * 2] fp32; out: [members * n_lat * n_lon, channels] fp32.
+ * 2 * wavenumbers <= n_lon; channels * wavenumbers * 8 bytes must fit shared memory.
+ */
+GC_API int gc_sh_synthesis(void* stream, const float* coef, const float* table, float* spec, float* out,
+                           int32_t wavenumbers, int32_t members, int32_t channels, int32_t n_lat, int32_t n_lon);
+
+/*
  * Fair CRPS of an M-member ensemble per grid point and channel (no reference implementation
  * exists; defined in DESIGN.md / parallel.py):
  *   crps[i] = mean_m |x_m[i] - y[i]|  -  sum_{j<k} |x_j[i] - x_k[i]| / (M (M - 1))

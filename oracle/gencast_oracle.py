@@ -377,12 +377,34 @@ def noise_schedule(max_noise_level=80.0, min_noise_level=0.03, num_noise_levels=
     return np.append(levels, 0.0)
 
 
+def stochastic_churn_rate_schedule(noise_levels, stochastic_churn_rate=0.0, churn_min_noise_level=0.05,
+                                   churn_max_noise_level=50.0) -> np.ndarray:
+    """Per-step churn rates (reference: gencast/samplers_utils.py:414-431)."""
+    noise_levels = np.asarray(noise_levels, np.float64)
+    n = len(noise_levels) - 1
+    per_step = min(stochastic_churn_rate / n, np.sqrt(2) - 1)
+    return ((churn_min_noise_level <= noise_levels[:-1]) & (noise_levels[:-1] <= churn_max_noise_level)) * per_step
+
+
+def apply_stochastic_churn(x: Mapping[str, torch.Tensor], noise_level: float, churn_rate: float, inflation: float,
+                           unit_noise: Mapping[str, torch.Tensor]):
+    """x at a higher noise level, and that level (reference: gencast/samplers_utils.py:434-452; `unit_noise` stands for
+    its spherical_white_noise_like draw)."""
+    new_level = noise_level * (1.0 + churn_rate)
+    extra = math.sqrt(max(new_level ** 2 - noise_level ** 2, 0.0)) * inflation
+    return {k: v + unit_noise[k].to(v.dtype) * extra for k, v in x.items()}, new_level
+
+
 def dpm_solver_2s(p, g, arch, inputs_stacked, forcings, init_x: Mapping[str, torch.Tensor],
                   sigmas: Sequence[float], dtype, num_steps: Optional[int] = None,
-                  trace: Optional[list] = None, network_fn=None):
+                  trace: Optional[list] = None, network_fn=None, churn_rates: Optional[Sequence[float]] = None,
+                  inflation: float = 1.0, churn_noise: Optional[Sequence[Mapping[str, torch.Tensor]]] = None):
     """Deterministic DPM-Solver++ 2S loop (stochastic churn = 0).
 
-    Reference: gencast/dpm_solver_plus_plus_2s.py:120-158.  init_x already holds
+    Reference: gencast/dpm_solver_plus_plus_2s.py:120-158.  With `churn_rates` (per step, :38-43) the state is first
+    moved to a higher noise level with fresh noise (:127-137; the reference calls an `_arr` variant of
+    apply_stochastic_churn that it does not define -- the documented function, samplers_utils.py:434-452, is what is
+    restated); `churn_noise[k]` is the unit-variance draw of the k-th churned step.  init_x already holds
     noise * sigmas[0] (:78).  sigma is clamped to >= 1e-6 before each denoiser
     call (:85).  On the last iteration (sigma_next == 0) the reference still
     evaluates the second denoiser call and discards it (:148-153); it is skipped
@@ -395,8 +417,12 @@ def dpm_solver_2s(p, g, arch, inputs_stacked, forcings, init_x: Mapping[str, tor
         s_safe = max(float(s), 1e-6)
         return preconditioned_denoiser(p, g, arch, inputs_stacked, forcings, state,
                                        torch.full((B,), s_safe, dtype=dtype), dtype, network_fn)
+    k_churn = 0
     for i in range(n):
         sigma, sigma_next = float(sigmas[i]), float(sigmas[i + 1])
+        if churn_rates is not None and churn_rates[i] > 0:
+            x, sigma = apply_stochastic_churn(x, sigma, float(churn_rates[i]), inflation, churn_noise[k_churn])
+            k_churn += 1
         sigma_mid = math.sqrt(sigma * sigma_next)
         den = D(x, sigma)
         if sigma_next == 0:

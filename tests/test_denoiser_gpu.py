@@ -299,3 +299,40 @@ def test_c_forward_equals_python_sequencing(cuda_device, monkeypatch, name, memb
     for a, b in zip(outs["py"], outs["c"]):
         assert np.isfinite(a).all() and np.array_equal(a, b)
     assert np.array_equal(outs["c"][1], outs["c"][2])
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_sampler_with_stochastic_churn_matches_oracle(cuda_device, dtype):
+    """DPM-Solver++ 2S with stochastic churn (gencast/samplers_utils.py:414-452, dpm...2s.py:127-137): churned steps
+    move the state to sigma (1 + rate) with fresh noise before the 2S update; same noises on both sides."""
+    from gencast_flax_nnx_b200.engine import SamplerEngine, noise_schedule, stochastic_churn_rate_schedule
+    from oracle import gencast_oracle as o
+    case = make_case("tiny")
+    eng = _engine(case, dtype)
+    sigmas = noise_schedule(80.0, 0.03, 4, 7.0)
+    rates = stochastic_churn_rate_schedule(sigmas, 2.5, 0.75, float("inf"))
+    np.testing.assert_allclose(rates, o.stochastic_churn_rate_schedule(sigmas, 2.5, 0.75, float("inf")))
+    assert 0 < (rates > 0).sum() < len(rates)                       # some steps churn, the low-noise ones do not
+    eng.set_constant_features(case.inp_nodes[:, 0], case.frc_nodes[:, 0])
+    rng = np.random.default_rng(13)
+    noise = rng.standard_normal((eng.G, eng.n_out)).astype(np.float32)
+    se = SamplerEngine(eng, sigmas, churn_rates=rates, noise_level_inflation_factor=1.05)
+    cn = rng.standard_normal((se.num_churn_steps, eng.G, eng.n_out)).astype(np.float32)
+    got = se.sample(noise, use_graph=True, churn_noise=torch.from_numpy(cn)).cpu().numpy().copy()
+    eager = se.sample(noise, use_graph=False, churn_noise=torch.from_numpy(cn)).cpu().numpy().copy()
+    assert np.array_equal(got, eager)
+    with pytest.raises(ValueError):
+        se.sample(noise)
+    dt = torch.float64
+    init = case.split_targets(torch.as_tensor(noise[:, None, :] * sigmas[0]).to(dt))
+    frc = {k: torch.as_tensor(v).to(dt) for k, v in case.frc_vars.items()}
+    cnoise = [case.split_targets(torch.as_tensor(c[:, None, :]).to(dt)) for c in cn]
+    ref = o.dpm_solver_2s(case.params, case.oracle_graph, case.oracle_arch, torch.as_tensor(case.inp_nodes).to(dt), frc, init,
+                          sigmas, dt, churn_rates=rates, inflation=1.05, churn_noise=cnoise)
+    ref = torch.cat([ref[n] for n, _ in case.target_vars], dim=-1)[:, 0].numpy()
+    errs = per_variable_error(case, got, ref)
+    print(f"sampler with churn {dtype}: worst per-variable error {max(errs.values()):.3e}")
+    assert max(errs.values()) <= (2e-3 if dtype == "f32" else 5e-2), errs
+    # and it differs from the deterministic sampler
+    det = SamplerEngine(eng, sigmas).sample(noise, use_graph=False).cpu().numpy()
+    assert np.abs(det - got).max() > 1e-3

@@ -220,9 +220,11 @@ def test_rollout_driver_matches_reference_semantics():
 
 def test_api_errors_without_gpu():
     from gencast_flax_nnx_b200 import dpm_solver_plus_plus_2s as dpm
-    with pytest.raises(NotImplementedError):
-        dpm.Sampler(None, 80.0, 0.03, 20, 7.0, 2.5, 0.75, float("inf"), 1.05)
+    churned = dpm.Sampler(None, 80.0, 0.03, 20, 7.0, 2.5, 0.75, float("inf"), 1.05)
+    assert churned._stochastic_churn and (churned._per_step_churn_rates > 0).sum() == 14      # levels >= 0.75 churn
+    assert np.isclose(churned._per_step_churn_rates.max(), 2.5 / 20)
     s = dpm.Sampler(None, 80.0, 0.03, 20, 7.0, 0.0, 0.75, float("inf"), 1.05)
+    assert not s._stochastic_churn and not s._per_step_churn_rates.any()
     with pytest.raises(ValueError):
         s(None, None, None, rngs=None)
     assert configs.num_outputs(configs.TASK) == 82

@@ -121,6 +121,9 @@ def test_oracle_sampler_matches_reference_sampler_body():
     np.testing.assert_allclose(o.noise_schedule(80.0, 0.03, m.NUM_LEVELS, 7.0), sig, rtol=1e-14)
     np.testing.assert_allclose(noise_schedule(80.0, 0.03, m.NUM_LEVELS, 7.0), sig, rtol=1e-14)
     assert not gold["sampler/churn_rates"].any()                    # churn rate 0 -> no stochastic churn
+    from gencast_flax_nnx_b200.engine import stochastic_churn_rate_schedule
+    for fn in (stochastic_churn_rate_schedule, o.stochastic_churn_rate_schedule):
+        np.testing.assert_allclose(fn(sig, 2.5, 0.75, float("inf")), gold["sampler/churn_schedule_rate2p5"], rtol=1e-14)
     w = torch.as_tensor(gold["sampler/toy_w"])
 
     def net(feats, sigma):

@@ -176,6 +176,9 @@ def run_reference():
     result = sampler(inputs, targets, forcings, rngs=nnx.Rngs(0))
     out["sampler/noise_levels"] = np.asarray(sampler._noise_levels, np.float64)
     out["sampler/churn_rates"] = np.asarray(sampler._per_step_churn_rates, np.float64)
+    # the reference's own churn-rate schedule for a non-zero rate (gencast/samplers_utils.py:414-431)
+    out["sampler/churn_schedule_rate2p5"] = np.asarray(su.stochastic_churn_rate_schedule(
+        sampler._noise_levels, 2.5, 0.75, float("inf")), np.float64)
     out["sampler/toy_w"] = ToyDenoiser.w
     for n in tnames:
         # dims come back in to_array()'s broadcast order (level last); xarray semantics are by name
