@@ -133,6 +133,10 @@ SIGNATURES = {
                               c_void_p, c_int64]),
     "gc_select_columns": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                                     c_int64, c_int64, c_int32]),
+    "gc_normalize_cast": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_int32, c_int64, c_int64]),
+    "gc_unnormalize_residual": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int64,
+                                          c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_int64]),
     "gc_edge_hidden": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                  c_int64, c_int32, c_void_p, c_int64, c_int64, c_int32]),
     "gc_edge_mlp_sum3": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,

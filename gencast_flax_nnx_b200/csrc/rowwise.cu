@@ -567,6 +567,66 @@ __global__ void __launch_bounds__(256) ensemble_accumulate_kernel(const float* _
   }
 }
 
+// dst[r, c] = cast( fill_post( (fill_pre(src[r, c]) - loc[c]) / scale[c] ) ): per-channel input normalisation with NaN
+// cleaning on either side of it, written straight into a (padded) GEMM operand.
+__global__ void __launch_bounds__(256) normalize_cast_kernel(const float* __restrict__ src, int64_t ld_src, int cols,
+                                                             const float* __restrict__ loc, const float* __restrict__ scale,
+                                                             const float* __restrict__ fill_pre, const float* __restrict__ fill_post,
+                                                             void* __restrict__ dst, int dst_dtype, int64_t ld_dst, int64_t rows) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t total = rows * cols;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    float v = __ldg(src + r * ld_src + c);
+    if (fill_pre != nullptr && isnan(v)) v = __ldg(fill_pre + c);          // a NaN fill value keeps the NaN
+    if (loc != nullptr) v = __fsub_rn(v, __ldg(loc + c));
+    if (scale != nullptr) v = __fdiv_rn(v, __ldg(scale + c));
+    if (fill_post != nullptr && isnan(v)) v = __ldg(fill_post + c);
+    if (dst_dtype == GC_BF16) reinterpret_cast<__nv_bfloat16*>(dst)[r * ld_dst + c] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(dst)[r * ld_dst + c] = v;
+  }
+}
+
+// out[r, c] = pred[r, c] * scale[c] (+ loc[c]) (+ window[r, res_col[c]], NaN-filled with res_fill[c]); NaN where one of
+// the listed input columns is NaN.  No FMA contraction: bitwise what the reference's three array operations give in fp32.
+__global__ void __launch_bounds__(256) unnormalize_residual_kernel(const float* __restrict__ pred, int64_t ld_pred, int cols,
+                                                                   const float* __restrict__ scale, const float* __restrict__ loc,
+                                                                   const float* __restrict__ window, int64_t ld_window,
+                                                                   const int32_t* __restrict__ res_col,
+                                                                   const float* __restrict__ res_fill,
+                                                                   const int32_t* __restrict__ nan_cols, int nan_per_col,
+                                                                   float* __restrict__ out, int64_t ldo, int64_t rows) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t total = rows * cols;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    float v = __ldg(pred + r * ld_pred + c);
+    if (scale != nullptr) v = __fmul_rn(v, __ldg(scale + c));
+    if (loc != nullptr) v = __fadd_rn(v, __ldg(loc + c));
+    if (res_col != nullptr) {
+      const int rc = __ldg(res_col + c);
+      if (rc >= 0) {
+        float last = __ldg(window + r * ld_window + rc);
+        if (res_fill != nullptr && isnan(last)) last = __ldg(res_fill + c);
+        v = __fadd_rn(v, last);
+      }
+    }
+    if (nan_cols != nullptr) {
+      for (int k = 0; k < nan_per_col; ++k) {
+        const int nc = __ldg(nan_cols + c * nan_per_col + k);
+        if (nc >= 0 && isnan(__ldg(window + r * ld_window + nc))) v = __int_as_float(0x7fc00000);
+      }
+    }
+    out[r * ldo + c] = v;
+  }
+}
+
 int sm_count() {
   int dev = 0, n = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -690,6 +750,32 @@ int gc_cast_pad(void* stream, const void* src, int32_t src_dtype, int64_t ld_src
   GC_CHECK_CUDA(launch_kernel(cast_pad_kernel, dim3(grid_for(rows * cols_dst, 256 * 4, 8)), dim3(256), 0, st, src, src_dtype,
                               ld_src, cols_src, dst, dst_dtype, ld_dst, cols_dst, scale_dev, rows), "cast_pad_kernel");
   GC_CHECK_LAUNCH("cast_pad_kernel");
+  return GC_OK;
+}
+
+int gc_normalize_cast(void* stream, const float* src, int64_t ld_src, int32_t cols, const float* loc, const float* scale,
+                      const float* fill_pre, const float* fill_post, void* dst, int32_t dst_dtype, int64_t ld_dst, int64_t rows) {
+  GC_REQUIRE(src && dst, "gc_normalize_cast: null buffer");
+  GC_REQUIRE(dtype_ok(dst_dtype) && cols > 0 && ld_src >= cols && ld_dst >= cols, "gc_normalize_cast: bad arguments");
+  if (rows <= 0) return GC_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GC_CHECK_CUDA(launch_kernel(normalize_cast_kernel, dim3(grid_for(rows * cols, 256 * 4, 8)), dim3(256), 0, st, src, ld_src, (int)cols,
+                              loc, scale, fill_pre, fill_post, dst, (int)dst_dtype, ld_dst, rows), "normalize_cast_kernel");
+  return GC_OK;
+}
+
+int gc_unnormalize_residual(void* stream, const float* pred, int64_t ld_pred, int32_t cols, const float* scale, const float* loc,
+                            const float* window, int64_t ld_window, const int32_t* res_col, const float* res_fill,
+                            const int32_t* nan_cols, int32_t nan_per_col, float* out, int64_t ldo, int64_t rows) {
+  GC_REQUIRE(pred && out, "gc_unnormalize_residual: null buffer");
+  GC_REQUIRE(cols > 0 && ld_pred >= cols && ldo >= cols, "gc_unnormalize_residual: bad sizes");
+  GC_REQUIRE((res_col == nullptr && nan_cols == nullptr) || window != nullptr, "gc_unnormalize_residual: window missing");
+  GC_REQUIRE(nan_cols == nullptr || nan_per_col > 0, "gc_unnormalize_residual: nan_per_col");
+  if (rows <= 0) return GC_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GC_CHECK_CUDA(launch_kernel(unnormalize_residual_kernel, dim3(grid_for(rows * cols, 256 * 4, 8)), dim3(256), 0, st, pred, ld_pred,
+                              (int)cols, scale, loc, window, ld_window, res_col, res_fill, nan_cols, (int)nan_per_col, out, ldo, rows),
+                "unnormalize_residual_kernel");
   return GC_OK;
 }
 

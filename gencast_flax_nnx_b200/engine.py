@@ -575,10 +575,21 @@ class DenoiserEngine:
         dev.copy_(pin, non_blocking=True)
         return dev
 
-    def set_constant_features(self, inputs_nodes, forcings_nodes) -> None:
+    def set_constant_features(self, inputs_nodes, forcings_nodes, transform: Optional[Dict[str, torch.Tensor]] = None) -> None:
         """Per-step constants: stacked inputs [members * G, C_in] and forcings [members * G, C_f]
-        (member-major blocks of grid rows; host or device, fp32)."""
+        (member-major blocks of grid rows; host or device, fp32).  `transform` (device fp32 vectors per stacked channel:
+        in_loc, in_scale, in_fill_pre, in_fill_post, frc_loc, frc_scale, frc_fill_pre, frc_fill_post; any may be absent)
+        normalises / NaN-cleans physical-unit device tensors on the way in (gc_normalize_cast: the input side of
+        common/normalization.py:154-155 and gencast/nan_cleaning.py:47-53)."""
         ni, nf = self.layout.num_input_channels, self.layout.num_forcings
+        if transform is not None:
+            with torch.cuda.device(self.device):
+                g = transform.get
+                ops.normalize_cast(inputs_nodes, self.a_const[:, 3:3 + ni], g("in_loc"), g("in_scale"), g("in_fill_pre"), g("in_fill_post"))
+                if nf:
+                    ops.normalize_cast(forcings_nodes, self.a_const[:, 3 + ni:3 + ni + nf], g("frc_loc"), g("frc_scale"),
+                                       g("frc_fill_pre"), g("frc_fill_post"))
+            return
         with torch.cuda.device(self.device):
             cat = self._to_device_f32("const", [inputs_nodes, forcings_nodes])
             if cat.shape[1] != ni + nf:

@@ -265,6 +265,34 @@ def cast_pad(src: torch.Tensor, dst: torch.Tensor, cols_src: Optional[int] = Non
     return dst
 
 
+def normalize_cast(src: torch.Tensor, dst: torch.Tensor, loc=None, scale=None, fill_pre=None, fill_post=None) -> torch.Tensor:
+    """dst[:, c] = cast(fill_post((fill_pre(src[:, c]) - loc[c]) / scale[c])) (gc_normalize_cast); src fp32 [rows, C]."""
+    lib = _lib.load()
+    if src.dtype != torch.float32:
+        raise TypeError("normalize_cast: fp32 source expected")
+    rows, cols = src.shape
+    for v in (loc, scale, fill_pre, fill_post):
+        if v is not None and (v.dtype != torch.float32 or v.numel() != cols):
+            raise ValueError("normalize_cast: per-channel vectors must be fp32 [cols]")
+    _lib.check(lib.gc_normalize_cast(_stream(), src.data_ptr(), _row_major(src, "src"), cols, _p(loc), _p(scale), _p(fill_pre),
+                                     _p(fill_post), dst.data_ptr(), _dt(dst), _row_major(dst, "dst"), rows), "gc_normalize_cast")
+    return dst
+
+
+def unnormalize_residual(pred: torch.Tensor, cols: int, out: torch.Tensor, scale=None, loc=None, window=None, res_col=None,
+                         res_fill=None, nan_cols=None) -> torch.Tensor:
+    """out[:, c] = pred[:, c] * scale[c] + loc[c] + window[:, res_col[c]]; NaN where listed input columns are NaN
+    (gc_unnormalize_residual)."""
+    lib = _lib.load()
+    rows = pred.shape[0]
+    npc = 0 if nan_cols is None else nan_cols.shape[1]
+    _lib.check(lib.gc_unnormalize_residual(_stream(), pred.data_ptr(), _row_major(pred, "pred"), cols, _p(scale), _p(loc),
+                                           _p(window), _row_major(window, "window") if window is not None else 0,
+                                           _p(res_col), _p(res_fill), _p(nan_cols), npc, out.data_ptr(), _row_major(out, "out"),
+                                           rows), "gc_unnormalize_residual")
+    return out
+
+
 def select_columns(sources: Sequence[Optional[torch.Tensor]], table: torch.Tensor, out: torch.Tensor):
     """out[r, j] = sources[table[j] >> 24][r, table[j] & 0xffffff] (fp32 matrices; the rollout's window update)."""
     lib = _lib.load()

@@ -137,6 +137,57 @@ def window_update_table(inputs: Dataset, predictions: Dataset, forcings: Dataset
     return table.astype(np.int32)
 
 
+def _wrapper_transforms(model, inputs: Dataset, targets_template: Dataset, forcings: Dataset):
+    """Unwraps `normalization.InputsAndResiduals` / `nan_cleaning.NaNCleaner` around a GenCast model (in either order,
+    as training/train_helpers.py:160-214 composes them) into per-stacked-channel vectors for gc_normalize_cast /
+    gc_unnormalize_residual.  Returns (gencast model, dict of numpy vectors or None)."""
+    from .nan_cleaning import NaNCleaner
+    from .normalization import InputsAndResiduals
+    chain = []
+    while hasattr(model, "predictor"):
+        chain.append(model)
+        model = model.predictor
+    if not chain:
+        return model, None
+    t = {}
+    normalised = False
+    for w in chain:                                        # outermost first: the order the inputs pass through
+        if isinstance(w, InputsAndResiduals):
+            if normalised:
+                raise ValueError("two InputsAndResiduals wrappers")
+            t.update(w.channel_transforms(inputs, targets_template, forcings))
+            # the residual is added to the inputs AS THIS WRAPPER SEES THEM: cleaned if a NaNCleaner sits outside
+            if "in_fill_pre" in t:
+                fill_in = t["in_fill_pre"]
+                t["res_fill"] = np.where(t["res_col"] >= 0, fill_in[np.maximum(t["res_col"], 0)], np.nan).astype(np.float32)
+            normalised = True
+        elif isinstance(w, NaNCleaner):
+            side = "post" if normalised else "pre"
+            t[f"in_fill_{side}"] = w.channel_fill(inputs)
+            t[f"frc_fill_{side}"] = w.channel_fill(forcings)
+            if w._reintroduce_nans and w._var_to_clean in targets_template and w._var_to_clean in inputs:
+                in_off, off = {}, 0
+                for n in sorted(inputs.keys()):
+                    in_off[n] = off
+                    off += _channel_index(inputs[n])[1].size
+                iv = inputs[w._var_to_clean]
+                i_extra, i_idx = _channel_index(iv)
+                T = iv.sizes["time"]
+                cols = []
+                for n in sorted(targets_template.keys()):
+                    extra, idx = _channel_index(targets_template[n])
+                    if n != w._var_to_clean:
+                        cols.append(np.full((idx.size, T), -1, np.int64))
+                        continue
+                    frames = [np.transpose(np.take(i_idx, [k], axis=i_extra.index("time")), [i_extra.index(d) for d in extra]).reshape(-1)
+                              for k in range(T)]
+                    cols.append(in_off[n] + np.stack(frames, axis=1))
+                t["nan_cols"] = np.concatenate(cols).astype(np.int32)
+        else:
+            raise TypeError(f"device rollout: unsupported predictor wrapper {type(w).__name__}")
+    return model, t
+
+
 def device_chunked_prediction_generator(model, inputs: Dataset, targets_template: Dataset, forcings: Dataset,
                                         verbose: bool = False) -> Iterator[Dataset]:
     """`chunked_prediction_generator` (common/rollout.py:245-376) for a `gencast.GenCast` model with one target
@@ -145,9 +196,17 @@ def device_chunked_prediction_generator(model, inputs: Dataset, targets_template
     the prediction and the forcings (`window_update_table`, gc_select_columns), and only the prediction comes
     back to the host.  Step for step it yields what
     `chunked_prediction_generator(lambda rng, inputs, targets_template, forcings: model.full_sampling(inputs,
-    targets_template, forcings), ...)` yields with the same `model.rngs` state."""
+    targets_template, forcings), ...)` yields with the same `model.rngs` state.
+
+    `model` may be wrapped in `normalization.InputsAndResiduals` and / or `nan_cleaning.NaNCleaner`: the window then holds
+    physical values, gc_normalize_cast normalises / cleans them into the network's operand every step and
+    gc_unnormalize_residual turns the sample back into physical units with the residual connection (and the NaNs put
+    back where asked) before it enters the window -- the reference's wrappers without leaving the device."""
     import torch
     from . import ops
+    outer = model
+    model, tr_np = _wrapper_transforms(outer, inputs, targets_template.isel(time=slice(0, 1)), forcings.isel(time=slice(0, 1)))
+    tr = None
     if model._sampler is None:
         raise ValueError("Sampler config must be specified to run inference.")
     times = np.asarray(targets_template.coords["time"])
@@ -171,9 +230,15 @@ def device_chunked_prediction_generator(model, inputs: Dataset, targets_template
                 window = den.member_major(den.stacker.to_nodes("inputs", inputs, sizes)).clone()      # [B*G, C_in] fp32
                 nxt = torch.empty_like(window)
                 table = torch.from_numpy(window_update_table(inputs, cur_t, cur_f)).to(engine.device)
+                if tr_np is not None:
+                    tr = {k: torch.from_numpy(np.ascontiguousarray(v)).to(engine.device) for k, v in tr_np.items()}
+                    phys = torch.empty(window.shape[0], engine.n_out, dtype=torch.float32, device=engine.device)
             frc = den.member_major(den.stacker.to_nodes("forcings", cur_f, sizes))
-            engine.set_constant_features(window, frc)
+            engine.set_constant_features(window, frc, transform=tr)
             res = sampler.sample_on_device(cur_t, model.rngs.noise())
+            if tr is not None:
+                res = ops.unnormalize_residual(res, engine.n_out, phys, tr.get("out_scale"), tr.get("out_loc"), window,
+                                               tr.get("res_col"), tr.get("res_fill"), tr.get("nan_cols"))
             out = res.reshape(sizes["batch"], engine.G, engine.n_out).permute(1, 0, 2)
             pred = den.stacker.from_nodes(out, cur_t)
             ops.select_columns([window, res, frc], table, nxt)

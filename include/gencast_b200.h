@@ -248,6 +248,32 @@ GC_API int gc_select_columns(void* stream, const float* src0, int64_t ld0, const
                       int64_t rows, int32_t cols_out);
 
 /*
+ * Input side of the reference's predictor wrappers on the device-resident rollout window: per stacked channel c
+ *   dst[r, c] = cast( fill_post_c( ( fill_pre_c(src[r, c]) - loc[c] ) / scale[c] ) ),   fill_x(v) = isnan(v) ? fill_x[c] : v
+ * i.e. normalization.normalize (common/normalization.py:31-50, called at :154-155, :216-217) with NaNCleaner._clean
+ * (gencast/nan_cleaning.py:47-53) on either side of it, written straight into the denoiser's (padded, possibly bf16)
+ * constant-feature operand.  Any of loc / scale / fill_pre / fill_post may be NULL (identity); a NaN fill keeps NaNs.
+ * Exactly rounded fp32 subtract and divide: bitwise what the reference's array arithmetic gives.
+ */
+GC_API int gc_normalize_cast(void* stream, const float* src, int64_t ld_src, int32_t cols, const float* loc,
+                             const float* scale, const float* fill_pre, const float* fill_post, void* dst,
+                             int32_t dst_dtype, int64_t ld_dst, int64_t rows);
+
+/*
+ * Output side: un-normalise the network's prediction, add the last input frame where the variable is also an input
+ * (InputsAndResiduals._unnormalize_prediction_and_add_input, common/normalization.py:114-133) and optionally put NaNs
+ * back where the inputs had them (NaNCleaner._maybe_reintroduce_nans, gencast/nan_cleaning.py:55-64):
+ *   out[r, c] = pred[r, c] * scale[c] (+ loc[c]) (+ fill(window[r, res_col[c]], res_fill[c]) if res_col[c] >= 0);
+ *   out[r, c] = NaN if window[r, nan_cols[c * nan_per_col + k]] is NaN for some k (entries < 0 are skipped).
+ * `window` is the stacked physical input window of the step ([rows, ld_window] fp32).  Separate, exactly rounded fp32
+ * multiply and adds (no contraction).  scale / loc / res_col / res_fill / nan_cols may be NULL.
+ */
+GC_API int gc_unnormalize_residual(void* stream, const float* pred, int64_t ld_pred, int32_t cols, const float* scale,
+                                   const float* loc, const float* window, int64_t ld_window, const int32_t* res_col,
+                                   const float* res_fill, const int32_t* nan_cols, int32_t nan_per_col, float* out,
+                                   int64_t ldo, int64_t rows);
+
+/*
  * Hidden layer of an edge MLP whose edge-feature part is known in advance:
  *   out[e, :] = act( base[e % period, :] + g0[idx0[e], :] + g1[idx1[e], :] )        (bf16 in / out, fp32 sum)
  * The reference's edge update is MLP([e | n_s | n_r]) (common/typed_graph_net.py:134-159, :301-305); its first

@@ -336,3 +336,54 @@ def test_sampler_with_stochastic_churn_matches_oracle(cuda_device, dtype):
     # and it differs from the deterministic sampler
     det = SamplerEngine(eng, sigmas).sample(noise, use_graph=False).cpu().numpy()
     assert np.abs(det - got).max() > 1e-3
+
+
+@pytest.mark.parametrize("order", ["nan_outside", "norm_outside"])
+def test_device_rollout_with_normalization_and_nan_cleaning_equals_host_wrappers(cuda_device, order):
+    """Autoregressive rollout with the window on the GPU around InputsAndResiduals + NaNCleaner (gc_normalize_cast,
+    gc_unnormalize_residual) yields, step for step and bit for bit, what the reference-shaped host wrappers
+    (common/normalization.py:200-238, gencast/nan_cleaning.py:129-156) yield around GenCast.full_sampling."""
+    from gencast_flax_nnx_b200 import configs, gencast, graph, nan_cleaning, normalization, rollout, synthetic
+    from gencast_flax_nnx_b200.rngs import Rngs
+    from gencast_flax_nnx_b200.xarray_lite import DataArray, Dataset
+    case = make_case("tiny")
+    res, arch = configs.named_config("tiny")
+    lat, lon = graph.regular_grid(res)
+    inputs, targets, forcings = synthetic.make_example(lat, lon, batch=2, seed=2, num_target_steps=3)
+    rng = np.random.default_rng(4)
+    var = "sea_surface_temperature"
+    # physical-looking inputs: offset and scale per variable; NaNs over "land" in the cleaned variable (all frames)
+    lev = len(configs.TASK.pressure_levels)
+    stat = lambda lo, hi, v: (DataArray(np.linspace(lo, hi, lev).astype(np.float32), ("level",)) if "level" in inputs[v].dims
+                              else DataArray(np.float32(0.5 * (lo + hi)), ()))
+    std = Dataset({v: stat(2.0, 5.0, v) for v in inputs.keys()})
+    mean = Dataset({v: stat(-1.0, 3.0, v) for v in inputs.keys()})
+    dstd = Dataset({v: DataArray(np.float32(0.5 + 0.1 * i), ()) for i, v in enumerate(sorted(targets.keys()))})
+    phys = {}
+    for v, a in inputs.items():
+        x = a.data * normalization._stat_like(a, std[v]) + normalization._stat_like(a, mean[v])
+        if v == var:
+            x = x.copy()
+            x[..., 3:6, 5:11] = np.nan
+        phys[v] = DataArray(x.astype(np.float32), a.dims)
+    inputs = Dataset(phys, inputs.coords)
+    sc = configs.SamplerConfig(num_noise_levels=3, stochastic_churn_rate=0.0)
+    fill = Dataset({var: DataArray(np.float32(271.0), ())})
+
+    def wrapped():
+        m = gencast.GenCast(configs.TASK, arch, sampler_config=sc, rngs=Rngs(7), params=case.params, compute_dtype="bf16")
+        if order == "nan_outside":
+            w = normalization.InputsAndResiduals(m, std, mean, dstd)
+            return nan_cleaning.NaNCleaner(w, var, fill, reintroduce_nans=True)
+        w = nan_cleaning.NaNCleaner(m, var, Dataset({var: DataArray(np.float32(0.25), ())}), reintroduce_nans=True)
+        return normalization.InputsAndResiduals(w, std, mean, dstd)
+
+    m1 = wrapped()
+    host = rollout.chunked_prediction(lambda rng, inputs, targets_template, forcings: m1.full_sampling(inputs, targets_template, forcings),
+                                      0, inputs, targets, forcings)
+    dev = rollout.device_chunked_prediction(wrapped(), inputs, targets, forcings)
+    for k in host.keys():
+        assert dev[k].dims == host[k].dims
+        np.testing.assert_array_equal(dev[k].data, host[k].data)
+    assert np.isnan(host[var].data[..., 3:6, 5:11]).all() and np.isfinite(host[var].data[..., 0, :]).all()
+    assert np.isfinite(host["2m_temperature"].data).all()
