@@ -76,6 +76,44 @@ def chunked_prediction(predictor_fn: PredictorFn, rng, inputs: Dataset, targets_
     return concat_time(chunks)
 
 
+def chunked_prediction_generator_multiple_runs(predictor_fn: PredictorFn, rngs, inputs: Dataset, targets_template: Dataset,
+                                               forcings, num_samples: int, pmap_devices=None,
+                                               **chunked_prediction_kwargs) -> Iterator[Dataset]:
+    """Ensemble fan-out of the reference (common/rollout.py:78-202): one trajectory per sample, every yielded chunk
+    labelled with its `sample` coordinate; `inputs` / `forcings` may carry a leading 'sample' dim (one initial
+    condition per member) or be shared.  `rngs[i]` seeds sample i.
+
+    Where the reference fans samples out with `pmap` over `pmap_devices` (:109-175), members here are sharded one
+    process per GPU: with `pmap_devices` given (any sequence whose length is the number of GPUs / ranks), this process
+    runs the samples `parallel.member_assignment(num_samples, len(pmap_devices), rank)` assigns to it -- the same
+    divisibility rule as the reference (:110-112) -- and yields only those; without it every sample runs here, in order.
+    """
+    if num_samples is None:
+        num_samples = len(rngs)
+    if pmap_devices is not None:
+        from . import parallel
+        world = len(pmap_devices)
+        if num_samples % world != 0:
+            raise AssertionError("num_samples must be a multiple of len(pmap_devices)")
+        rank, _ = parallel._world(None)
+        samples = parallel.member_assignment(num_samples, world, rank % world)
+    else:
+        samples = range(num_samples)
+    for i in samples:
+        sample_inputs = inputs.isel(sample=i) if "sample" in inputs.sizes else inputs
+        sample_forcings = forcings
+        if sample_forcings is not None and "sample" in sample_forcings.sizes:
+            sample_forcings = sample_forcings.isel(sample=i)
+        if "sample" in sample_inputs.coords:
+            sample_inputs = Dataset(sample_inputs.data_vars, {k: v for k, v in sample_inputs.coords.items() if k != "sample"})
+        for chunk in chunked_prediction_generator(predictor_fn=predictor_fn, rng=rngs[i], inputs=sample_inputs,
+                                                  targets_template=targets_template, forcings=sample_forcings,
+                                                  **chunked_prediction_kwargs):
+            coords = dict(chunk.coords)
+            coords["sample"] = np.asarray(i)
+            yield Dataset(chunk.data_vars, coords)
+
+
 # ----------------------------------------------------------------------------------------------
 # The same rollout with the autoregressive window resident on the GPU
 # ----------------------------------------------------------------------------------------------

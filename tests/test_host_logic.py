@@ -322,3 +322,47 @@ def test_khop_compact_steps_reconstruct_the_pattern():
         for r in range(rows):
             rebuilt[t * 128 + r, k[b[r]]] = True
     np.testing.assert_array_equal(rebuilt, dense)
+
+
+def test_multiple_runs_fan_out_and_packed_writer(tmp_path):
+    """chunked_prediction_generator_multiple_runs (common/rollout.py:78-202): per-sample trajectories labelled with
+    `sample`, per-sample initial conditions, device groups -> member assignment; PackedRolloutWriter / Reader round trip."""
+    from gencast_flax_nnx_b200 import rollout
+    from gencast_flax_nnx_b200.ensemble_writer import PackedRolloutReader, PackedRolloutWriter
+    lat, lon = graph.regular_grid(30.0)
+    inputs, targets, forcings = synthetic.make_example(lat, lon, batch=1, seed=3, num_target_steps=2)
+    S = 4
+    # one initial condition per sample along a leading 'sample' dim
+    inp_s = Dataset({k: DataArray(np.stack([v.data * (1 + s) for s in range(S)]), ("sample",) + tuple(v.dims))
+                     for k, v in inputs.items()}, inputs.coords)
+
+    def predictor(rng, inputs, targets_template, forcings):
+        # prediction = last input frame + rng-dependent offset
+        return Dataset({k: DataArray(inputs[k].isel(time=slice(-1, None)).transpose(*v.dims).data + np.float32(rng % 7), v.dims)
+                        for k, v in targets_template.items()}, targets_template.coords)
+
+    chunks = list(rollout.chunked_prediction_generator_multiple_runs(predictor, list(range(10, 10 + S)), inp_s, targets, forcings, S))
+    assert len(chunks) == S * 2 and [int(c.coords["sample"]) for c in chunks] == [0, 0, 1, 1, 2, 2, 3, 3]
+    assert [c.coords["time"].tolist() for c in chunks[:2]] == [[12], [24]]
+    a, b = chunks[0]["2m_temperature"].data, chunks[2]["2m_temperature"].data
+    assert not np.array_equal(a, b)
+    with pytest.raises(AssertionError):
+        list(rollout.chunked_prediction_generator_multiple_runs(predictor, list(range(3)), inputs, targets, forcings, 3, pmap_devices=[0, 1]))
+    only = list(rollout.chunked_prediction_generator_multiple_runs(predictor, list(range(S)), inputs, targets, forcings, S, pmap_devices=[0, 1]))
+    assert sorted({int(c.coords["sample"]) for c in only}) == [0, 1]            # rank 0 of 2 (no process group): first half
+    # packed writer: [time, member, G, C]
+    tmpl = targets.isel(time=slice(0, 1))
+    path = str(tmp_path / "rollout.bin")
+    w = PackedRolloutWriter(path, tmpl, [12, 24], num_members=S)
+    sizes = dict(tmpl.sizes)
+    for c in chunks:
+        step = [12, 24].index(int(c.coords["time"][0]))
+        nodes, _ = stacking.dataset_to_nodes(Dataset(c.data_vars, {k: v for k, v in c.coords.items() if k != "sample"}), sizes)
+        w.write_step(step, nodes[:, 0], first_member=int(c.coords["sample"]))
+    w.close()
+    r = PackedRolloutReader(path)
+    assert r.shape == (2, S, len(lat) * len(lon), 82)
+    back = r.step(1, slice(2, 3))
+    want = [c for c in chunks if int(c.coords["sample"]) == 2 and int(c.coords["time"][0]) == 24][0]
+    for k in want.keys():
+        np.testing.assert_array_equal(back[k].data, want[k].data)
