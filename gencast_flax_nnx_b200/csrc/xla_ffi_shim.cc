@@ -82,4 +82,109 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(gc_khop_attention_ffi, AttentionImpl,
                                   .Arg<ffi::Buffer<ffi::U32>>().Ret<ffi::Buffer<ffi::BF16>>()
                                   .Attr<int32_t>("heads").Attr<int32_t>("head_dim"),
                               {ffi::Traits::kCmdBufferCompatible});
+// The same attention over per-query-tile compacted key lists (gc_khop_attention_gather).
+static ffi::Error AttentionGatherImpl(cudaStream_t stream, ffi::Buffer<ffi::BF16> qkv, ffi::Buffer<ffi::S32> step_ptr,
+                                      ffi::Buffer<ffi::S32> keys, ffi::Buffer<ffi::U32> mask, ffi::Buffer<ffi::S32> work,
+                                      ffi::Result<ffi::Buffer<ffi::BF16>> out, int32_t heads, int32_t head_dim,
+                                      int32_t mask_period) {
+  return status(gc_khop_attention_gather(stream, qkv.typed_data(), qkv.dimensions()[1], step_ptr.typed_data(), keys.typed_data(),
+                                         mask.typed_data(), work.typed_data(), (int32_t)work.dimensions()[0], mask_period,
+                                         out->typed_data(), out->dimensions()[1], qkv.dimensions()[0], heads, head_dim));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(gc_khop_attention_gather_ffi, AttentionGatherImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>().Arg<ffi::Buffer<ffi::S32>>().Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::U32>>().Arg<ffi::Buffer<ffi::S32>>().Ret<ffi::Buffer<ffi::BF16>>()
+                                  .Attr<int32_t>("heads").Attr<int32_t>("head_dim").Attr<int32_t>("mask_period"),
+                              {ffi::Traits::kCmdBufferCompatible});
+
+// Hidden layer of an edge MLP from its tabulated edge part + two gathered node parts (gc_edge_hidden).
+static ffi::Error EdgeHiddenImpl(cudaStream_t stream, ffi::Buffer<ffi::BF16> base, ffi::Buffer<ffi::BF16> g0, ffi::Buffer<ffi::S32> i0,
+                                 ffi::Buffer<ffi::BF16> g1, ffi::Buffer<ffi::S32> i1, ffi::Result<ffi::Buffer<ffi::BF16>> out,
+                                 int32_t act) {
+  const int32_t cols = (int32_t)out->dimensions()[1];
+  return status(gc_edge_hidden(stream, base.typed_data(), cols, base.dimensions()[0], g0.typed_data(), i0.typed_data(), cols,
+                               g1.typed_data(), i1.typed_data(), cols, act, out->typed_data(), cols, out->dimensions()[0], cols));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(gc_edge_hidden_ffi, EdgeHiddenImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>().Arg<ffi::Buffer<ffi::BF16>>().Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>().Arg<ffi::Buffer<ffi::S32>>().Ret<ffi::Buffer<ffi::BF16>>()
+                                  .Attr<int32_t>("act"),
+                              {ffi::Traits::kCmdBufferCompatible});
+
+// Fused degree-3 edge update + aggregation (gc_edge_mlp_sum3): the mesh2grid decoder's edge path in one call.
+static ffi::Error EdgeMlpSum3Impl(cudaStream_t stream, ffi::Buffer<ffi::BF16> base, ffi::Buffer<ffi::BF16> gs, ffi::Buffer<ffi::S32> is,
+                                  ffi::Buffer<ffi::BF16> gr, ffi::Buffer<ffi::S32> ir, ffi::Buffer<ffi::BF16> w2,
+                                  ffi::Buffer<ffi::F32> b2, ffi::Buffer<ffi::F32> scale_offset, ffi::Result<ffi::AnyBuffer> out,
+                                  int32_t act) {
+  const int32_t cols = (int32_t)out->dimensions()[1];
+  return status(gc_edge_mlp_sum3(stream, base.typed_data(), cols, base.dimensions()[0], gs.typed_data(), is.typed_data(), cols,
+                                 gr.typed_data(), ir.typed_data(), cols, act, w2.typed_data(), cols, b2.typed_data(),
+                                 scale_offset.typed_data(), 1, out->untyped_data(), dtype_code(out->element_type()), cols,
+                                 out->dimensions()[0], cols));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(gc_edge_mlp_sum3_ffi, EdgeMlpSum3Impl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>().Arg<ffi::Buffer<ffi::BF16>>().Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>().Arg<ffi::Buffer<ffi::S32>>().Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::Buffer<ffi::F32>>().Ret<ffi::AnyBuffer>()
+                                  .Attr<int32_t>("act"),
+                              {ffi::Traits::kCmdBufferCompatible});
+
+// Preconditioning + DPM-Solver++ 2S update (gc_dpm_update): x_out and the next call's c_in-scaled input.
+static ffi::Error DpmUpdateImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> f, ffi::Buffer<ffi::F32> x_cur, ffi::Buffer<ffi::F32> x_base,
+                                ffi::Buffer<ffi::F32> sched, ffi::Result<ffi::Buffer<ffi::F32>> x_out,
+                                ffi::Result<ffi::AnyBuffer> xin_out) {
+  const int64_t rows = x_cur.dimensions()[0];
+  const int32_t cols = (int32_t)x_cur.dimensions()[1];
+  return status(gc_dpm_update(stream, f.typed_data(), f.dimensions()[1], x_cur.typed_data(), x_base.typed_data(), cols,
+                              sched.typed_data(), x_out->typed_data(), xin_out->untyped_data(), dtype_code(xin_out->element_type()),
+                              xin_out->dimensions()[1], rows, cols));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(gc_dpm_update_ffi, DpmUpdateImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>().Ret<ffi::AnyBuffer>(),
+                              {ffi::Traits::kCmdBufferCompatible});
+
+// Noise-level encoder + all conditional linears (gc_cond_tables).
+static ffi::Error CondTablesImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> sigma, ffi::Buffer<ffi::F32> w0, ffi::Buffer<ffi::F32> b0,
+                                 ffi::Buffer<ffi::F32> w1, ffi::Buffer<ffi::F32> b1, ffi::Buffer<ffi::F32> wc, ffi::Buffer<ffi::F32> bc,
+                                 ffi::Result<ffi::Buffer<ffi::F32>> table, float base_period) {
+  return status(gc_cond_tables(stream, sigma.typed_data(), (int32_t)sigma.dimensions()[0], w0.typed_data(), b0.typed_data(),
+                               w1.typed_data(), b1.typed_data(), base_period, (int32_t)(w0.dimensions()[0] / 2), wc.typed_data(),
+                               bc.typed_data(), (int32_t)wc.dimensions()[0], (int32_t)(wc.dimensions()[2] / 2), table->typed_data()));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(gc_cond_tables_ffi, CondTablesImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>().Attr<float>("base_period"),
+                              {ffi::Traits::kCmdBufferCompatible});
+
+// Whole network evaluation (gc_denoiser_forward).  The descriptors hold device pointers, so the host registers them
+// once per (model, graph, noise level) with gc_ffi_register_forward() below -- weights and graph tables are constants
+// of the jitted function, exactly like the reference's TypedGraph templates closed over at trace time
+// (gencast/denoiser.py:343-360) -- and the custom call carries only the per-call operands: the c_in-scaled noisy
+// targets, the per-step constant features and the output.  `handle` is the value gc_ffi_register_forward returned.
+struct ForwardBundle { gc_denoiser_model model; gc_denoiser_graph graph; gc_sigma_context sigma; gc_denoiser_workspace ws; };
+extern "C" __attribute__((visibility("default"))) int64_t gc_ffi_register_forward(const gc_denoiser_model* m, const gc_denoiser_graph* g,
+                                                                                  const gc_sigma_context* s,
+                                                                                  const gc_denoiser_workspace* w) {
+  return reinterpret_cast<int64_t>(new ForwardBundle{*m, *g, *s, *w});
+}
+static ffi::Error ForwardImpl(cudaStream_t stream, ffi::AnyBuffer xin, ffi::AnyBuffer a_const, ffi::Result<ffi::Buffer<ffi::F32>> f_out,
+                              int64_t handle) {
+  ForwardBundle b = *reinterpret_cast<const ForwardBundle*>(handle);     // per-call copy: the handler stays re-entrant
+  b.ws.xin = xin.untyped_data();
+  b.ws.a_const = a_const.untyped_data();
+  b.ws.f_out = f_out->typed_data();
+  b.ws.branch_stream = nullptr;
+  return status(gc_denoiser_forward(stream, &b.model, &b.graph, &b.sigma, &b.ws));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(gc_denoiser_forward_ffi, ForwardImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Ret<ffi::Buffer<ffi::F32>>().Attr<int64_t>("handle"),
+                              {ffi::Traits::kCmdBufferCompatible});
 #endif  // __has_include("xla/ffi/api/ffi.h")
