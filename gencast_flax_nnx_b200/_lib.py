@@ -167,6 +167,14 @@ def load() -> ctypes.CDLL:
         raise GencastKernelError(
             f"{LIB_PATH} is missing: build the CUDA kernels first (python -m gencast_flax_nnx_b200.build). "
             "There is no CPU fallback.")
+    try:
+        from . import build as _build
+        if (_build.CSRC / "abi.cu").exists() and not _build.is_current():
+            import warnings
+            warnings.warn(f"{LIB_PATH.name} is older than the sources under csrc/ (fingerprint mismatch): rebuild with "
+                          "`python -m gencast_flax_nnx_b200.build`", RuntimeWarning)
+    except ImportError:
+        pass
     lib = ctypes.CDLL(str(LIB_PATH))
     for name, (restype, argtypes) in SIGNATURES.items():
         fn = getattr(lib, name)     # AttributeError if the symbol is not exported

@@ -55,6 +55,9 @@ class Denoiser:
                 raise ValueError("Denoiser was initialised for a different lat/lon grid")
             return self._engine
         forc = forcings if forcings is not None else Dataset({}, inputs.coords)
+        # a name shared by forcings and noisy targets: the noisy target wins, as `forcings.assign(noisy_targets)` does in
+        # the reference (gencast/denoiser.py:184)
+        forc = forc.drop_vars([n for n in forc.keys() if n in noisy_targets])
         sizes = dict(inputs.sizes)
         sizes.setdefault("batch", 1)
         layout = ChannelLayout(
@@ -98,6 +101,8 @@ class Denoiser:
     def stack_constants(self, inputs: Dataset, forcings: Optional[Dataset], sizes):
         """(inputs, forcings) as device tensors [G, B, C] (layout transposes run on the GPU)."""
         forc = forcings if forcings is not None else Dataset({}, inputs.coords)
+        names = {n for n, _ in self.engine.layout.forcing_vars}
+        forc = forc.drop_vars([n for n in forc.keys() if n not in names])      # forcings overridden by noisy targets
         return self.stacker.to_nodes("inputs", inputs, sizes), self.stacker.to_nodes("forcings", forc, sizes)
 
     def __call__(self, inputs: Dataset, noisy_targets: Dataset, noise_levels: DataArray,
@@ -113,16 +118,24 @@ class Denoiser:
         levels = np.asarray(noise_levels.data, np.float64)
         if engine.B != batch:
             raise ValueError(f"Denoiser was initialised for batch size {engine.B}, got {batch}")
-        if batch > 1 and not np.all(levels == levels[0]):
-            raise NotImplementedError("batch elements with different noise levels in one call: evaluate them "
-                                      "separately (the sampler always passes one level)")
         with torch.cuda.device(engine.device):
             inp, frc = self.stack_constants(inputs, forcings, sizes)
             noisy = self.stacker.to_nodes("noisy", noisy_targets, sizes)
             engine.set_constant_features(self.member_major(inp), self.member_major(frc))
             engine.set_network_input(self.member_major(noisy))
-            f = engine.forward(engine.sigma_context(float(levels[0])))
-            out = f[:, :engine.n_out].reshape(batch, engine.G, engine.n_out).permute(1, 0, 2)
+            uniq = np.unique(levels)
+            if len(uniq) == 1:
+                f = engine.forward(engine.sigma_context(float(levels[0])))[:, :engine.n_out]
+            else:
+                # batch elements at different noise levels (the reference conditions every element on its own level,
+                # gencast/denoiser.py:190-198): the members are evaluated together once per distinct level and each
+                # keeps the rows computed with its level
+                f = torch.empty(batch * engine.G, engine.n_out, dtype=torch.float32, device=engine.device)
+                for lv in uniq:
+                    g = engine.forward(engine.sigma_context(float(lv)))
+                    for b in np.nonzero(levels == lv)[0]:
+                        f[b * engine.G:(b + 1) * engine.G] = g[b * engine.G:(b + 1) * engine.G, :engine.n_out]
+            out = f.reshape(batch, engine.G, engine.n_out).permute(1, 0, 2)
             return self.stacker.from_nodes(out, noisy_targets)
 
     @staticmethod

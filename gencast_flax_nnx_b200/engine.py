@@ -165,7 +165,13 @@ class DenoiserEngine:
         self._pre = mlp_prefixes()
         self.mesh_order = mesh_order
         self.use_tc_attention = (attention == "auto" and compute_dtype == "bf16" and self.head_dim in (64, 128))
+        if not noise_cfg.apply_log_first:
+            raise ValueError("NoiseEncoderConfig.apply_log_first=False is not supported: gc_cond_tables encodes log(sigma) "
+                             "(the reference's default, gencast/denoiser.py:57)")
         self._sigma_cache: Dict[float, SigmaContext] = {}
+        self._sigma_pinned: set = set()          # levels a sampler schedule holds on to (never evicted)
+        self.sigma_cache_size = int(os.environ.get("GENCAST_SIGMA_CACHE", "16"))   # unpinned contexts kept (LRU)
+        self.expected_levels = 40                # levels an edge-table budget is sized for (20-step 2S schedule)
         self.edge_table_budget_bytes = int(float(os.environ.get("GENCAST_EDGE_TABLE_GB", "24")) * 2 ** 30)
         # mesh2grid edge update + aggregation in one kernel (gc_edge_mlp_sum3); GENCAST_EDGE_FUSED=0 keeps the
         # three-kernel path (gc_edge_hidden / edge GEMM with gathers -> second-layer GEMM -> gc_ln_cond_segment_sum)
@@ -513,11 +519,20 @@ class DenoiserEngine:
         return ctx.c_struct
 
     # ------------------------------------------------------------------ per-sigma
-    def sigma_context(self, sigma: float) -> SigmaContext:
+    def sigma_context(self, sigma: float, pin: bool = False) -> SigmaContext:
+        """Everything that depends on the noise level only, cached.  `pin=True` (a sampler's schedule) keeps the context
+        for the engine's lifetime; other levels (Denoiser.__call__ with arbitrary sigmas, loss sweeps) live in an LRU
+        of `sigma_cache_size` entries, so HBM use stays bounded."""
         sigma = float(sigma)
         ctx = self._sigma_cache.get(sigma)
+        if pin:
+            self._sigma_pinned.add(sigma)
         if ctx is not None:
+            self._sigma_cache[sigma] = self._sigma_cache.pop(sigma)       # most recently used last
             return ctx
+        unpinned = [k for k in self._sigma_cache if k not in self._sigma_pinned]
+        while len(unpinned) >= max(self.sigma_cache_size, 1):
+            del self._sigma_cache[unpinned.pop(0)]
         L = self.L
         with torch.cuda.device(self.device):
             table = torch.empty(1, self.num_cond, 2 * L, dtype=torch.float32, device=self.device)
@@ -540,8 +555,12 @@ class DenoiserEngine:
             # all members.  The per-call work is then a gather-add-activation (gc_edge_hidden) instead of an edge
             # GEMM with gathers.  Kept while the tables of all cached levels fit the budget (12 GB at 1 deg for
             # the 40 levels of the schedule; at 0.25 deg they would not, and the GEMM path is used).
-            need = 2 * (self.E1 + self.E2) * L * max(40, len(self._sigma_cache) + 1)     # 40 = levels of a 20-step 2S schedule
-            if self.cd == torch.bfloat16 and need <= self.edge_table_budget_bytes:
+            levels = max(self.expected_levels, len(self._sigma_pinned), 1)
+            need = 2 * (self.E1 + self.E2) * L * levels
+            free_bytes, _ = torch.cuda.mem_get_info(self.device)
+            have = sum(2 * (self.E1 + self.E2) * L for c in self._sigma_cache.values() if c.g2m_base is not None)
+            budget = min(self.edge_table_budget_bytes, have + int(0.6 * free_bytes))
+            if self.cd == torch.bfloat16 and need <= budget and (pin or len(self._sigma_pinned) == 0):
                 ctx.g2m_base = torch.empty(self.E1, L, dtype=self.cd, device=self.device)
                 # g_w / d_w were written by the fold kernels queued just above: not static weights (no early W fetch)
                 ops.gemm([(self.g2m_e_ln[:self.E1], g_w)], ctx.g2m_base, bias=g_b)
@@ -566,6 +585,9 @@ class DenoiserEngine:
             t = torch.cat([p.reshape(self.Gt, -1).to(torch.float32) for p in parts], dim=1)
             return t.contiguous()
         pin, dev = self._stage(name, cols)
+        ev = self.__dict__.setdefault("_stage_events", {}).get(name)
+        if ev is not None:
+            ev.synchronize()          # the previous H2D copy out of this pinned buffer has finished reading it
         c = 0
         for p in parts:
             a = p.detach().cpu().numpy() if isinstance(p, torch.Tensor) else np.asarray(p)
@@ -573,6 +595,9 @@ class DenoiserEngine:
             pin[:, c:c + a.shape[1]] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
             c += a.shape[1]
         dev.copy_(pin, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._stage_events[name] = ev
         return dev
 
     def set_constant_features(self, inputs_nodes, forcings_nodes, transform: Optional[Dict[str, torch.Tensor]] = None) -> None:
@@ -799,7 +824,8 @@ class SamplerEngine:
                 plan.append((s_safe, "first", (_c_out(s_safe), _c_skip(s_safe), a, _c_in(mid_safe))))
                 plan.append((mid_safe, "second", (_c_out(mid_safe), _c_skip(mid_safe), b, _c_in(nxt))))
         self.plan = plan
-        self.ctx = [None if p[1] == "churn" else e.sigma_context(p[0]) for p in plan]
+        e.expected_levels = max(1, len({p[0] for p in plan if p[1] != "churn"}))
+        self.ctx = [None if p[1] == "churn" else e.sigma_context(p[0], pin=True) for p in plan]
         sched = np.asarray([p[2] for p in plan], np.float32)
         self.sched = torch.from_numpy(sched).to(e.device)
         self.init_scale = torch.tensor([self.sigmas[0], self.sigmas[0] * _c_in(self.sigmas[0])], dtype=torch.float32,

@@ -387,3 +387,25 @@ def test_device_rollout_with_normalization_and_nan_cleaning_equals_host_wrappers
         np.testing.assert_array_equal(dev[k].data, host[k].data)
     assert np.isnan(host[var].data[..., 3:6, 5:11]).all() and np.isfinite(host[var].data[..., 0, :]).all()
     assert np.isfinite(host["mean_sea_level_pressure"].data).all()
+
+
+def test_denoiser_call_with_a_different_noise_level_per_batch_element(cuda_device):
+    """Denoiser.__call__ conditions every batch element on its own noise level (gencast/denoiser.py:190-198): with
+    levels (1.0, 0.1) element b equals the evaluation of the whole batch at level b's value."""
+    from gencast_flax_nnx_b200 import configs, gencast, graph, stacking, synthetic
+    from gencast_flax_nnx_b200.rngs import Rngs
+    from gencast_flax_nnx_b200.xarray_lite import DataArray
+    case = make_case("tiny")
+    res, arch = configs.named_config("tiny")
+    lat, lon = graph.regular_grid(res)
+    inputs, targets, forcings = synthetic.make_example(lat, lon, batch=2, seed=6)
+    model = gencast.GenCast(configs.TASK, arch, rngs=Rngs(0), params=case.params, compute_dtype="f32")
+    noisy = stacking.nodes_to_dataset(np.random.default_rng(1).standard_normal((len(lat) * len(lon), 2, 82)).astype(np.float32), targets)
+    lv = lambda a, b: DataArray(np.array([a, b], np.float32), ("batch",))
+    mixed = model.denoiser(inputs, noisy, lv(1.0, 0.1), forcings)
+    hi, lo = model.denoiser(inputs, noisy, lv(1.0, 1.0), forcings), model.denoiser(inputs, noisy, lv(0.1, 0.1), forcings)
+    for k in mixed.keys():
+        ax = mixed[k].dims.index("batch")
+        np.testing.assert_array_equal(np.take(mixed[k].data, 0, ax), np.take(hi[k].data, 0, ax))
+        np.testing.assert_array_equal(np.take(mixed[k].data, 1, ax), np.take(lo[k].data, 1, ax))
+        assert not np.array_equal(np.take(hi[k].data, 1, ax), np.take(lo[k].data, 1, ax))
