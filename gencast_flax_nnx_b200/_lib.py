@@ -104,6 +104,7 @@ class DenoiserWorkspace(Structure):
 
 GC_ATTENTION_CSR, GC_ATTENTION_TILES, GC_ATTENTION_GATHER = 0, 1, 2
 GC_FORWARD_FUSE_M2G = 1
+GC_FORWARD_FUSE_LN = 2
 FORWARD_STRUCTS = (DenoiserModel, DenoiserGraph, SigmaContextC, DenoiserWorkspace, Mlp2, TransformerLayer)
 
 # name -> (restype, argtypes); also the list of symbols tests check for.
@@ -139,6 +140,8 @@ SIGNATURES = {
                                           c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_int64]),
     "gc_edge_hidden": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                  c_int64, c_int32, c_void_p, c_int64, c_int64, c_int32]),
+    "gc_linear_ln_cond": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int32,
+                                    c_void_p, c_int32, c_int64, c_void_p, c_int32, c_int64, c_int32]),
     "gc_edge_mlp_sum3": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                    c_int64, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_int32,
                                    c_int64, c_int64, c_int32]),

@@ -360,6 +360,274 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const EdgeFusedP
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Second MLP layer + LayerNorm + conditional affine (+ residual) in one kernel, for the node MLPs:
+//     out = LN(A W2^T + b2) * (1 + s) + o (+ residual)            MLPWithNormConditioning, common/mlp.py:115-147,
+//                                                                  residual of common/deep_typed_graph_net.py:569-581
+// Same whole-row accumulator as above (128 rows x L columns of TMEM per tile, persistent CTA per SM), but the A operand
+// is the hidden layer in HBM and arrives by TMA, so there are no producer warps: warp 0 streams A and W2 k-blocks,
+// warp 1 issues the MMAs, eight epilogue warps (two per TMEM lane quarter, half of the columns each) compute the row
+// statistics in a first pass over the accumulator and normalise / transpose / add the residual / store in a second.
+// It replaces a GEMM that writes y, and a LayerNorm kernel that reads y and the residual and writes out: y never
+// exists in HBM.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int LN_THREADS = 320;
+
+struct LinearLnParams {
+  const float* b2;
+  const float* scale_offset;
+  int do_ln;
+  const void* residual; int res_dtype; int64_t ld_res;
+  void* out; int out_dtype; int64_t ldo;
+  int64_t rows;
+  int num_tiles;
+};
+
+template <int L>
+__global__ void __launch_bounds__(LN_THREADS, 1)
+linear_ln_cond_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w_map, const LinearLnParams p) {
+  using namespace sm100;
+  using C = EFCfg<L>;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_smem = smem_base + C::A_OFF;
+  const uint32_t w_smem = smem_base + C::W_OFF;
+  const uint32_t bars = smem_base + C::BAR_OFF;
+  float* vec_s = reinterpret_cast<float*>(smem_gen + C::VEC_OFF);
+  float2* stat_s = reinterpret_cast<float2*>(smem_gen + C::STAT_OFF);
+  auto a_full = [&](int s) { return bars + 8u * s; };
+  auto a_empty = [&](int s) { return bars + 8u * (EF_A_STAGES + s); };
+  auto w_full = [&](int s) { return bars + 8u * (2 * EF_A_STAGES + s); };
+  auto w_empty = [&](int s) { return bars + 8u * (2 * EF_A_STAGES + EF_W_STAGES + s); };
+  const uint32_t acc_full = bars + 8u * (2 * EF_A_STAGES + 2 * EF_W_STAGES);
+  const uint32_t acc_empty = acc_full + 8u;
+  const uint32_t tmem_ptr_smem = acc_full + 16u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&a_map);
+    prefetch_tensormap(&w_map);
+    for (int s = 0; s < EF_A_STAGES; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < EF_W_STAGES; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, EF_EPI_WARPS);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    // ---------------- TMA producer: W2 k-blocks (static weights: the first ring pass is requested before the wait for
+    // the predecessor grid) and the A k-blocks of this CTA's tiles
+    int sa = 0, sw = 0;
+    uint32_t pa = 0, pw = 0;
+    auto load_w = [&](int kb, int h) {
+      mbar_wait(w_empty(sw), pw ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(w_full(sw), C::W_STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < C::NI / 128; ++j)
+          tma_load_2d(w_smem + sw * C::W_STAGE_BYTES + j * (128 * 128), &w_map, w_full(sw), kb * 64, h * C::NI + j * 128);
+      }
+      __syncwarp();
+      if (++sw == EF_W_STAGES) { sw = 0; pw ^= 1u; }
+    };
+    // W stages needed before the first A k-block can be consumed: (kb, h) pairs in issue order
+    int pre = 0;
+    const int first_total = C::KB * C::NH;
+    if (static_cast<int>(blockIdx.x) < p.num_tiles)
+      for (; pre < EF_W_STAGES && pre < first_total; ++pre) load_w(pre / C::NH, pre % C::NH);
+    pdl_wait();
+    bool first = true;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < C::KB; ++kb) {
+        mbar_wait(a_empty(sa), pa ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(a_full(sa), EF_A_STAGE_BYTES);
+          tma_load_2d(a_smem + sa * EF_A_STAGE_BYTES, &a_map, a_full(sa), kb * 64, tile * 128);
+        }
+        __syncwarp();
+        if (++sa == EF_A_STAGES) { sa = 0; pa ^= 1u; }
+        for (int h = 0; h < C::NH; ++h) {
+          if (first && kb * C::NH + h < pre) continue;        // already requested above
+          load_w(kb, h);
+        }
+      }
+      first = false;
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer
+    constexpr uint32_t idesc = idesc_bf16_f32(128, C::NI, 0, 0);
+    int sa = 0, sw = 0;
+    uint32_t pa = 0, pw = 0;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+      mbar_wait(acc_empty, (static_cast<uint32_t>(lt) & 1u) ^ 1u);
+      tc_fence_after();
+      for (int kb = 0; kb < C::KB; ++kb) {
+        mbar_wait(a_full(sa), pa);
+        const uint64_t da = desc_kmajor_sw128(a_smem + sa * EF_A_STAGE_BYTES);
+        for (int h = 0; h < C::NH; ++h) {
+          mbar_wait(w_full(sw), pw);
+          tc_fence_after();
+          const uint64_t dw = desc_kmajor_sw128(w_smem + sw * C::W_STAGE_BYTES);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tmem_base + h * C::NI, da + 2u * k, dw + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(w_empty(sw));
+          }
+          __syncwarp();
+          if (++sw == EF_W_STAGES) { sw = 0; pw ^= 1u; }
+        }
+        if (elect_one()) umma_commit(a_empty(sa));
+        __syncwarp();
+        if (++sa == EF_A_STAGES) { sa = 0; pa ^= 1u; }
+      }
+      if (elect_one()) umma_commit(acc_full);
+      __syncwarp();
+    }
+  } else {
+    // ---------------- epilogue
+    const int ew = warp - 2;                             // 0 .. 7
+    const int q = warp & 3;                              // TMEM lane quarter this warp may read
+    const int half = ew >> 2;
+    constexpr int CH = L / 2;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * CH;
+    float* patch = reinterpret_cast<float*>(smem_gen + C::PATCH_OFF + ew * EF_PATCH_BYTES);
+    const int et = threadIdx.x - 64;                     // 0 .. 255
+    pdl_wait();
+    for (int c = et; c < 3 * L; c += 32 * EF_EPI_WARPS) {
+      float v;
+      if (c < L) v = p.b2 != nullptr ? __ldg(p.b2 + c) : 0.0f;
+      else if (p.scale_offset != nullptr) v = __ldg(p.scale_offset + (c - L));
+      else v = c < 2 * L ? 1.0f : 0.0f;
+      vec_s[c] = v;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float* b2s = vec_s + half * CH;
+    const float* scs = vec_s + L + half * CH;
+    const float* ofs = vec_s + 2 * L + half * CH;
+    const float inv_n = 1.0f / static_cast<float>(L);
+    const int cp = lane & 15;                            // column pair of a 32-column chunk
+    const int rsel = lane >> 4;                          // row parity handled in the store loop
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+      mbar_wait(acc_full, static_cast<uint32_t>(lt) & 1u);
+      tc_fence_after();
+      float s = 0.0f, ss = 0.0f;
+      {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr, r);
+#pragma unroll 1
+        for (int c = 0; c < CH; c += 32) {
+          float v[32];
+          tc_wait_ld();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+          if (c + 32 < CH) tmem_ld_32x32b_x32(taddr + c + 32, r);
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(b2s + c + k);
+            const float y0 = v[k] + b.x, y1 = v[k + 1] + b.y, y2 = v[k + 2] + b.z, y3 = v[k + 3] + b.w;
+            s += (y0 + y1) + (y2 + y3);
+            ss = fmaf(y0, y0, ss); ss = fmaf(y1, y1, ss); ss = fmaf(y2, y2, ss); ss = fmaf(y3, y3, ss);
+          }
+        }
+      }
+      stat_s[half * 128 + q * 32 + lane] = make_float2(s, ss);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float mean = 0.0f, rstd = 1.0f;
+      if (p.do_ln) {
+        const float2 o = stat_s[(half ^ 1) * 128 + q * 32 + lane];
+        mean = (s + o.x) * inv_n;
+        rstd = rsqrtf(fmaxf((ss + o.y) * inv_n - mean * mean, 0.0f) + EF_LN_EPS);
+      }
+      const int64_t row0 = static_cast<int64_t>(tile) * 128 + q * 32;
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr, r);
+#pragma unroll 1
+      for (int c = 0; c < CH; c += 32) {
+        float v[32];
+        tc_wait_ld();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+        if (c + 32 < CH) {
+          tmem_ld_32x32b_x32(taddr + c + 32, r);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty);
+        }
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(b2s + c + k);
+          const float4 sc = *reinterpret_cast<const float4*>(scs + c + k);
+          const float4 of = *reinterpret_cast<const float4*>(ofs + c + k);
+          float4 x;
+          x.x = fmaf((v[k] + b.x - mean) * rstd, sc.x, of.x); x.y = fmaf((v[k + 1] + b.y - mean) * rstd, sc.y, of.y);
+          x.z = fmaf((v[k + 2] + b.z - mean) * rstd, sc.z, of.z); x.w = fmaf((v[k + 3] + b.w - mean) * rstd, sc.w, of.w);
+          *reinterpret_cast<float4*>(patch + lane * EF_PATCH_STRIDE + k) = x;
+        }
+        __syncwarp();
+        // rows of the patch leave 16 lanes at a time (64 B of bf16 / 128 B of fp32 per row and instruction)
+        const int col = half * CH + c + 2 * cp;
+#pragma unroll 4
+        for (int it = 0; it < 16; ++it) {
+          const int rr = 2 * it + rsel;
+          const int64_t row = row0 + rr;
+          float2 x = *reinterpret_cast<const float2*>(patch + rr * EF_PATCH_STRIDE + 2 * cp);
+          if (row < p.rows) {
+            if (p.residual != nullptr) {
+              if (p.res_dtype == GC_BF16) {
+                const float2 rsd = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(
+                    reinterpret_cast<const __nv_bfloat16*>(p.residual) + row * p.ld_res + col));
+                x.x += rsd.x; x.y += rsd.y;
+              } else {
+                const float2 rsd = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(p.residual) + row * p.ld_res + col);
+                x.x += rsd.x; x.y += rsd.y;
+              }
+            }
+            if (p.out_dtype == GC_BF16) {
+              *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col) = __floats2bfloat162_rn(x.x, x.y);
+            } else {
+              *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + row * p.ldo + col) = x;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int L>
+int launch_linear_ln(cudaStream_t st, const CUtensorMap& a_map, const CUtensorMap& w_map, const LinearLnParams& p) {
+  using C = EFCfg<L>;
+  GC_CHECK_CUDA(cudaFuncSetAttribute(linear_ln_cond_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM),
+                "cudaFuncSetAttribute(linear_ln_cond_kernel)");
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = static_cast<unsigned>(p.num_tiles < sms ? p.num_tiles : sms);
+  GC_CHECK_CUDA(launch_kernel(linear_ln_cond_kernel<L>, dim3(grid), dim3(LN_THREADS), (size_t)C::SMEM, st, a_map, w_map, p),
+                "linear_ln_cond_kernel");
+  return GC_OK;
+}
+
 template <int L>
 int launch_edge_fused(cudaStream_t st, const CUtensorMap& w_map, const EdgeFusedParams& p) {
   using C = EFCfg<L>;
@@ -375,6 +643,35 @@ int launch_edge_fused(cudaStream_t st, const CUtensorMap& w_map, const EdgeFused
 
 }  // namespace
 }  // namespace gc
+
+extern "C" int gc_linear_ln_cond(void* stream, const void* a, int64_t lda, int64_t rows, const void* w, int64_t ldw, const float* bias,
+                                 const float* scale_offset, int32_t do_layer_norm, const void* residual, int32_t res_dtype,
+                                 int64_t ld_res, void* out, int32_t out_dtype, int64_t ldo, int32_t cols) {
+  using namespace gc;
+  GC_REQUIRE(a && w && out, "gc_linear_ln_cond: null buffer");
+  GC_REQUIRE(cols == 128 || cols == 256 || cols == 512, "gc_linear_ln_cond: cols=%d (supported: 128, 256, 512)", cols);
+  GC_REQUIRE(rows >= 0 && rows < (1LL << 31), "gc_linear_ln_cond: rows=%lld", (long long)rows);
+  GC_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0 && lda >= cols && ldw >= cols && ldo >= cols && aligned16(a) &&
+                 aligned16(w) && aligned16(out), "gc_linear_ln_cond: alignment");
+  GC_REQUIRE(out_dtype == GC_BF16 || out_dtype == GC_F32, "gc_linear_ln_cond: bad out dtype");
+  if (residual != nullptr)
+    GC_REQUIRE((res_dtype == GC_BF16 || res_dtype == GC_F32) && ld_res % 8 == 0 && aligned16(residual), "gc_linear_ln_cond: residual");
+  if (rows == 0) return GC_OK;
+  CUtensorMap a_map, w_map;
+  int rc = make_tmap_bf16_2d(&a_map, a, (uint64_t)rows, (uint64_t)cols, (uint64_t)lda, 64, 128);
+  if (rc != GC_OK) return rc;
+  rc = make_tmap_bf16_2d(&w_map, w, (uint64_t)cols, (uint64_t)cols, (uint64_t)ldw, 64, 128);
+  if (rc != GC_OK) return rc;
+  LinearLnParams p;
+  p.b2 = bias; p.scale_offset = scale_offset; p.do_ln = do_layer_norm;
+  p.residual = residual; p.res_dtype = res_dtype; p.ld_res = ld_res;
+  p.out = out; p.out_dtype = out_dtype; p.ldo = ldo; p.rows = rows;
+  p.num_tiles = (int)((rows + 127) / 128);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cols == 128) return launch_linear_ln<128>(st, a_map, w_map, p);
+  if (cols == 256) return launch_linear_ln<256>(st, a_map, w_map, p);
+  return launch_linear_ln<512>(st, a_map, w_map, p);
+}
 
 extern "C" int gc_edge_mlp_sum3(void* stream, const void* base, int64_t ld_base, int64_t period, const void* gs,
                                 const int32_t* idx_s, int64_t ld_gs, const void* gr, const int32_t* idx_r, int64_t ld_gr,

@@ -22,6 +22,7 @@ struct Ctx {
   cudaStream_t st;
   int dtype;        // operand dtype of every GEMM
   int L;
+  bool fuse_ln;     // second MLP layer + LayerNorm + affine + residual through gc_linear_ln_cond
 };
 
 int run_gemm(const Ctx& c, cudaStream_t st, const Seg* segs, int nseg, int64_t m, int n, void* out, int out_dtype,
@@ -54,6 +55,9 @@ int mlp_ln(const Ctx& c, cudaStream_t st, const gc_mlp2& w, const void* const* a
   for (int s = 0; s < w.num_segments; ++s) segs[s] = Seg{a[s], w.k1[s], w.w1[s], w.k1[s]};
   GC_TRY(run_gemm(c, st, segs, w.num_segments, rows, c.L, h, c.dtype, w.b1, GC_ACT_SWISH, nullptr, 0, nullptr, nullptr, nullptr,
                   nullptr, true));
+  if (c.fuse_ln)
+    return gc_linear_ln_cond(st, h, c.L, rows, w.w2, c.L, w.b2, so, 1, residual, res_dtype, residual != nullptr ? c.L : 0, out,
+                             out_dtype, c.L, c.L);
   const Seg s2{h, c.L, w.w2, c.L};
   GC_TRY(run_gemm(c, st, &s2, 1, rows, c.L, y, c.dtype, w.b2, GC_ACT_NONE, nullptr, 0, nullptr, nullptr, nullptr, nullptr, true));
   return gc_ln_cond(st, y, c.dtype, c.L, so, 1, residual, res_dtype, residual != nullptr ? c.L : 0, out, out_dtype, c.L, rows, c.L);
@@ -85,7 +89,7 @@ extern "C" int gc_denoiser_forward(void* stream, const gc_denoiser_model* m, con
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaStream_t bs = reinterpret_cast<cudaStream_t>(ws->branch_stream);
   const bool branch = bs != nullptr && ws->fork_event != nullptr && ws->join_event != nullptr;
-  const Ctx c{st, m->dtype, m->latent};
+  const Ctx c{st, m->dtype, m->latent, (ws->flags & GC_FORWARD_FUSE_LN) != 0 && m->dtype == GC_BF16};
   const int L = m->latent, dt = m->dtype;
   const int64_t G = g->grid_rows, V = g->mesh_rows, E1 = g->g2m_edges, E2 = g->m2g_edges;
   auto T = [&](int row) { return sc->table + static_cast<int64_t>(row) * 2 * L; };

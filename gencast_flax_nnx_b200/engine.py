@@ -176,6 +176,9 @@ class DenoiserEngine:
         # mesh2grid edge update + aggregation in one kernel (gc_edge_mlp_sum3); GENCAST_EDGE_FUSED=0 keeps the
         # three-kernel path (gc_edge_hidden / edge GEMM with gathers -> second-layer GEMM -> gc_ln_cond_segment_sum)
         self.fuse_m2g = compute_dtype == "bf16" and os.environ.get("GENCAST_EDGE_FUSED", "1") != "0"
+        # second MLP layer + LayerNorm + affine + residual of the node MLPs in one kernel (gc_linear_ln_cond);
+        # GENCAST_LN_FUSED=0 keeps GEMM -> gc_ln_cond
+        self.fuse_ln = compute_dtype == "bf16" and os.environ.get("GENCAST_LN_FUSED", "1") != "0"
         # launch sequencing of one evaluation: 'c' = one gc_denoiser_forward call (C++), 'py' = the same sequence issued
         # from Python through the per-kernel entry points (what the per-kernel timing recorder needs)
         self.forward_impl = os.environ.get("GENCAST_FORWARD", "c")
@@ -501,7 +504,7 @@ class DenoiserEngine:
             if branch_stream is not None:
                 ws.branch_stream = branch_stream.cuda_stream
                 ws.fork_event, ws.join_event = self._fork_ev.cuda_event, self._join_ev.cuda_event
-            ws.flags = ops._lib.GC_FORWARD_FUSE_M2G if self.fuse_m2g else 0
+            ws.flags = (ops._lib.GC_FORWARD_FUSE_M2G if self.fuse_m2g else 0) | (ops._lib.GC_FORWARD_FUSE_LN if self.fuse_ln else 0)
             self._c_workspaces[key] = ws
         return ws
 
@@ -637,6 +640,9 @@ class DenoiserEngine:
     # ------------------------------------------------------------------ forward
     def _mlp_ln(self, segs, w1b, w2, b2, h, y, out, so, residual=None, gathers=(), act="swish"):
         _gemm(segs, h, bias=w1b, act=act, gathers=gathers)
+        if self.fuse_ln:
+            ops.linear_ln_cond(h, w2, b2, so, out, residual=residual)
+            return
         _gemm([(h, w2)], y, bias=b2)
         ops.ln_cond(y, out, so, residual=residual)
 
@@ -737,6 +743,8 @@ class DenoiserEngine:
     @property
     def launches_per_forward(self) -> int:
         n = self.LAUNCHES_PER_FORWARD_FIXED + 7 * self.NL
+        if self.fuse_ln:
+            n -= 4                               # grid embed, mesh update, grid update, mesh2grid grid update
         if self.fuse_m2g and self.m2g_perm is None:
             # fused mesh2grid edge path: 1 kernel instead of 3 with the per-level tables, 2 instead of 3 without
             tables = bool(self._sigma_cache) and next(iter(self._sigma_cache.values())).m2g_base is not None

@@ -327,6 +327,24 @@ def edge_hidden(base: torch.Tensor, gathers: Sequence[Tuple[torch.Tensor, torch.
     return out
 
 
+@_recorded("linear_ln_cond", lambda a, w, bias, so, out, **kw: (2.0 * a.shape[0] * w.shape[0] * w.shape[1], _nbytes(a, w, out, kw.get("residual"))))
+def linear_ln_cond(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], scale_offset: Optional[torch.Tensor],
+                   out: torch.Tensor, *, residual: Optional[torch.Tensor] = None, layer_norm: bool = True) -> torch.Tensor:
+    """out = LN(a @ w^T + bias) * scale + offset (+ residual) in one kernel (gc_linear_ln_cond); a, w bf16."""
+    lib = _lib.load()
+    if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
+        raise TypeError("linear_ln_cond: bf16 operands expected")
+    rows, cols = out.shape
+    if a.shape != (rows, cols) or w.shape != (cols, cols):
+        raise ValueError("linear_ln_cond: a must be [rows, cols] and w [cols, cols]")
+    _lib.check(lib.gc_linear_ln_cond(_stream(), a.data_ptr(), _row_major(a, "a"), rows, w.data_ptr(), _row_major(w, "w"),
+                                     _p(bias), _p(scale_offset), int(layer_norm), _p(residual),
+                                     _dt(residual) if residual is not None else 0,
+                                     _row_major(residual, "residual") if residual is not None else 0, out.data_ptr(), _dt(out),
+                                     _row_major(out, "out"), cols), "gc_linear_ln_cond")
+    return out
+
+
 def _edge_fused_cost(base, gathers, w2, b2, so, out, **kw):
     e = 3 * out.shape[0]
     cols = out.shape[1]

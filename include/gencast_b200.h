@@ -288,6 +288,19 @@ GC_API int gc_edge_hidden(void* stream, const void* base, int64_t ld_base, int64
                    int32_t act, void* out, int64_t ldo, int64_t rows, int32_t cols);
 
 /*
+ * Second MLP layer + LayerNorm + conditional affine (+ residual) in one kernel (bf16 operands, tcgen05):
+ *   out = LayerNorm(a . w^T + bias) * scale + offset (+ residual)
+ * i.e. the tail of MLPWithNormConditioning (common/mlp.py:121-147) and the residual add of
+ * common/deep_typed_graph_net.py:569-581 without the pre-norm activations ever leaving the SM: every tile holds whole
+ * rows (128 x cols fp32) in tensor memory, the epilogue reads them twice (statistics, normalise).  a: [rows, cols] bf16,
+ * w: [cols, cols] bf16 stored [out, in]; bias [cols], scale_offset [2 cols] = (1 + s | o) fp32 or NULL;
+ * residual [rows, cols] bf16 / fp32 or NULL; out bf16 / fp32.  cols in {128, 256, 512}.
+ */
+GC_API int gc_linear_ln_cond(void* stream, const void* a, int64_t lda, int64_t rows, const void* w, int64_t ldw,
+                             const float* bias, const float* scale_offset, int32_t do_layer_norm, const void* residual,
+                             int32_t res_dtype, int64_t ld_res, void* out, int32_t out_dtype, int64_t ldo, int32_t cols);
+
+/*
  * Fused edge update + aggregation for a bipartite graph whose receivers have exactly three incoming edges each,
  * stored receiver-major (edges 3v, 3v+1, 3v+2 -> receiver v; GenCast's mesh2grid decoder,
  * common/grid_mesh_connectivity.py:104, :125-131).  One kernel, no [E, cols] tensor in HBM:
@@ -368,6 +381,7 @@ GC_API int gc_ensemble_accumulate(void* stream, const float* x, float* sum, floa
                                     the mesh2grid edge embedding, edge update and grid update */
 
 #define GC_FORWARD_FUSE_M2G 1    /* mesh2grid edge update + aggregation through gc_edge_mlp_sum3 */
+#define GC_FORWARD_FUSE_LN 2     /* second MLP layer + LayerNorm + affine + residual through gc_linear_ln_cond */
 
 /* Linear -> swish -> Linear (common/mlp.py:152-203); the first layer may be split in K-segments (concatenated
  * operands of the reference, common/typed_graph_net.py:301-305, :315-326) */

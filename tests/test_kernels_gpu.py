@@ -377,6 +377,35 @@ def test_edge_mlp_sum3_fused(cuda_device, cols, nrecv, members, out_dtype):
     assert _rel(out.cpu(), (h @ w2.double().T).reshape(R, 3, cols).sum(1)) < 8e-3
 
 
+@pytest.mark.parametrize("cols,rows", [(128, 100), (256, 5000), (512, 20001), (512, 128)])
+@pytest.mark.parametrize("res_dtype,out_dtype", [(None, torch.bfloat16), (torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32),
+                                                 (torch.float32, torch.float32)])
+def test_linear_ln_cond_fused(cuda_device, cols, rows, res_dtype, out_dtype):
+    """Second MLP layer + LayerNorm + conditional affine + residual in one kernel against fp64; bitwise repeatable."""
+    from gencast_flax_nnx_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(cols + rows)
+    d = cuda_device
+    a = torch.randn(rows, cols, generator=g).to(torch.bfloat16)
+    w = (torch.randn(cols, cols, generator=g) / math.sqrt(cols)).to(torch.bfloat16)
+    b = torch.randn(cols, generator=g) * 0.1
+    so = torch.cat([1 + 0.1 * torch.randn(cols, generator=g), torch.randn(cols, generator=g)])
+    res = None if res_dtype is None else torch.randn(rows, cols, generator=g).to(res_dtype)
+    y = a.double() @ w.double().T + b.double()
+    mean = y.mean(-1, keepdim=True)
+    var = ((y * y).mean(-1, keepdim=True) - mean * mean).clamp_min(0)
+    ref = (y - mean) / torch.sqrt(var + 1e-6) * so[:cols].double() + so[cols:].double()
+    if res is not None:
+        ref = ref + res.double()
+    outs = []
+    for _ in range(2):
+        out = torch.full((rows, cols), float("nan"), dtype=out_dtype, device=d)
+        ops.linear_ln_cond(a.to(d), w.to(d), b.to(d), so.to(d), out, residual=None if res is None else res.to(d))
+        torch.cuda.synchronize()
+        outs.append(out.cpu())
+    assert _rel(outs[0], ref) < (6e-3 if out_dtype == torch.bfloat16 else 2e-5 * 50)
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_cond_tables_and_fold(cuda_device):
     from gencast_flax_nnx_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(9)
