@@ -176,9 +176,12 @@ class DenoiserEngine:
         # mesh2grid edge update + aggregation in one kernel (gc_edge_mlp_sum3); GENCAST_EDGE_FUSED=0 keeps the
         # three-kernel path (gc_edge_hidden / edge GEMM with gathers -> second-layer GEMM -> gc_ln_cond_segment_sum)
         self.fuse_m2g = compute_dtype == "bf16" and os.environ.get("GENCAST_EDGE_FUSED", "1") != "0"
-        # second MLP layer + LayerNorm + affine + residual of the node MLPs in one kernel (gc_linear_ln_cond);
-        # GENCAST_LN_FUSED=0 keeps GEMM -> gc_ln_cond
-        self.fuse_ln = compute_dtype == "bf16" and os.environ.get("GENCAST_LN_FUSED", "1") != "0"
+        # second MLP layer + LayerNorm + affine + residual of the node MLPs in one kernel (gc_linear_ln_cond): opt-in
+        # (GENCAST_LN_FUSED=1).  Measured at 1 deg x 4 (260 640 rows): 271 us against 231 us for GEMM -> gc_ln_cond
+        # (389 vs 312 us with a residual): with the whole row in TMEM the accumulator cannot be double buffered and the
+        # 8-warp epilogue (two TMEM passes, ~8 instructions per element) takes 3 x the tile's MMA time, whereas the
+        # separate LayerNorm runs at full occupancy at 70 % of the HBM roofline.  See profiles/README.md.
+        self.fuse_ln = compute_dtype == "bf16" and os.environ.get("GENCAST_LN_FUSED", "0") == "1"
         # launch sequencing of one evaluation: 'c' = one gc_denoiser_forward call (C++), 'py' = the same sequence issued
         # from Python through the per-kernel entry points (what the per-kernel timing recorder needs)
         self.forward_impl = os.environ.get("GENCAST_FORWARD", "c")
