@@ -445,14 +445,20 @@ def measure(args, config: str, MB: int, steps: int, warmup: int, dev, rank: int,
         roof = {"kernel": dom, "bound": "hbm", "achieved": domk["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": domk["gbs"] / peaks["hbm"], "traffic": None}
     try:
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel family from an ncu capture of
-        # the same workload (profiles/r01_gemm_dram_traffic.json names the command); not measured live
-        with open(os.path.join(ROOT, "profiles", "r01_gemm_dram_traffic.json")) as f:
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of every kernel family from an ncu capture of one
+        # evaluation of the same workload (profiles/r02_dram_traffic.json names the command); not measured live
+        with open(os.path.join(ROOT, "profiles", "r02_dram_traffic.json")) as f:
             tr = json.load(f)
-        if tr["workload"] == config and tr["members_per_gpu"] == MB and dom.startswith(tr["kernel"]):
-            roof["traffic"] = tr["dram_bytes_per_launch"]
-            roof["traffic_unit"] = "bytes per launch (ncu capture, profiles/r01_gemm_dram_traffic.json)"
-            roof["algorithmic_bytes_per_launch"] = domk["gbs"] * 1e9 * domk["avg_us"] * 1e-6
+        if tr["workload"] == config and tr["members_per_gpu"] == MB:
+            for name, k in kernels.items():
+                fam = tr["families"].get(name)
+                if fam is not None:
+                    k["dram_bytes_per_launch"] = fam["dram_bytes_per_launch"]
+            fam = tr["families"].get(dom)
+            if fam is not None:
+                roof["traffic"] = fam["dram_bytes_per_launch"]
+                roof["traffic_unit"] = "bytes per launch (ncu capture, profiles/r02_dram_traffic.json)"
+                roof["algorithmic_bytes_per_launch"] = domk["gbs"] * 1e9 * domk["avg_us"] * 1e-6
     except Exception:
         pass
     roof["peak_source"] = peaks["source"] + (" (sustained bf16 GEMM: the kernel is timed inside a long step)"
