@@ -128,8 +128,8 @@ extern "C" int gc_denoiser_forward(void* stream, const gc_denoiser_model* m, con
     }
     const Seg s2{ws->e_h, L, m->g2m_w2, L};
     GC_TRY(run_gemm(c, st, &s2, 1, E1, L, ws->e_y, dt, m->g2m_b2, GC_ACT_NONE, nullptr, 0, nullptr, nullptr, nullptr, nullptr, true));
-    GC_TRY(gc_ln_cond_segment_sum(st, ws->e_y, dt, L, T(GC_COND_G2M_EDGE_UPDATE), 1, g->g2m_row_ptr, g->g2m_perm, ws->m_agg, dt, L,
-                                  V, L));
+    GC_TRY(gc_ln_cond_segment_sum(st, ws->e_y, dt, L, T(GC_COND_G2M_EDGE_UPDATE), 1 | GC_SEGSUM_IRREGULAR, g->g2m_row_ptr,
+                                  g->g2m_perm, ws->m_agg, dt, L, V, L));
   }
   // mesh-node update (+ residual) -> fp32 transformer stream
   {

@@ -682,14 +682,16 @@ int gc_ln_cond_segment_sum(void* stream, const void* y, int32_t y_dtype, int64_t
   if (num_segments <= 0) return GC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const unsigned grid = grid_for(num_segments, SEG_WARPS, 8);
+  const int do_ln = do_layer_norm & 1;
+  const bool irregular = edge_perm != nullptr || (do_layer_norm & GC_SEGSUM_IRREGULAR) != 0;
 #define GC_LAUNCH_SEG(NV, BF, OCC)                                                                             \
   GC_CHECK_CUDA(launch_kernel(ln_cond_segment_sum_kernel<NV, BF, OCC>, dim3(grid), dim3(SEG_WARPS * 32), 0, st, y, ldy, \
-                              scale_offset, do_layer_norm, row_ptr, edge_perm, out, out_dtype, ldo, num_segments),      \
+                              scale_offset, do_ln, row_ptr, edge_perm, out, out_dtype, ldo, num_segments),              \
                 "ln_cond_segment_sum_kernel")
   if (y_dtype == GC_BF16) {
     if (cols == 128) GC_LAUNCH_SEG(4, true, 2);
     else if (cols == 256) GC_LAUNCH_SEG(8, true, 2);
-    else if (edge_perm != nullptr) GC_LAUNCH_SEG(16, true, 3);
+    else if (irregular) GC_LAUNCH_SEG(16, true, 3);
     else GC_LAUNCH_SEG(16, true, 2);
   } else {
     if (cols == 128) GC_LAUNCH_SEG(4, false, 2);

@@ -257,11 +257,15 @@ class DenoiserEngine:
                 rp[b * n_seg_padded + n_seg + 1: (b + 1) * n_seg_padded + 1] = (b + 1) * n_edges   # padded rows: empty
             return rp.astype(np.int32), (None if perm is None else blocks(perm, n_edges))
 
-        self.g2m_s = self._dev(blocks(g.g2m_senders, G))
-        self.g2m_r = self._dev(blocks(g2m_recv, Vp))
+        # grid2mesh edges are stored receiver-sorted inside the engine (edges never leave it): the stable sort that defines
+        # the deterministic summation order is applied to the edge tables themselves, so the segment sum reads consecutive
+        # rows and needs no edge permutation (same order of additions per receiver, hence the same bits)
         rp, perm = csr_by_receiver(g2m_recv, V)
-        rp, perm = csr_blocks(rp, perm, V, Vp, E1)
-        self.g2m_row_ptr, self.g2m_perm = self._dev(rp), self._dev(perm)
+        self._g2m_edge_order = perm.astype(np.int64)
+        self.g2m_s = self._dev(blocks(g.g2m_senders[self._g2m_edge_order], G))
+        self.g2m_r = self._dev(blocks(g2m_recv[self._g2m_edge_order], Vp))
+        rp, _ = csr_blocks(rp, None, V, Vp, E1)
+        self.g2m_row_ptr, self.g2m_perm = self._dev(rp), None
         self.m2g_s = self._dev(blocks(m2g_send, Vp))
         self.m2g_r = self._dev(blocks(g.m2g_receivers, G))
         # mesh2grid edges are emitted grid-major, three per grid node
@@ -432,7 +436,7 @@ class DenoiserEngine:
     def _precompute_static(self):
         g, pre = self.graphs, self._pre
         B = self.B
-        self.g2m_e_ln = self._static_embed(pre["g2m_edge_embed"], g.g2m_edge_feat, slice(0, 4)).repeat(B, 1)
+        self.g2m_e_ln = self._static_embed(pre["g2m_edge_embed"], g.g2m_edge_feat[self._g2m_edge_order], slice(0, 4)).repeat(B, 1)
         self.m2g_e_ln = self._static_embed(pre["m2g_edge_embed"], g.m2g_edge_feat, slice(0, 4)).repeat(B, 1)
         # mesh nodes: [structural | zeros] (gencast/denoiser.py:640-657) -> only the first 3 kernel rows matter
         m0 = self._static_embed(pre["g2m_mesh_embed"], self._mesh_feat, slice(0, 3))
@@ -688,7 +692,7 @@ class DenoiserEngine:
             ops.gemm([(self.g2m_e_ln, ctx.g2m_w1e)], e_h, bias=ctx.g2m_b1, act="swish",
                      gathers=[(self.g_p, self.g2m_s), (ctx.m_p, self.g2m_r)])
         _gemm([(e_h, w["eu_w2"])], e_y, bias=w["eu_b2"])
-        ops.ln_cond_segment_sum(e_y, self.m_agg, T[self.C_G2M_EU], self.g2m_row_ptr, self.g2m_perm)
+        ops.ln_cond_segment_sum(e_y, self.m_agg, T[self.C_G2M_EU], self.g2m_row_ptr, self.g2m_perm, irregular=True)
         self._mlp_ln([(ctx.m0, w["mu_w1a"]), (self.m_agg, w["mu_w1b"])], w["mu_b1"], w["mu_w2"], w["mu_b2"],
                      self.m_h, self.m_y, self.x, T[self.C_G2M_MU], residual=ctx.m0)
         if branch_stream is None:

@@ -162,15 +162,19 @@ def ln_cond(x: torch.Tensor, out: torch.Tensor, scale_offset: Optional[torch.Ten
     return out
 
 
-@_recorded("ln_cond_segment_sum", lambda y, out, so, rp, perm, **kw: (0.0, _nbytes(y, out, rp, perm)))
+@_recorded(lambda y, out, so, rp, perm, **kw: "ln_cond_segment_sum", lambda y, out, so, rp, perm, **kw: (0.0, _nbytes(y, out, rp, perm)))
 def ln_cond_segment_sum(y: torch.Tensor, out: torch.Tensor, scale_offset: Optional[torch.Tensor],
-                        row_ptr: torch.Tensor, edge_perm: Optional[torch.Tensor], *, layer_norm: bool = True):
+                        row_ptr: torch.Tensor, edge_perm: Optional[torch.Tensor], *, layer_norm: bool = True,
+                        irregular: bool = False):
+    """`irregular`: hint that segment lengths vary widely (grid2mesh: 3 .. 594 edges per mesh node); selects the
+    higher-occupancy kernel variant (GC_SEGSUM_IRREGULAR)."""
     lib = _lib.load()
     nseg, cols = out.shape
     if row_ptr.dtype != torch.int32 or row_ptr.numel() != nseg + 1:
         raise ValueError("row_ptr must be int32 [num_segments + 1]")
     _lib.check(lib.gc_ln_cond_segment_sum(_stream(), y.data_ptr(), _dt(y), _row_major(y, "y"), _p(scale_offset),
-                                          int(layer_norm), row_ptr.data_ptr(), _p(edge_perm), out.data_ptr(), _dt(out),
+                                          int(layer_norm) | (2 if irregular else 0), row_ptr.data_ptr(), _p(edge_perm),
+                                          out.data_ptr(), _dt(out),
                                           _row_major(out, "out"), nseg, cols), "gc_ln_cond_segment_sum")
     return out
 

@@ -130,8 +130,11 @@ GC_API int gc_ln_cond(void* stream, const void* x, int32_t x_dtype, int64_t ldx,
  * jraph.segment_sum (call sites common/typed_graph_net.py:173-182, f32
  * aggregation of common/deep_typed_graph_net.py:396-404).  The sum runs in
  * fp32 in a fixed order (no atomics) so results are bitwise reproducible.
- * edge_perm may be NULL (edges already receiver-sorted: mesh2grid).
+ * edge_perm may be NULL (edges already receiver-sorted: mesh2grid, and grid2mesh as the engine stores it).
+ * do_layer_norm: bit 0 = apply LayerNorm; bit 1 (GC_SEGSUM_IRREGULAR) = hint that segment lengths vary widely
+ * (selects the higher-occupancy kernel variant; implied by a non-NULL edge_perm).
  */
+#define GC_SEGSUM_IRREGULAR 2
 GC_API int gc_ln_cond_segment_sum(void* stream, const void* y, int32_t y_dtype, int64_t ldy,
                            const float* scale_offset, int32_t do_layer_norm,
                            const int32_t* row_ptr, const int32_t* edge_perm,
