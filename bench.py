@@ -477,6 +477,12 @@ def measure(args, config: str, MB: int, steps: int, warmup: int, dev, rank: int,
     roof["forward_exec_tflops_per_member"] = f_exec / MB / 1e12
     roof["forward_exec_tflops"] = f_exec / (res["denoiser_fwd_ms"] * 1e-3) / 1e12
     roof["forward_exec_frac_of_peak"] = roof["forward_exec_tflops"] / peaks["tensor_sustained"]
+    # the same GEMM shapes through cuBLAS (torch.matmul), back to back under the same power cap: how much of the gap
+    # to the 8192^3 peak is the shape (M x 512 x 512 problems are L2 / HBM fed) and how much the kernel
+    try:
+        roof["gemm_vs_cublas_same_shape"] = gemm_vs_cublas(eng, dev)
+    except Exception as e:                                   # a comparison, never a reason to lose the line
+        roof["gemm_vs_cublas_same_shape"] = {"error": str(e)[:200]}
     res["roofline"], res["kernels"] = roofline_clean(roof), kernels
 
     # ---- single denoiser evaluation latency (graph-free, events)
@@ -493,6 +499,38 @@ def measure(args, config: str, MB: int, steps: int, warmup: int, dev, rank: int,
     del model, se, eng, stats, flush, noises
     torch.cuda.empty_cache()
     return res
+
+
+def gemm_vs_cublas(eng, dev, seconds: float = 0.25):
+    """Sustained TFLOP/s of gc_gemm and of torch.matmul (cuBLAS) on the transformer / grid-MLP GEMM shapes of this
+    workload; cuBLAS is the comparison here, never on the product path."""
+    import torch
+    from gencast_flax_nnx_b200 import ops
+    L, F, V, G = eng.L, eng.F, eng.Vt, eng.Gt
+    out = {}
+    for name, m, n, k in (("qkv", V, 3 * L, L), ("out_proj", V, L, L), ("ffw_in", V, F, L), ("ffw_out", V, L, F), ("grid_mlp", G, L, L)):
+        a = torch.randn(m, k, device=dev).to(torch.bfloat16)
+        w = (torch.randn(n, k, device=dev) / 22.6).to(torch.bfloat16)
+        o = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
+        tf = {}
+        for impl, fn in (("gc_gemm", lambda: ops.gemm([(a, w)], o, static_weights=True)), ("cublas", lambda: torch.matmul(a, w.t(), out=o))):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            iters, start = 0, time.perf_counter()
+            t0.record()
+            while time.perf_counter() - start < seconds:
+                for _ in range(20):
+                    fn()
+                iters += 20
+                torch.cuda.synchronize()
+            t1.record()
+            torch.cuda.synchronize()
+            tf[impl] = 2.0 * m * n * k * iters / (t0.elapsed_time(t1) * 1e-3) / 1e12
+        out[name] = {"m": m, "n": n, "k": k, "gc_gemm_tflops": round(tf["gc_gemm"], 1), "cublas_tflops": round(tf["cublas"], 1),
+                     "ratio": round(tf["gc_gemm"] / tf["cublas"], 3)}
+    return out
 
 
 def algorithmic_flops(eng) -> float:
