@@ -18,39 +18,51 @@
 // receiver always belong to one epilogue warp.
 //   warp 0      TMA producer of W2 k-blocks (static weights: never waits for the predecessor grid)
 //   warp 1      MMA issuer (M = 128, N = min(L, 256) per instruction, L / 256 instructions per K step), TMEM owner
-//   warps 2-9   A producers: gather the three operand rows with 16-byte loads, add in fp32, activation, bf16,
-//               write the k-block into a 128B-swizzled K-major stage (the layout TMA would have produced)
+//   warps 2-9   A producers: sum the three operand rows in fp32, activation, bf16, write the k-block into a
+//               128B-swizzled K-major stage (the layout TMA would have produced)
+//   warp 18     (FAST) TMA loader of the two operands that are contiguous per tile, see below
 //   warps 10-17 epilogue, two per TMEM lane quarter (half of the columns each): pass 1 row statistics over
 //               acc + b2, pass 2 normalise, transpose 32-column chunks through a per-warp shared-memory patch,
 //               sum the three rows of each receiver, conditional affine, coalesced stores
-// The A ring (5 x 16 KB) and the W ring (3 x 32 KB) run ahead of the tensor core across tile boundaries, so the
-// gathers of tile t+1 proceed under the epilogue of tile t (the accumulator itself cannot be double buffered:
-// 128 x 512 fp32 is all of tensor memory).
+// The A ring and the W ring (3 x 32 KB) run ahead of the tensor core across tile boundaries, so the gathers of tile
+// t+1 proceed under the epilogue of tile t (the accumulator itself cannot be double buffered: 128 x 512 fp32 is all of
+// tensor memory).
+//
+// Operand feed.  With all three operands fetched through registers (12 x 16 B per thread and k-block, consumed before
+// the next k-block's loads are issued) a k-block costs one full load latency, ~2 000 clk under load, and 8 of them per
+// tile are more than the tile's MMA + epilogue time: 48 KB in flight per SM is what bounded the kernel.  In the FAST
+// instantiation (receivers' own rows: idx_r == null, and period a multiple of 30 edges) the `base` rows of a tile
+// quarter (30 consecutive table rows) and the receiver rows of the tile (40 consecutive rows) arrive by TMA straight
+// into the stage - base rows in the final swizzled position, where the producers finish them in place - up to four
+// k-blocks ahead, and only the sender rows are gathered through registers, two k-blocks ahead of their use.
 #include "common.cuh"
 #include "sm100.cuh"
 
 namespace gc {
 namespace {
 
-constexpr int EF_THREADS = 576;
+constexpr int EF_THREADS = 608;
 constexpr int EF_PRODUCER_WARPS = 8;
 constexpr int EF_EPI_WARPS = 8;
 constexpr int EF_RECV_PER_TILE = 40;
 constexpr int EF_A_STAGES = 5;
+constexpr int EF_GR_BYTES = EF_RECV_PER_TILE * 128;     // FAST: receiver rows of one k-block (40 x 64 bf16)
 constexpr int EF_W_STAGES = 3;
 constexpr int EF_A_STAGE_BYTES = 128 * 64 * 2;
 constexpr int EF_PATCH_STRIDE = 36;                     // floats per row of the transposition patch (32 + pad, 16 B aligned)
 constexpr int EF_PATCH_BYTES = 32 * EF_PATCH_STRIDE * 4;
 constexpr float EF_LN_EPS = 1e-6f;
 
-template <int L>
+template <int L, bool FAST = false>
 struct EFCfg {
   static constexpr int NI = L < 256 ? L : 256;          // columns per MMA instruction
   static constexpr int NH = L / NI;                     // instructions per K step
   static constexpr int KB = L / 64;                     // k-blocks (the hidden layer is L wide)
   static constexpr int W_STAGE_BYTES = NI * 64 * 2;
+  static constexpr int A_STAGES = FAST ? 4 : EF_A_STAGES;
+  static constexpr int A_STRIDE = EF_A_STAGE_BYTES + (FAST ? EF_GR_BYTES : 0);     // multiple of 1024 either way
   static constexpr int A_OFF = 0;
-  static constexpr int W_OFF = EF_A_STAGES * EF_A_STAGE_BYTES;
+  static constexpr int W_OFF = A_STAGES * A_STRIDE;
   static constexpr int PATCH_OFF = W_OFF + EF_W_STAGES * W_STAGE_BYTES;
   static constexpr int VEC_OFF = PATCH_OFF + EF_EPI_WARPS * EF_PATCH_BYTES;      // b2 [L] | scale [L] | offset [L] floats
   static constexpr int STAT_OFF = VEC_OFF + 3 * L * 4;                            // [2 halves][128 rows] float2
@@ -82,11 +94,13 @@ __device__ __forceinline__ int tile_of(const EdgeFusedParams& p, int slot) {
   return (slot % p.members) * p.tiles_per_member + slot / p.members;
 }
 
-template <int L>
+template <int L, bool FAST>
 __global__ void __launch_bounds__(EF_THREADS, 1)
-edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const EdgeFusedParams p) {
+edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant__ CUtensorMap base_map,
+                     const __grid_constant__ CUtensorMap gr_map, const EdgeFusedParams p) {
   using namespace sm100;
-  using C = EFCfg<L>;
+  using C = EFCfg<L, FAST>;
+  constexpr int A_STAGES = C::A_STAGES;
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -97,19 +111,25 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const EdgeFusedP
   float* vec_s = reinterpret_cast<float*>(smem_gen + C::VEC_OFF);
   float2* stat_s = reinterpret_cast<float2*>(smem_gen + C::STAT_OFF);
   auto a_full = [&](int s) { return bars + 8u * s; };
-  auto a_empty = [&](int s) { return bars + 8u * (EF_A_STAGES + s); };
-  auto w_full = [&](int s) { return bars + 8u * (2 * EF_A_STAGES + s); };
-  auto w_empty = [&](int s) { return bars + 8u * (2 * EF_A_STAGES + EF_W_STAGES + s); };
-  const uint32_t acc_full = bars + 8u * (2 * EF_A_STAGES + 2 * EF_W_STAGES);
+  auto a_empty = [&](int s) { return bars + 8u * (A_STAGES + s); };
+  auto w_full = [&](int s) { return bars + 8u * (2 * A_STAGES + s); };
+  auto w_empty = [&](int s) { return bars + 8u * (2 * A_STAGES + EF_W_STAGES + s); };
+  const uint32_t acc_full = bars + 8u * (2 * A_STAGES + 2 * EF_W_STAGES);
   const uint32_t acc_empty = acc_full + 8u;
   const uint32_t tmem_ptr_smem = acc_full + 16u;
+  auto raw_full = [&](int s) { return acc_full + 24u + 8u * s; };      // FAST: TMA-fed operands of stage s have landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&w_map);
-    for (int s = 0; s < EF_A_STAGES; ++s) { mbar_init(a_full(s), EF_PRODUCER_WARPS); mbar_init(a_empty(s), 1); }
+    if (FAST) { prefetch_tensormap(&base_map); prefetch_tensormap(&gr_map); }
+    for (int s = 0; s < A_STAGES; ++s) {
+      mbar_init(a_full(s), EF_PRODUCER_WARPS);
+      mbar_init(a_empty(s), 1);
+      mbar_init(raw_full(s), 1);
+    }
     for (int s = 0; s < EF_W_STAGES; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, EF_EPI_WARPS);
@@ -157,7 +177,7 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const EdgeFusedP
       tc_fence_after();
       for (int kb = 0; kb < C::KB; ++kb) {
         mbar_wait(a_full(sa), pa);
-        const uint64_t da = desc_kmajor_sw128(a_smem + sa * EF_A_STAGE_BYTES);
+        const uint64_t da = desc_kmajor_sw128(a_smem + sa * C::A_STRIDE);
         for (int h = 0; h < C::NH; ++h) {
           mbar_wait(w_full(sw), pw);
           tc_fence_after();
@@ -173,7 +193,7 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const EdgeFusedP
         }
         if (elect_one()) umma_commit(a_empty(sa));
         __syncwarp();
-        if (++sa == EF_A_STAGES) { sa = 0; pa ^= 1u; }
+        if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
       }
       if (elect_one()) umma_commit(acc_full);
       __syncwarp();
@@ -186,64 +206,172 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const EdgeFusedP
     pdl_wait();
     int sa = 0;
     uint32_t pa = 0;
-    for (int slot = blockIdx.x; slot < p.num_tiles; slot += gridDim.x) {
-      const int tile = tile_of(p, slot);
-      // rows of this thread: quarter j holds receivers 10 j .. 10 j + 9 of the tile
-      const __nv_bfloat16* pb[4];
-      const __nv_bfloat16* ps[4];
-      const __nv_bfloat16* pr[4];
-      bool valid[4];
+    if constexpr (FAST) {
+      // base and receiver rows are in the stage (TMA); sender rows come through registers, two k-blocks ahead
+      const int grow = i / 3;                      // receiver of this row inside its quarter
+      auto setup = [&](int slot, const __nv_bfloat16* (&ps)[4], uint32_t& vmask) {
+        vmask = 0u;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int64_t recv = static_cast<int64_t>(tile) * EF_RECV_PER_TILE + 10 * j + i / 3;
-        valid[j] = i < 30 && recv < p.num_receivers;
-        const int64_t e = static_cast<int64_t>(tile) * (3 * EF_RECV_PER_TILE) + 30 * j + i;
-        if (valid[j]) {
-          pb[j] = p.base + (e % p.period) * p.ld_base + u * 8;
-          ps[j] = p.gs + static_cast<int64_t>(__ldg(p.idx_s + e)) * p.ld_gs + u * 8;
-          pr[j] = p.gr + static_cast<int64_t>(__ldg(p.idx_r + e)) * p.ld_gr + u * 8;
-        } else {
-          pb[j] = ps[j] = pr[j] = p.base;
-        }
-      }
-      for (int kb = 0; kb < C::KB; ++kb) {
-        uint4 xb[4], xs[4], xr[4];
+        for (int j = 0; j < 4; ++j) ps[j] = p.gs;
+        if (slot < p.num_tiles) {
+          const int tile = tile_of(p, slot);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (valid[j]) {
-            xb[j] = __ldg(reinterpret_cast<const uint4*>(pb[j] + kb * 64));
-            xs[j] = __ldg(reinterpret_cast<const uint4*>(ps[j] + kb * 64));
-            xr[j] = __ldg(reinterpret_cast<const uint4*>(pr[j] + kb * 64));
-          }
-        }
-        if (lane == 0) mbar_wait(a_empty(sa), pa ^ 1u);
-        __syncwarp();
-        const uint32_t stage = a_smem + sa * EF_A_STAGE_BYTES;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 o = make_uint4(0u, 0u, 0u, 0u);
-          if (valid[j]) {
-            const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&xb[j]);
-            const __nv_bfloat162* hs = reinterpret_cast<const __nv_bfloat162*>(&xs[j]);
-            const __nv_bfloat162* hr = reinterpret_cast<const __nv_bfloat162*>(&xr[j]);
-            __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 fb = __bfloat1622float2(hb[k]), fs = __bfloat1622float2(hs[k]), fr = __bfloat1622float2(hr[k]);
-              float v0 = fb.x + fs.x + fr.x, v1 = fb.y + fs.y + fr.y;
-              v0 = apply_act<true>(v0, p.act);
-              v1 = apply_act<true>(v1, p.act);
-              ho[k] = __floats2bfloat162_rn(v0, v1);
+          for (int j = 0; j < 4; ++j) {
+            const int64_t recv = static_cast<int64_t>(tile) * EF_RECV_PER_TILE + 10 * j + grow;
+            if (i < 30 && recv < p.num_receivers) {
+              const int64_t e = static_cast<int64_t>(tile) * (3 * EF_RECV_PER_TILE) + 30 * j + i;
+              ps[j] = p.gs + static_cast<int64_t>(__ldg(p.idx_s + e)) * p.ld_gs + u * 8;
+              vmask |= 1u << j;
             }
           }
-          const uint32_t row = static_cast<uint32_t>(32 * j + i);
-          const uint32_t addr = stage + row * 128u + ((static_cast<uint32_t>(u) ^ (row & 7u)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
         }
-        fence_proxy_async_smem();                // generic-proxy stores -> visible to the tensor core's async-proxy reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_full(sa));
-        if (++sa == EF_A_STAGES) { sa = 0; pa ^= 1u; }
+      };
+      auto issue = [&](const __nv_bfloat16* const (&ps)[4], uint32_t vmask, int kb, uint4 (&x)[4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (vmask & (1u << j)) x[j] = __ldg(reinterpret_cast<const uint4*>(ps[j] + kb * 64));
+      };
+      const __nv_bfloat16* ps[4];
+      uint32_t vm;
+      uint4 xs[2][4];
+      setup(blockIdx.x, ps, vm);
+      issue(ps, vm, 0, xs[0]);
+      issue(ps, vm, 1, xs[1]);
+      for (int slot = blockIdx.x; slot < p.num_tiles; slot += gridDim.x) {
+        const __nv_bfloat16* pn[4];
+        uint32_t vn;
+        setup(slot + static_cast<int>(gridDim.x), pn, vn);
+#pragma unroll
+        for (int kb = 0; kb < C::KB; ++kb) {
+          uint4 (&cur)[4] = xs[kb & 1];
+          mbar_wait(raw_full(sa), pa);
+          const uint32_t stage = a_smem + sa * C::A_STRIDE;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t row = static_cast<uint32_t>(32 * j + i);
+            const uint32_t addr = stage + row * 128u + ((static_cast<uint32_t>(u) ^ (row & 7u)) << 4);
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (vm & (1u << j)) {
+              const uint32_t rr = static_cast<uint32_t>(10 * j + grow);
+              const uint32_t raddr = stage + EF_A_STAGE_BYTES + rr * 128u + ((static_cast<uint32_t>(u) ^ (rr & 7u)) << 4);
+              uint4 xb, xr;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xb.x), "=r"(xb.y), "=r"(xb.z), "=r"(xb.w) : "r"(addr));
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xr.x), "=r"(xr.y), "=r"(xr.z), "=r"(xr.w) : "r"(raddr));
+              const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&xb);
+              const __nv_bfloat162* hs = reinterpret_cast<const __nv_bfloat162*>(&cur[j]);
+              const __nv_bfloat162* hr = reinterpret_cast<const __nv_bfloat162*>(&xr);
+              __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 fb = __bfloat1622float2(hb[k]), fs = __bfloat1622float2(hs[k]), fr = __bfloat1622float2(hr[k]);
+                float v0 = fb.x + fs.x + fr.x, v1 = fb.y + fs.y + fr.y;
+                v0 = apply_act<true>(v0, p.act);
+                v1 = apply_act<true>(v1, p.act);
+                ho[k] = __floats2bfloat162_rn(v0, v1);
+              }
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+          }
+          fence_proxy_async_smem();                // generic-proxy stores -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_full(sa));
+          if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
+          // refill the register slot just consumed with the sender rows of k-block kb + 2 (of the next tile at the end)
+          if (kb + 2 < C::KB) issue(ps, vm, kb + 2, xs[kb & 1]);
+          else issue(pn, vn, kb + 2 - C::KB, xs[kb & 1]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ps[j] = pn[j];
+        vm = vn;
+      }
+    } else {
+      for (int slot = blockIdx.x; slot < p.num_tiles; slot += gridDim.x) {
+        const int tile = tile_of(p, slot);
+        // rows of this thread: quarter j holds receivers 10 j .. 10 j + 9 of the tile
+        const __nv_bfloat16* pb[4];
+        const __nv_bfloat16* ps[4];
+        const __nv_bfloat16* pr[4];
+        bool valid[4];
+  #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t recv = static_cast<int64_t>(tile) * EF_RECV_PER_TILE + 10 * j + i / 3;
+          valid[j] = i < 30 && recv < p.num_receivers;
+          const int64_t e = static_cast<int64_t>(tile) * (3 * EF_RECV_PER_TILE) + 30 * j + i;
+          if (valid[j]) {
+            pb[j] = p.base + (e % p.period) * p.ld_base + u * 8;
+            ps[j] = p.gs + static_cast<int64_t>(__ldg(p.idx_s + e)) * p.ld_gs + u * 8;
+            pr[j] = p.gr + (p.idx_r != nullptr ? static_cast<int64_t>(__ldg(p.idx_r + e)) : e / 3) * p.ld_gr + u * 8;
+          } else {
+            pb[j] = ps[j] = pr[j] = p.base;
+          }
+        }
+        for (int kb = 0; kb < C::KB; ++kb) {
+          uint4 xb[4], xs[4], xr[4];
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (valid[j]) {
+              xb[j] = __ldg(reinterpret_cast<const uint4*>(pb[j] + kb * 64));
+              xs[j] = __ldg(reinterpret_cast<const uint4*>(ps[j] + kb * 64));
+              xr[j] = __ldg(reinterpret_cast<const uint4*>(pr[j] + kb * 64));
+            }
+          }
+          if (lane == 0) mbar_wait(a_empty(sa), pa ^ 1u);
+          __syncwarp();
+          const uint32_t stage = a_smem + sa * C::A_STRIDE;
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (valid[j]) {
+              const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&xb[j]);
+              const __nv_bfloat162* hs = reinterpret_cast<const __nv_bfloat162*>(&xs[j]);
+              const __nv_bfloat162* hr = reinterpret_cast<const __nv_bfloat162*>(&xr[j]);
+              __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+  #pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 fb = __bfloat1622float2(hb[k]), fs = __bfloat1622float2(hs[k]), fr = __bfloat1622float2(hr[k]);
+                float v0 = fb.x + fs.x + fr.x, v1 = fb.y + fs.y + fr.y;
+                v0 = apply_act<true>(v0, p.act);
+                v1 = apply_act<true>(v1, p.act);
+                ho[k] = __floats2bfloat162_rn(v0, v1);
+              }
+            }
+            const uint32_t row = static_cast<uint32_t>(32 * j + i);
+            const uint32_t addr = stage + row * 128u + ((static_cast<uint32_t>(u) ^ (row & 7u)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+          }
+          fence_proxy_async_smem();                // generic-proxy stores -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_full(sa));
+          if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 2 + EF_PRODUCER_WARPS + EF_EPI_WARPS) {
+    // ---------------- (FAST) TMA loader: per k-block the base rows of the four tile quarters into their final place
+    // (quarter j = rows 32 j .. 32 j + 29 of the stage) and the 40 receiver rows behind the stage
+    if constexpr (FAST) {
+      pdl_wait();                                  // the receiver rows are the predecessor's output
+      int sa = 0;
+      uint32_t pa = 0;
+      for (int slot = blockIdx.x; slot < p.num_tiles; slot += gridDim.x) {
+        const int tile = tile_of(p, slot);
+        int b_row[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          b_row[j] = static_cast<int>((static_cast<int64_t>(tile) * (3 * EF_RECV_PER_TILE) + 30 * j) % p.period);
+        const int r_row = tile * EF_RECV_PER_TILE;
+        for (int kb = 0; kb < C::KB; ++kb) {
+          mbar_wait(a_empty(sa), pa ^ 1u);
+          if (elect_one()) {
+            const uint32_t stage = a_smem + sa * C::A_STRIDE;
+            mbar_arrive_expect_tx(raw_full(sa), 4 * 30 * 128 + EF_GR_BYTES);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_2d(stage + j * 4096, &base_map, raw_full(sa), kb * 64, b_row[j]);
+            tma_load_2d(stage + EF_A_STAGE_BYTES, &gr_map, raw_full(sa), kb * 64, r_row);
+          }
+          __syncwarp();
+          if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
+        }
       }
     }
   } else {
@@ -653,15 +781,27 @@ int launch_linear_ln(cudaStream_t st, const CUtensorMap& a_map, const CUtensorMa
   return GC_OK;
 }
 
-template <int L>
-int launch_edge_fused(cudaStream_t st, const CUtensorMap& w_map, const EdgeFusedParams& p) {
-  using C = EFCfg<L>;
-  GC_CHECK_CUDA(cudaFuncSetAttribute(edge_mlp_sum3_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM),
+// GENCAST_EDGE_TMA=0: all three operands through registers (the round-2 first version), for A/B measurements
+bool edge_tma_enabled() {
+  static const bool on = []() {
+    const char* v = getenv("GENCAST_EDGE_TMA");
+    return !(v != nullptr && v[0] == '0');
+  }();
+  return on;
+}
+
+template <int L, bool FAST>
+int launch_edge_fused(cudaStream_t st, const CUtensorMap& w_map, const CUtensorMap& base_map, const CUtensorMap& gr_map,
+                      const EdgeFusedParams& p) {
+  using C = EFCfg<L, FAST>;
+  static_assert(C::SMEM <= 232448, "edge_mlp_sum3_kernel: shared memory plan does not fit");
+  GC_CHECK_CUDA(cudaFuncSetAttribute(edge_mlp_sum3_kernel<L, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM),
                 "cudaFuncSetAttribute(edge_mlp_sum3_kernel)");
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = static_cast<unsigned>(p.num_tiles < sms ? p.num_tiles : sms);
-  GC_CHECK_CUDA(launch_kernel(edge_mlp_sum3_kernel<L>, dim3(grid), dim3(EF_THREADS), (size_t)C::SMEM, st, w_map, p),
+  GC_CHECK_CUDA(launch_kernel(edge_mlp_sum3_kernel<L, FAST>, dim3(grid), dim3(EF_THREADS), (size_t)C::SMEM, st, w_map, base_map,
+                              gr_map, p),
                 "edge_mlp_sum3_kernel");
   return GC_OK;
 }
@@ -704,7 +844,7 @@ extern "C" int gc_edge_mlp_sum3(void* stream, const void* base, int64_t ld_base,
                                 int32_t do_layer_norm, void* out, int32_t out_dtype, int64_t ldo, int64_t num_receivers,
                                 int32_t cols) {
   using namespace gc;
-  GC_REQUIRE(base && gs && idx_s && gr && idx_r && w2 && out, "gc_edge_mlp_sum3: null buffer");
+  GC_REQUIRE(base && gs && idx_s && gr && w2 && out, "gc_edge_mlp_sum3: null buffer");
   GC_REQUIRE(cols == 128 || cols == 256 || cols == 512, "gc_edge_mlp_sum3: cols=%d (supported: 128, 256, 512)", cols);
   GC_REQUIRE(period > 0 && num_receivers > 0 && num_receivers < (1LL << 31) / 3, "gc_edge_mlp_sum3: bad sizes");
   GC_REQUIRE(ld_base % 8 == 0 && ld_gs % 8 == 0 && ld_gr % 8 == 0 && ld_w2 % 8 == 0 && ldo % 8 == 0 && aligned16(base) &&
@@ -731,7 +871,19 @@ extern "C" int gc_edge_mlp_sum3(void* stream, const void* base, int64_t ld_base,
     }
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (cols == 128) return launch_edge_fused<128>(st, w_map, p);
-  if (cols == 256) return launch_edge_fused<256>(st, w_map, p);
-  return launch_edge_fused<512>(st, w_map, p);
+  // FAST: the tile's base rows and receiver rows are contiguous, so they travel by TMA (see the kernel's header)
+  const bool fast = idx_r == nullptr && period % 30 == 0 && edge_tma_enabled();
+  if (fast) {
+    CUtensorMap base_map, gr_map;
+    rc = make_tmap_bf16_2d(&base_map, base, (uint64_t)period, (uint64_t)cols, (uint64_t)ld_base, 64, 30);
+    if (rc != GC_OK) return rc;
+    rc = make_tmap_bf16_2d(&gr_map, gr, (uint64_t)num_receivers, (uint64_t)cols, (uint64_t)ld_gr, 64, EF_RECV_PER_TILE);
+    if (rc != GC_OK) return rc;
+    if (cols == 128) return launch_edge_fused<128, true>(st, w_map, base_map, gr_map, p);
+    if (cols == 256) return launch_edge_fused<256, true>(st, w_map, base_map, gr_map, p);
+    return launch_edge_fused<512, true>(st, w_map, base_map, gr_map, p);
+  }
+  if (cols == 128) return launch_edge_fused<128, false>(st, w_map, w_map, w_map, p);
+  if (cols == 256) return launch_edge_fused<256, false>(st, w_map, w_map, w_map, p);
+  return launch_edge_fused<512, false>(st, w_map, w_map, w_map, p);
 }

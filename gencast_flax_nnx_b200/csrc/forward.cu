@@ -181,7 +181,9 @@ extern "C" int gc_denoiser_forward(void* stream, const gc_denoiser_model* m, con
       base = ws->e_h;
       base_rows = E2;
     }
-    GC_TRY(gc_edge_mlp_sum3(st, base, L, base_rows, ws->m_p, g->m2g_senders, L, ws->g_p2, g->m2g_receivers, L, GC_ACT_SWISH,
+    // m2g_perm == NULL says the edges are stored grid-major, three per grid node: receiver of edge e = e / 3, which is
+    // what a null receiver table means to gc_edge_mlp_sum3 (its receiver rows then travel by TMA)
+    GC_TRY(gc_edge_mlp_sum3(st, base, L, base_rows, ws->m_p, g->m2g_senders, L, ws->g_p2, nullptr, L, GC_ACT_SWISH,
                             m->m2g_w2, L, m->m2g_b2, T(c_m2g_eu), 1, ws->g_agg, dt, L, G, L));
   } else {
     if (sc->m2g_base != nullptr) {

@@ -92,7 +92,8 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpilogueParams& ep, con
                                                    float alpha, uint32_t taddr, const float* bias_ptr, int64_t row0,
                                                    int col_base, int lane, uint32_t stage_smem, int& stage_use,
                                                    uint32_t gather_smem, WaitAcc wait_acc, Release release,
-                                                   long long* etrace = nullptr, int* etrace_ev = nullptr) {
+                                                   long long* etrace = nullptr, int* etrace_ev = nullptr,
+                                                   const int ncols = HALF) {
   using namespace sm100;
 #define GC_ESTAMP()                                                                                     \
   do {                                                                                                  \
@@ -152,14 +153,14 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpilogueParams& ep, con
   // copies of this body (~35 KB of SASS each way through the store modes) thrash the instruction cache
   // of an SM whose ten warps sit in different copies ('no_inst' stalls in the source-level profile).
 #pragma unroll 1
-  for (int c = 0; c < HALF; c += 32) {
+  for (int c = 0; c < ncols; c += 32) {
     float v[32];
     GC_ESTAMP();                 // chunk start
     tc_wait_ld();
     GC_ESTAMP();                 // accumulator chunk in registers
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-    if (c + 32 < HALF) {
+    if (c + 32 < ncols) {
       tmem_ld_32x32b_x32(taddr + c + 32, r);
     } else {
       tc_fence_before();
@@ -185,7 +186,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpilogueParams& ep, con
     if (gathers) {
       // this chunk's rows are in ga / gb; the next chunk's loads are issued before they are consumed
       uint4 na[4] = {}, nb[4] = {};
-      const bool more = c + 32 < HALF;
+      const bool more = c + 32 < ncols;
       if (more) gather_issue(ep.gsrc0, ep.ldg0, gi0, c + 32, na);
       gather_add(ga, v);
       if (has_g1) {
@@ -227,7 +228,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpilogueParams& ep, con
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + unit * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
                      "r"(pk[3]) : "memory");
       }
-      if (half_chunk == 1 || c + 32 >= HALF) {
+      if (half_chunk == 1 || c + 32 >= ncols) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -602,23 +603,41 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ GemmMaps maps, const
 // double-buffered accumulator and eight epilogue warps per CTA as above.
 // ---------------------------------------------------------------------------------------------
 constexpr int QBN = 256;                        // tile width (both CTAs)
-constexpr int Q_STAGES = 4;
 constexpr int Q_B_STAGE_BYTES = 128 * BK * 2;   // this CTA's half of the W tile
 constexpr int Q_STAGE_BYTES = A_STAGE_BYTES + Q_B_STAGE_BYTES;
-constexpr int Q_STAGING_OFFSET = Q_STAGES * Q_STAGE_BYTES;           // 8 warps x 2 x 4 KB store staging
-constexpr int Q_GATHER_OFFSET = Q_STAGING_OFFSET + 8 * 8192;       // 8 warps x 2 KB gather transposition
-constexpr int Q_BAR_OFFSET = Q_GATHER_OFFSET + 8 * 2048;
-constexpr int Q_BIAS_OFFSET = Q_BAR_OFFSET + 256;
-constexpr int Q_SMEM_BYTES = Q_BIAS_OFFSET + 2 * QBN * 4 + 1024;
+constexpr int SMEM_OPT_IN_MAX = 232448;         // 227 KB per CTA
+// Shared-memory plan: Q_STAGES operand stages of 32 KB | 8 warps x NBUF x 4 KB store staging | (GATHER) 8 warps x 2 KB
+// gather transposition | barriers | bias.  The operand ring is what bounds the kernel: a TMA load takes ~2 300 clk
+// from issue to arrival under load while the MMAs of one stage take 512, so the tensor pipe runs at
+// min(1, STAGES * 512 / 2 300) of its rate (measured: operands arrive in bursts of STAGES).
+template <int STAGES, int NBUF, bool GATHER>
+struct PairCfg {
+  static constexpr int Q_STAGES = STAGES;
+  static constexpr int STAGING_OFFSET = STAGES * Q_STAGE_BYTES;
+  static constexpr int GATHER_OFFSET = STAGING_OFFSET + 8 * NBUF * 4096;
+  static constexpr int BAR_OFFSET = GATHER_OFFSET + (GATHER ? 8 * 2048 : 0);
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;
+  static constexpr int USED_BYTES = BIAS_OFFSET + 2 * QBN * 4;
+  // slack for rounding the dynamic shared memory base up to 1024 B (the kernel traps if it does not suffice)
+  static constexpr int SLACK = USED_BYTES + 1024 <= SMEM_OPT_IN_MAX ? 1024 : SMEM_OPT_IN_MAX - USED_BYTES;
+  static constexpr int SMEM_BYTES = USED_BYTES + SLACK;
+  static_assert(SLACK >= 0, "pair kernel configuration does not fit in shared memory");
+};
 
+template <int STAGES, int NBUF, bool GATHER>
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmShape shape, const EpilogueParams ep,
-                              const int num_tiles, long long* trace) {
+                              const int full_units, const int num_units, long long* trace) {
   using namespace sm100;
   pdl_launch_dependents();
   constexpr int HALF = QBN / 2;                 // columns per epilogue warp
+  using C = PairCfg<STAGES, NBUF, GATHER>;
+  constexpr int Q_STAGES = C::Q_STAGES;
+  constexpr int Q_STAGING_OFFSET = C::STAGING_OFFSET, Q_GATHER_OFFSET = C::GATHER_OFFSET;
+  constexpr int Q_BAR_OFFSET = C::BAR_OFFSET, Q_BIAS_OFFSET = C::BIAS_OFFSET;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (smem_base - smem_u32(smem_raw) > static_cast<uint32_t>(C::SLACK)) __trap();
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + Q_STAGES * A_STAGE_BYTES;
@@ -635,6 +654,24 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmS
   const uint32_t rank = cluster_ctarank();      // 0 = leader
   const int pair_id = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
+  // Work units: the first `full_units` are the 256 x 256 tiles of the complete rounds (tile = unit).  The tiles of a
+  // last, partial round that would leave more than half of the pairs idle are issued as two 256 x 128 half-width units
+  // each (same A rows, half of the W rows), so that round takes half as long: 324 tiles on 74 pairs (the N = 512
+  // mesh-side GEMMs) are 4.5 rounds instead of 5.  Which columns a unit covers is a pure function of the problem size,
+  // so results stay bitwise reproducible.
+  auto decode = [&](int u, int& m_pair, int& col0, int& width) {
+    int tile = u;
+    width = QBN;
+    int sub = 0;
+    if (u >= full_units) {
+      const int h = u - full_units;
+      tile = full_units + (h >> 1);
+      sub = h & 1;
+      width = QBN / 2;
+    }
+    m_pair = tile / shape.n_tiles;
+    col0 = (tile % shape.n_tiles) * QBN + sub * (QBN / 2);
+  };
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < shape.num_segments; ++s) {
@@ -666,8 +703,10 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmS
   if (warp == 0) {
     // weights of the first ring pass before the wait for the predecessor grid (see the one-tile kernel)
     int pre = 0;
-    if (shape.early_w && pair_id < num_tiles) {
-      const int n_row0 = (pair_id % shape.n_tiles) * QBN + static_cast<int>(rank) * 128;
+    if (shape.early_w && pair_id < num_units) {
+      int m0, c0, w0;
+      decode(pair_id, m0, c0, w0);
+      const int n_row0 = c0 + static_cast<int>(rank) * (w0 / 2);
       for (int s = 0; s < shape.num_segments && pre < Q_STAGES; ++s)
         for (int kb = 0; kb < shape.kblocks[s] && pre < Q_STAGES; ++kb, ++pre) {
           if (elect_one()) {
@@ -681,10 +720,12 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmS
     int stage = 0, issued = 0;
     uint32_t phase = 0;
     int ev = 0;
-    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
-      const int n_blk = tile % shape.n_tiles, m_pair = tile / shape.n_tiles;
+    for (int unit = pair_id; unit < num_units; unit += num_pairs) {
+      int m_pair, col0, width;
+      decode(unit, m_pair, col0, width);
       const int m_row = m_pair * 256 + static_cast<int>(rank) * 128;
-      const int n_row = n_blk * QBN + static_cast<int>(rank) * 128;
+      // each CTA stages its half of the unit's W rows; the box is always 128 rows (a half-width unit uses the first 64)
+      const int n_row = col0 + static_cast<int>(rank) * (width / 2);
       for (int s = 0; s < shape.num_segments; ++s) {
         for (int kb = 0; kb < shape.kblocks[s]; ++kb, ++issued) {
           if (issued >= pre) {
@@ -706,12 +747,14 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmS
     }
   } else if (warp == 1) {
     if (rank == 0) {
-      constexpr uint32_t idesc = idesc_bf16_f32(256, QBN, 0, 0);
+      constexpr uint32_t idesc_full = idesc_bf16_f32(256, QBN, 0, 0);
+      constexpr uint32_t idesc_half = idesc_bf16_f32(256, QBN / 2, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int lt = 0;
       int mev = 0;
-      for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++lt) {
+      for (int unit = pair_id; unit < num_units; unit += num_pairs, ++lt) {
+        const uint32_t idesc = unit < full_units ? idesc_full : idesc_half;
         const int b = lt & 1;
         GC_GTRACE(1, 4 * lt);
         mbar_wait(acc_empty(b), ((lt >> 1) & 1) ^ 1u);      // both CTAs' epilogues have drained this buffer
@@ -748,32 +791,35 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmMaps maps, const GemmS
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     pdl_wait();
     const float alpha = ep.alpha_dev != nullptr ? __ldg(ep.alpha_dev) : 1.0f;
-    const uint32_t stage_smem = smem_base + Q_STAGING_OFFSET + static_cast<uint32_t>(warp - 2) * 8192u;
-    const uint32_t gather_smem = shape.gather_staged ? smem_base + Q_GATHER_OFFSET + static_cast<uint32_t>(warp - 2) * 2048u : 0u;
+    const uint32_t stage_smem = smem_base + Q_STAGING_OFFSET + static_cast<uint32_t>(warp - 2) * (NBUF * 4096u);
+    const uint32_t gather_smem = (GATHER && shape.gather_staged) ? smem_base + Q_GATHER_OFFSET + static_cast<uint32_t>(warp - 2) * 2048u : 0u;
     int stage_use = 0;
     int etrace_ev = 0;
     int lt = 0;
-    for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++lt) {
-      const int n_blk = tile % shape.n_tiles, m_pair = tile / shape.n_tiles;
+    for (int unit = pair_id; unit < num_units; unit += num_pairs, ++lt) {
+      int m_pair, col0, width;
+      decode(unit, m_pair, col0, width);
       const int b = lt & 1;
-      if (et < QBN) bias_s[b * QBN + et] = ep.bias != nullptr ? __ldg(ep.bias + n_blk * QBN + et) : 0.0f;
+      if (et < width) bias_s[b * QBN + et] = ep.bias != nullptr ? __ldg(ep.bias + col0 + et) : 0.0f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float* bias_ptr = ep.bias != nullptr ? bias_s + b * QBN + half * HALF : nullptr;
-      const int col_base = n_blk * QBN + half * HALF;
-      const uint32_t taddr = tmem_base + b * QBN + half * HALF + lane_addr;
+      const int wcols = width / 2;                 // columns per epilogue warp: 128, or 64 in a half-width unit
+      const float* bias_ptr = ep.bias != nullptr ? bias_s + b * QBN + half * wcols : nullptr;
+      const int col_base = col0 + half * wcols;
+      const uint32_t taddr = tmem_base + b * QBN + half * wcols + lane_addr;
       const uint32_t acc_bar = acc_empty(b), full_bar_b = acc_full(b);
       const uint32_t full_parity = (lt >> 1) & 1;
-      epilogue_warp_tile<HALF>(ep, &maps.out, shape.store_mode, alpha, taddr, bias_ptr,
-                               static_cast<int64_t>(m_pair) * 256 + rank * 128 + q * 32, col_base, lane, stage_smem, stage_use,
-                               gather_smem,
-                               [&]() {
-                                 if (threadIdx.x == 64) GC_GTRACE(2, 4 * lt);
-                                 mbar_wait(full_bar_b, full_parity);
-                                 if (threadIdx.x == 64) GC_GTRACE(2, 4 * lt + 1);
-                                 tc_fence_after();
-                               },
-                               [&]() { if (lane == 0) mbar_arrive_cluster(acc_bar, 0); },
-                               (trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64) ? trace : nullptr, &etrace_ev);
+      const int64_t row0 = static_cast<int64_t>(m_pair) * 256 + rank * 128 + q * 32;
+      auto wait_acc = [&]() {
+        if (threadIdx.x == 64) GC_GTRACE(2, 4 * lt);
+        mbar_wait(full_bar_b, full_parity);
+        if (threadIdx.x == 64) GC_GTRACE(2, 4 * lt + 1);
+        tc_fence_after();
+      };
+      auto release = [&]() { if (lane == 0) mbar_arrive_cluster(acc_bar, 0); };
+      long long* etr = (trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64) ? trace : nullptr;
+      // one instantiation for both widths: in a half-width unit each warp walks 64 columns instead of 128
+      epilogue_warp_tile<HALF, NBUF>(ep, &maps.out, shape.store_mode, alpha, taddr, bias_ptr, row0, col_base, lane, stage_smem, stage_use,
+                               gather_smem, wait_acc, release, etr, &etrace_ev, wcols);
       if (threadIdx.x == 64) GC_GTRACE(2, 4 * lt + 2);
     }
     if (lane == 0) bulk_wait_group_all();
@@ -1095,6 +1141,22 @@ bool pair_kernel_enabled() {
   return on;
 }
 
+bool tail_split_enabled() {
+  static const bool on = []() {
+    const char* v = getenv("GENCAST_GEMM_TAIL_SPLIT");
+    return !(v != nullptr && v[0] == '0');
+  }();
+  return on;
+}
+
+int pair_stages() {
+  static const int n = []() {
+    const char* v = getenv("GENCAST_GEMM_STAGES");
+    return (v != nullptr && v[0] >= '4' && v[0] <= '6') ? v[0] - '0' : 6;
+  }();
+  return n;
+}
+
 int launch_pair(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams& ep) {
   GemmMaps maps;
   GemmShape shape;
@@ -1117,17 +1179,23 @@ int launch_pair(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams
     const int rc = fill_out_map(maps, shape, a, true);
     if (rc != GC_OK) return rc;
   }
-  GC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES),
-                "cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel)");
   const int64_t num_tiles = ((a.m + 255) / 256) * shape.n_tiles;
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int64_t pairs = sms / 2;
-  if (num_tiles < pairs) pairs = num_tiles;
+  // tiles of a last round that would leave at least half of the pairs idle become two half-width units each
+  int64_t full_units = num_tiles, num_units = num_tiles;
+  if (tail_split_enabled() && num_tiles > pairs) {
+    const int64_t rest = num_tiles % pairs;
+    if (rest > 0 && 2 * rest <= pairs) {
+      full_units = num_tiles - rest;
+      num_units = full_units + 2 * rest;
+    }
+  }
+  if (num_units < pairs) pairs = num_units;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * pairs));
   cfg.blockDim = dim3(P_THREADS);
-  cfg.dynamicSmemBytes = Q_SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1136,9 +1204,20 @@ int launch_pair(cudaStream_t stream, const gc_gemm_args& a, const EpilogueParams
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  GC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_pair_kernel, maps, shape, ep, (int)num_tiles, g_gemm_trace),
-                "gemm_bf16_tcgen05_pair_kernel");
-  return GC_OK;
+  // ring depth: 6 stages (one staging buffer per warp, no gather transposition buffers) unless the epilogue gathers
+  // rows through shared memory, then 5; GENCAST_GEMM_STAGES=4 selects the round-1 layout (4 stages, 2 staging buffers)
+  const int stages = pair_stages();
+  auto launch = [&](auto kernel, int smem_bytes) -> int {
+    GC_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes),
+                  "cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel)");
+    cfg.dynamicSmemBytes = smem_bytes;
+    GC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, maps, shape, ep, (int)full_units, (int)num_units, g_gemm_trace),
+                  "gemm_bf16_tcgen05_pair_kernel");
+    return GC_OK;
+  };
+  if (stages <= 4) return launch(gemm_bf16_tcgen05_pair_kernel<4, 2, true>, PairCfg<4, 2, true>::SMEM_BYTES);
+  if (stages == 5 || shape.gather_staged) return launch(gemm_bf16_tcgen05_pair_kernel<5, 1, true>, PairCfg<5, 1, true>::SMEM_BYTES);
+  return launch(gemm_bf16_tcgen05_pair_kernel<6, 1, false>, PairCfg<6, 1, false>::SMEM_BYTES);
 }
 
 // Opt-in (GENCAST_GEMM_ARES=1): measured on B200 at M = 40 968 it halves the L2 -> SM operand bytes but is

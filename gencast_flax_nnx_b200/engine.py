@@ -718,7 +718,8 @@ class DenoiserEngine:
             base = ctx.m2g_base
             if base is None:
                 base = ops.gemm([(self.m2g_e_ln, ctx.m2g_w1e)], e_h, bias=ctx.m2g_b1)
-            ops.edge_mlp_sum3(base, [(self.m_p, self.m2g_s), (self.g_p2, self.m2g_r)], w["du_w2"], w["du_b2"],
+            # (m2g_perm is None = receiver of edge e is grid node e // 3: no receiver table needed)
+            ops.edge_mlp_sum3(base, [(self.m_p, self.m2g_s), (self.g_p2, None)], w["du_w2"], w["du_b2"],
                               T[self.C_M2G_EU], self.g_agg, act="swish")
         elif ctx.m2g_base is not None:
             ops.edge_hidden(ctx.m2g_base, [(self.m_p, self.m2g_s), (self.g_p2, self.m2g_r)], e_h, act="swish")

@@ -361,19 +361,23 @@ def edge_mlp_sum3(base: torch.Tensor, gathers: Sequence[Tuple[torch.Tensor, torc
                   b2: Optional[torch.Tensor], scale_offset: Optional[torch.Tensor], out: torch.Tensor, *,
                   act: Optional[str] = "swish", layer_norm: bool = True) -> torch.Tensor:
     """out[v] = scale * sum_{e in 3v..3v+2} LN(act(base[e % len(base)] + gs[idx_s[e]] + gr[idx_r[e]]) @ w2^T + b2) + 3 * offset
-    in one kernel (see gc_edge_mlp_sum3): the fused edge update + aggregation of a degree-3, receiver-major graph."""
+    in one kernel (see gc_edge_mlp_sum3): the fused edge update + aggregation of a degree-3, receiver-major graph.
+    idx_r=None: receiver v's row is gr[v] (then base / gr rows are moved by TMA when len(base) % 30 == 0)."""
     lib = _lib.load()
     (gs, idx_s), (gr, idx_r) = gathers
     if any(t.dtype != torch.bfloat16 for t in (base, gs, gr, w2)):
         raise TypeError("edge_mlp_sum3: bf16 operands expected")
     nrecv, cols = out.shape
-    if idx_s.dtype != torch.int32 or idx_r.dtype != torch.int32 or idx_s.numel() != 3 * nrecv or idx_r.numel() != 3 * nrecv:
+    if idx_s.dtype != torch.int32 or idx_s.numel() != 3 * nrecv or (
+            idx_r is not None and (idx_r.dtype != torch.int32 or idx_r.numel() != 3 * nrecv)):
         raise ValueError("edge_mlp_sum3: index tables must be int32 [3 * receivers]")
+    if idx_r is None and gr.shape[0] < nrecv:
+        raise ValueError("edge_mlp_sum3: idx_r=None means gr[v] is receiver v's row; gr has too few rows")
     if w2.shape != (cols, cols):
         raise ValueError("edge_mlp_sum3: w2 must be [cols, cols]")
     _lib.check(lib.gc_edge_mlp_sum3(_stream(), base.data_ptr(), _row_major(base, "base"), base.shape[0],
                                     gs.data_ptr(), idx_s.data_ptr(), _row_major(gs, "gs"),
-                                    gr.data_ptr(), idx_r.data_ptr(), _row_major(gr, "gr"), ACT[act],
+                                    gr.data_ptr(), _p(idx_r), _row_major(gr, "gr"), ACT[act],
                                     w2.data_ptr(), _row_major(w2, "w2"), _p(b2), _p(scale_offset), int(layer_norm),
                                     out.data_ptr(), _dt(out), _row_major(out, "out"), nrecv, cols), "gc_edge_mlp_sum3")
     return out

@@ -315,6 +315,8 @@ GC_API int gc_linear_ln_cond(void* stream, const void* a, int64_t lda, int64_t r
  * common/deep_typed_graph_net.py:396-410).  base / gs / gr / w2 are bf16; w2 is [cols, cols] stored [out, in];
  * b2 [cols] and scale_offset [2 cols] = (1 + s | o) are fp32 (either may be NULL); out is bf16 or fp32,
  * [num_receivers, cols]; idx_s / idx_r have 3 * num_receivers entries.  cols in {128, 256, 512}.
+ * idx_r == NULL means "the receiver's own row": gr[e / 3] (the mesh2grid case).  Then, when `period` is a multiple of
+ * 30, the base rows and the receiver rows of a tile are contiguous and are moved by TMA (only gs is gathered).
  */
 GC_API int gc_edge_mlp_sum3(void* stream, const void* base, int64_t ld_base, int64_t period, const void* gs,
                             const int32_t* idx_s, int64_t ld_gs, const void* gr, const int32_t* idx_r, int64_t ld_gr,

@@ -333,7 +333,8 @@ def test_khop_attention_gather_members_share_masks(cuda_device):
     assert torch.equal(out2[:n], single[0]) and torch.equal(out2[n:], single[1])
 
 
-@pytest.mark.parametrize("cols,nrecv,members", [(128, 37, 1), (256, 1000, 2), (512, 6000, 1), (512, 20000, 4)])
+@pytest.mark.parametrize("cols,nrecv,members", [(128, 37, 1), (128, 50, 3), (256, 1000, 2), (512, 6000, 1), (512, 20000, 4),
+                                                (512, 10512, 2)])
 @pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
 def test_edge_mlp_sum3_fused(cuda_device, cols, nrecv, members, out_dtype):
     """Fused degree-3 edge update + aggregation (gather-add-swish -> tcgen05 GEMM -> LayerNorm -> 3-row segment sum ->
@@ -371,6 +372,11 @@ def test_edge_mlp_sum3_fused(cuda_device, cols, nrecv, members, out_dtype):
     # the hidden layer is rounded to bf16 on both sides; MUFU swish differs from the exact one by < 1 bf16 ulp
     assert _rel(outs[0], ref) < (1.2e-2 if out_dtype == torch.bfloat16 else 8e-3)
     assert torch.equal(outs[0], outs[1])
+    # no receiver table = "receiver v's own row" (base / receiver rows by TMA when the period allows): the same bits
+    out = torch.full((R, cols), float("nan"), dtype=out_dtype, device=d)
+    ops.edge_mlp_sum3(base.to(d), [(gs.to(d), idx_s.to(d)), (gr.to(d), None)], w2.to(d), b2.to(d), so.to(d), out)
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), outs[0])
     # without LayerNorm / affine / bias: plain sum of the three second-layer outputs
     out = torch.empty(R, cols, dtype=torch.float32, device=d)
     ops.edge_mlp_sum3(base.to(d), [(gs.to(d), idx_s.to(d)), (gr.to(d), idx_r.to(d))], w2.to(d), None, None, out, layer_norm=False)

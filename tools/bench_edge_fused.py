@@ -29,7 +29,8 @@ rp = torch.arange(0, 3 * R + 1, 3, dtype=torch.int32, device=d)
 
 
 def fused():
-    ops.edge_mlp_sum3(base, [(gs, idx_s), (gr, idx_r)], w2, b2, so, out)
+    # no receiver table: receiver v's row is gr[v] (base / receiver rows by TMA; GENCAST_EDGE_TMA=0 = all through registers)
+    ops.edge_mlp_sum3(base, [(gs, idx_s), (gr, None)], w2, b2, so, out)
 
 
 def unfused():
