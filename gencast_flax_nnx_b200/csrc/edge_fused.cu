@@ -22,8 +22,8 @@
 //               128B-swizzled K-major stage (the layout TMA would have produced)
 //   warp 18     (FAST) TMA loader of the two operands that are contiguous per tile, see below
 //   warps 10-17 epilogue, two per TMEM lane quarter (half of the columns each): pass 1 row statistics over
-//               acc + b2, pass 2 normalise, transpose 32-column chunks through a per-warp shared-memory patch,
-//               sum the three rows of each receiver, conditional affine, coalesced stores
+//               acc + b2, pass 2 normalise, sum the three rows of each receiver with two lane shuffles per element,
+//               conditional affine, 64-byte row segments stored by the first lane of each receiver
 // The A ring and the W ring (3 x 32 KB) run ahead of the tensor core across tile boundaries, so the gathers of tile
 // t+1 proceed under the epilogue of tile t (the accumulator itself cannot be double buffered: 128 x 512 fp32 is all of
 // tensor memory).
@@ -39,7 +39,16 @@
 #include "sm100.cuh"
 
 namespace gc {
+
+long long* g_edge_fused_trace = nullptr;   // debug: clock stamps of CTA 0 (null in normal use)
+
 namespace {
+
+// Debug timeline: CTA 0 records clock64() at pipeline events into trace[role * 512 + index].
+#define GC_ETR(role, index)                                                                                       \
+  do {                                                                                                            \
+    if (p.trace != nullptr && blockIdx.x == 0 && (index) < 512) p.trace[(role) * 512 + (index)] = clock64();      \
+  } while (0)
 
 constexpr int EF_THREADS = 608;
 constexpr int EF_PRODUCER_WARPS = 8;
@@ -59,12 +68,13 @@ struct EFCfg {
   static constexpr int NH = L / NI;                     // instructions per K step
   static constexpr int KB = L / 64;                     // k-blocks (the hidden layer is L wide)
   static constexpr int W_STAGE_BYTES = NI * 64 * 2;
-  static constexpr int A_STAGES = FAST ? 4 : EF_A_STAGES;
+  static constexpr int A_STAGES = EF_A_STAGES;
   static constexpr int A_STRIDE = EF_A_STAGE_BYTES + (FAST ? EF_GR_BYTES : 0);     // multiple of 1024 either way
   static constexpr int A_OFF = 0;
   static constexpr int W_OFF = A_STAGES * A_STRIDE;
   static constexpr int PATCH_OFF = W_OFF + EF_W_STAGES * W_STAGE_BYTES;
-  static constexpr int VEC_OFF = PATCH_OFF + EF_EPI_WARPS * EF_PATCH_BYTES;      // b2 [L] | scale [L] | offset [L] floats
+  // the transposition patches are used by linear_ln_cond_kernel only (FAST = false there)
+  static constexpr int VEC_OFF = PATCH_OFF + (FAST ? 0 : EF_EPI_WARPS * EF_PATCH_BYTES);   // b2 [L] | scale [L] | offset [L] floats
   static constexpr int STAT_OFF = VEC_OFF + 3 * L * 4;                            // [2 halves][128 rows] float2
   static constexpr int BAR_OFF = STAT_OFF + 2 * 128 * 8;
   static constexpr int SMEM = BAR_OFF + 256 + 1024;
@@ -83,6 +93,7 @@ struct EdgeFusedParams {
   int64_t num_receivers;
   int num_tiles;
   int members, tiles_per_member;   // tile order: see tile_of()
+  long long* trace;
 };
 
 // Ensemble members evaluated together share the `base` table (period = one member's edges).  Walking the tiles member by
@@ -173,10 +184,14 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
     uint32_t pa = 0, pw = 0;
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+      GC_ETR(0, 3 * lt);
       mbar_wait(acc_empty, (static_cast<uint32_t>(lt) & 1u) ^ 1u);      // the epilogue has drained the accumulator
+      GC_ETR(0, 3 * lt + 1);
       tc_fence_after();
       for (int kb = 0; kb < C::KB; ++kb) {
         mbar_wait(a_full(sa), pa);
+        GC_ETR(1, lt * C::KB + kb);
+        if (FAST) fence_proxy_async_smem();        // the producers' generic-proxy stores -> the tensor core's async-proxy reads
         const uint64_t da = desc_kmajor_sw128(a_smem + sa * C::A_STRIDE);
         for (int h = 0; h < C::NH; ++h) {
           mbar_wait(w_full(sw), pw);
@@ -197,6 +212,7 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
       }
       if (elect_one()) umma_commit(acc_full);
       __syncwarp();
+      GC_ETR(0, 3 * lt + 2);
     }
   } else if (warp < 2 + EF_PRODUCER_WARPS) {
     // ---------------- A producers: thread = (16-byte unit u of the k-block row, rows i, 32 + i, 64 + i, 96 + i)
@@ -241,10 +257,14 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
         const __nv_bfloat16* pn[4];
         uint32_t vn;
         setup(slot + static_cast<int>(gridDim.x), pn, vn);
-#pragma unroll
+        // unrolled by two only (the register slot alternates): eight copies of this body are 100 KB of SASS and the
+        // warps then stall on instruction fetch ('no_inst' in the source-level profile)
+#pragma unroll 2
         for (int kb = 0; kb < C::KB; ++kb) {
           uint4 (&cur)[4] = xs[kb & 1];
+          if (threadIdx.x == 64) GC_ETR(2, 3 * ((slot / gridDim.x) * C::KB + kb));
           mbar_wait(raw_full(sa), pa);
+          if (threadIdx.x == 64) GC_ETR(2, 3 * ((slot / gridDim.x) * C::KB + kb) + 1);
           const uint32_t stage = a_smem + sa * C::A_STRIDE;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -272,9 +292,12 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
             }
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
           }
-          fence_proxy_async_smem();                // generic-proxy stores -> visible to the tensor core's async-proxy reads
+          // No proxy fence here: fence.proxy.async is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the MEMBAR would wait for
+          // this thread's prefetched sender rows (measured: 35 % of all stall samples, the prefetch bought nothing).  The
+          // MMA warp, which has no loads in flight, fences after its wait on a_full (release / acquire through the barrier).
           __syncwarp();
           if (lane == 0) mbar_arrive(a_full(sa));
+          if (threadIdx.x == 64) GC_ETR(2, 3 * ((slot / gridDim.x) * C::KB + kb) + 2);
           if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
           // refill the register slot just consumed with the sender rows of k-block kb + 2 (of the next tile at the end)
           if (kb + 2 < C::KB) issue(ps, vm, kb + 2, xs[kb & 1]);
@@ -381,7 +404,6 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
     const int half = ew >> 2;                            // which half of the columns (warps 10-13: q = 2,3,0,1; 14-17 again)
     constexpr int CH = L / 2;                            // columns per warp
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * CH;
-    float* patch = reinterpret_cast<float*>(smem_gen + C::PATCH_OFF + ew * EF_PATCH_BYTES);
     const int et = threadIdx.x - 32 * (2 + EF_PRODUCER_WARPS);     // 0 .. 255
     pdl_wait();
     for (int c = et; c < 3 * L; c += 32 * EF_EPI_WARPS) {
@@ -399,7 +421,9 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
     int lt = 0;
     for (int slot = blockIdx.x; slot < p.num_tiles; slot += gridDim.x, ++lt) {
       const int tile = tile_of(p, slot);
+      if (et == 0) GC_ETR(3, 4 * lt);
       mbar_wait(acc_full, static_cast<uint32_t>(lt) & 1u);
+      if (et == 0) GC_ETR(3, 4 * lt + 1);
       tc_fence_after();
       // ---- pass 1: row statistics of y = acc + b2 over this warp's half of the columns
       float s = 0.0f, ss = 0.0f;
@@ -424,22 +448,27 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
       }
       stat_s[half * 128 + q * 32 + lane] = make_float2(s, ss);
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et == 0) GC_ETR(3, 4 * lt + 2);
       float mean = 0.0f, rstd = 1.0f;
       if (p.do_ln) {
         const float2 o = stat_s[(half ^ 1) * 128 + q * 32 + lane];
         mean = (s + o.x) * inv_n;
         rstd = rsqrtf(fmaxf((ss + o.y) * inv_n - mean * mean, 0.0f) + EF_LN_EPS);
       }
-      // ---- pass 2: normalise, transpose a 32-column chunk through the patch, 3-row sums, affine, store
-      const int cp = lane & 15;                          // column pair of the chunk
-      const int rsel = lane >> 4;                        // which of two receivers per iteration
-      const int64_t recv0 = static_cast<int64_t>(tile) * EF_RECV_PER_TILE + 10 * q;
+      // ---- pass 2: normalise, sum the three rows of each receiver across lanes (rows 3 v .. 3 v + 2 sit in lanes
+      // 3 v .. 3 v + 2 of this warp), affine, store.  Two shuffles per element instead of a trip through a shared-memory
+      // patch: every element is independent, so the warp is never latency-bound on a store -> sync -> load chain.
+      const bool leader = lane < 30 && lane % 3 == 0;
+      const int64_t recv = static_cast<int64_t>(tile) * EF_RECV_PER_TILE + 10 * q + lane / 3;
+      const bool store = leader && recv < p.num_receivers;
       uint32_t r[32];
       tmem_ld_32x32b_x32(taddr, r);
 #pragma unroll 1
       for (int c = 0; c < CH; c += 32) {
         float v[32];
+        if (et == 0 && lt == 2) GC_ETR(4, 4 * (c >> 5));
         tc_wait_ld();
+        if (et == 0 && lt == 2) GC_ETR(4, 4 * (c >> 5) + 1);
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
         if (c + 32 < CH) {
@@ -453,34 +482,44 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
 #pragma unroll
         for (int k = 0; k < 32; k += 4) {
           const float4 b = *reinterpret_cast<const float4*>(b2s + c + k);
-          float4 x;
-          x.x = (v[k] + b.x - mean) * rstd; x.y = (v[k + 1] + b.y - mean) * rstd;
-          x.z = (v[k + 2] + b.z - mean) * rstd; x.w = (v[k + 3] + b.w - mean) * rstd;
-          *reinterpret_cast<float4*>(patch + lane * EF_PATCH_STRIDE + k) = x;
-        }
-        __syncwarp();
-        const float2 sc = *reinterpret_cast<const float2*>(scs + c + 2 * cp);
-        const float2 of = *reinterpret_cast<const float2*>(ofs + c + 2 * cp);
+          const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int it = 0; it < 5; ++it) {
-          const int vr = 2 * it + rsel;                  // receiver 0 .. 9 of this quarter
-          const float2 x0 = *reinterpret_cast<const float2*>(patch + (3 * vr) * EF_PATCH_STRIDE + 2 * cp);
-          const float2 x1 = *reinterpret_cast<const float2*>(patch + (3 * vr + 1) * EF_PATCH_STRIDE + 2 * cp);
-          const float2 x2 = *reinterpret_cast<const float2*>(patch + (3 * vr + 2) * EF_PATCH_STRIDE + 2 * cp);
-          const float o0 = fmaf((x0.x + x1.x) + x2.x, sc.x, 3.0f * of.x);
-          const float o1 = fmaf((x0.y + x1.y) + x2.y, sc.y, 3.0f * of.y);
-          const int64_t recv = recv0 + vr;
-          if (recv < p.num_receivers) {
-            const int64_t off = recv * p.ldo + half * CH + c + 2 * cp;
-            if (p.out_dtype == GC_BF16) {
-              *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = __floats2bfloat162_rn(o0, o1);
-            } else {
-              *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + off) = make_float2(o0, o1);
-            }
+          for (int j = 0; j < 4; ++j) {
+            const float x = (v[k + j] + bb[j] - mean) * rstd;
+            const float x1 = __shfl_down_sync(0xffffffffu, x, 1);
+            const float x2 = __shfl_down_sync(0xffffffffu, x, 2);
+            v[k + j] = (x + x1) + x2;
           }
         }
-        __syncwarp();
+        if (et == 0 && lt == 2) GC_ETR(4, 4 * (c >> 5) + 2);
+        if (store) {
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(scs + c + k);
+            const float4 of = *reinterpret_cast<const float4*>(ofs + c + k);
+            v[k] = fmaf(v[k], sc.x, 3.0f * of.x); v[k + 1] = fmaf(v[k + 1], sc.y, 3.0f * of.y);
+            v[k + 2] = fmaf(v[k + 2], sc.z, 3.0f * of.z); v[k + 3] = fmaf(v[k + 3], sc.w, 3.0f * of.w);
+          }
+          const int64_t off = recv * p.ldo + half * CH + c;
+          if (p.out_dtype == GC_BF16) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) {
+              uint4 o;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[k + 2 * j], v[k + 2 * j + 1]);
+              dst[k >> 3] = o;
+            }
+          } else {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) dst[k >> 2] = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+          }
+        }
+        if (et == 0 && lt == 2) GC_ETR(4, 4 * (c >> 5) + 3);
       }
+      if (et == 0) GC_ETR(3, 4 * lt + 3);
     }
   }
   tc_fence_before();
@@ -809,6 +848,10 @@ int launch_edge_fused(cudaStream_t st, const CUtensorMap& w_map, const CUtensorM
 }  // namespace
 }  // namespace gc
 
+extern "C" __attribute__((visibility("default"))) void gc_debug_set_edge_fused_trace(void* ptr) {
+  gc::g_edge_fused_trace = reinterpret_cast<long long*>(ptr);
+}
+
 extern "C" int gc_linear_ln_cond(void* stream, const void* a, int64_t lda, int64_t rows, const void* w, int64_t ldw, const float* bias,
                                  const float* scale_offset, int32_t do_layer_norm, const void* residual, int32_t res_dtype,
                                  int64_t ld_res, void* out, int32_t out_dtype, int64_t ldo, int32_t cols) {
@@ -863,6 +906,7 @@ extern "C" int gc_edge_mlp_sum3(void* stream, const void* base, int64_t ld_base,
   p.out = out; p.out_dtype = out_dtype; p.ldo = ldo; p.num_receivers = num_receivers;
   p.num_tiles = (int)((num_receivers + EF_RECV_PER_TILE - 1) / EF_RECV_PER_TILE);
   p.members = 1; p.tiles_per_member = p.num_tiles;
+  p.trace = g_edge_fused_trace;
   {
     const int64_t edges = 3 * num_receivers, per_tile = 3 * EF_RECV_PER_TILE;
     if (period < edges && edges % period == 0 && period % per_tile == 0) {

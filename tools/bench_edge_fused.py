@@ -50,3 +50,30 @@ for name, fn in (("fused", fused), ("three kernels", unfused)):
     b.record()
     torch.cuda.synchronize()
     print(f"{name}: {a.elapsed_time(b) / 10 * 1e3:.1f} us  ({B} members, {E} edges, L={L})")
+
+# ---- clock-stamp timeline of CTA 0 of the fused kernel (tiles blockIdx.x, + gridDim.x, ...)
+import ctypes
+
+from gencast_flax_nnx_b200 import _lib
+
+lib = _lib.load()
+trace = torch.zeros(8 * 512, dtype=torch.int64, device=d)
+lib.gc_debug_set_edge_fused_trace(ctypes.c_void_p(trace.data_ptr()))
+fused()
+torch.cuda.synchronize()
+lib.gc_debug_set_edge_fused_trace(ctypes.c_void_p(0))
+tr = trace.cpu().numpy().reshape(8, 512)
+t0 = tr[tr > 0].min()
+rel = lambda x: int(x - t0) if x > 0 else -1
+KB = L // 64
+nt = min(6, int((tr[0][2::3] > 0).sum()))
+print("tiles of CTA 0 shown:", nt, "(cycles since the first stamp)")
+print("MMA per tile (wait acc_empty start, acc free, all issued):", [(rel(tr[0][3 * i]), rel(tr[0][3 * i + 1]), rel(tr[0][3 * i + 2])) for i in range(nt)])
+print("MMA: k-block operands ready at:", [[rel(tr[1][i * KB + k]) for k in range(KB)] for i in range(nt)])
+print("producer warp 2 per k-block (wait TMA start, landed, stage signalled):")
+for i in range(nt):
+    print("   ", [(rel(tr[2][3 * (i * KB + k)]), rel(tr[2][3 * (i * KB + k) + 1]), rel(tr[2][3 * (i * KB + k) + 2])) for k in range(KB)])
+print("epilogue warp 10 per tile (wait acc start, acc arrived, statistics done, tile stored):",
+      [tuple(rel(tr[3][4 * i + j]) for j in range(4)) for i in range(nt)])
+print("epilogue warp 10, third tile, pass 2 per 32-column chunk (start, accumulator in registers, normalised + summed, stored):",
+      [tuple(rel(tr[4][4 * i + j]) for j in range(4)) for i in range(L // 64)])
