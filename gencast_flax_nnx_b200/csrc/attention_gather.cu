@@ -111,11 +111,16 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&v)[32], uint32_t mw, 
   }
 }
 
-template <int D>
+// TMA_ROWS: the K / V rows of a step are fetched by TMA row gathers (cp.async.bulk.tensor tile::gather4, four rows per
+// instruction, issued by one warp per stream) instead of 16-byte cp.async copies by four warps.
+template <int D, int ROWS>
 __global__ void __launch_bounds__(G_THREADS, 2)
-khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const GatherAttParams p) {
+khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap row_map,
+                             const GatherAttParams p) {
   using namespace sm100;
   using C = GCfg<D>;
+  constexpr bool TMA_K = ROWS != 0, TMA_V = ROWS == 1;     // which streams use TMA row gathers
+  constexpr bool TMA_ROWS = TMA_K;
   pdl_launch_dependents();
   if (threadIdx.x == 0) GC_GTR(6, 0);
   extern __shared__ uint8_t smem_raw[];
@@ -148,9 +153,11 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&q_map);
+    if (TMA_ROWS) prefetch_tensormap(&row_map);
     mbar_init(q_full, 1);
-    for (int s = 0; s < C::NK; ++s) { mbar_init(k_full(s), (G_LOADERS / 2) * 32); mbar_init(k_empty(s), 1); }
-    for (int s = 0; s < C::NV; ++s) { mbar_init(v_full(s), (G_LOADERS / 2) * 32); mbar_init(v_empty(s), 1); }
+    // "full" barriers: one arrive.expect_tx (TMA), or one arrival per copying lane (cp.async)
+    for (int s = 0; s < C::NK; ++s) { mbar_init(k_full(s), TMA_K ? 1u : (G_LOADERS / 2) * 32); mbar_init(k_empty(s), 1); }
+    for (int s = 0; s < C::NV; ++s) { mbar_init(v_full(s), TMA_V ? 1u : (G_LOADERS / 2) * 32); mbar_init(v_empty(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(p_full(b), 4); }
     mbar_init(pv_done, 1);
     mbar_init(o_full, 1);
@@ -195,8 +202,8 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
       GC_GTR(1, 2 * t);
       mbar_wait(k_full(kslot), kphase);
       GC_GTR(1, 2 * t + 1);
-      fence_proxy_async_smem();      // the gathered rows were written by cp.async (generic proxy), the MMA reads them
-      tc_fence_after();              // through the async proxy
+      if (!TMA_K) fence_proxy_async_smem();      // rows written by cp.async (generic proxy), read by the MMA (async proxy)
+      tc_fence_after();
       const uint64_t dk0 = desc_kmajor_sw128(k_smem + kslot * C::SLOT_BYTES);
       if (elect_one()) {
 #pragma unroll
@@ -221,7 +228,7 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
       GC_GTR(2, 3 * t + 1);
       mbar_wait(p_full(b), (t >> 1) & 1);
       GC_GTR(2, 3 * t + 2);
-      fence_proxy_async_smem();
+      if (!TMA_V) fence_proxy_async_smem();
       tc_fence_after();
       // A: P[128 x 16 keys] from tensor memory (lane = query row, 8 columns of two bf16 each);
       // B: V[16 keys x D], MN-major: 16 key rows of 128 B start at j * 2048, 64-wide d chunks GS * 128 B apart
@@ -370,58 +377,90 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
       }
     }
   } else {
-    // ---------------- K / V row gather.  Warps 5, 6 fetch the K tiles (32 rows each), warps 7, 8 the V tiles: two
-    // independent streams, so a K tile is requested the moment its slot frees (S_t formed) and never queues behind a
-    // V tile whose slot only frees when P_{t-2} V_{t-2} has completed.
-    constexpr int UNITS = D / 8;                 // 16-byte units per row
-    constexpr int RPI = 32 / UNITS;              // rows per warp instruction
-    constexpr int ITER = 32 / RPI;
-    const int lw = (warp - 5) & 1;               // which half of the tile's rows
+    // ---------------- K / V row gather: two independent streams, so a K tile is requested the moment its slot frees
+    // (S_t formed) and never queues behind a V tile whose slot only frees when P_{t-2} V_{t-2} has completed.
+    // cp.async variant: warps 5, 6 fetch the K tiles (32 rows each), warps 7, 8 the V tiles.
     const bool v_stream = warp >= 7;
-    const int unit = lane % UNITS;
-    const int row_in = lane / UNITS;
-    const uint32_t dst_unit = static_cast<uint32_t>(unit >> 3) * (GS * 128);   // 64-wide d chunk of this unit
-    const uint32_t u8 = static_cast<uint32_t>(unit & 7);
     pdl_wait();                                  // qkv is the predecessor's output
     int ld_ev = 0;
-    auto key_of = [&](int t, int rl) -> int64_t {
-      if (t < G_MAX_STAGED_STEPS) return keys_s[t * GS + rl];
-      return __ldg(p.keys + (static_cast<int64_t>(s_beg) + t) * GS + rl);
-    };
-    // A gather warp never waits for its own copies: every lane's cp.async.mbarrier.arrive.noinc makes the tile's
-    // "full" barrier count that lane's copies when they land.  (Waiting with cp.async.wait_group and arriving with a
-    // plain mbarrier.arrive costs a MEMBAR.ALL that also waits for the NEXT tile's copies issued just before: one tile
-    // in flight per warp and 2 700 clk from issue to signal, which made the softmax warps wait for S half of the time.)
-    auto produce = [&](uint32_t empty_bar, uint32_t parity, uint32_t full_bar, uint32_t slot_base, int col0, int t) {
-      if (lane == 0) mbar_wait(empty_bar, parity);
-      __syncwarp();
-      if (lane == 0 && lw == 0) { GC_GTR(v_stream ? 5 : 0, ld_ev); ++ld_ev; }
-#pragma unroll
-      for (int i = 0; i < ITER; ++i) {
-        const int rl = lw * 32 + i * RPI + row_in;
-        const int64_t key = key_of(t, rl);
-        const __nv_bfloat16* src = p.qkv + key * p.ld_qkv + col0 + unit * 8;
-        const uint32_t dst = slot_base + dst_unit + static_cast<uint32_t>(rl) * 128u + ((u8 ^ (static_cast<uint32_t>(rl) & 7u)) << 4);
-        cp_async_16(dst, src);
-      }
-      cp_async_arrive_noinc(full_bar);
-    };
     const int k_col = p.hd + head * D;
     const int v_col = 2 * p.hd + head * D;
-    int kslot = 0, vslot = 0;
-    uint32_t kphase = 0, vphase = 0;
-    auto load_k = [&](int t) {
-      produce(k_empty(kslot), kphase ^ 1u, k_full(kslot), k_smem + kslot * C::SLOT_BYTES, k_col, t);
-      if (++kslot == C::NK) { kslot = 0; kphase ^= 1u; }
-    };
-    auto load_v = [&](int t) {
-      produce(v_empty(vslot), vphase ^ 1u, v_full(vslot), v_smem + vslot * C::SLOT_BYTES, v_col, t);
-      if (++vslot == C::NV) { vslot = 0; vphase ^= 1u; }
-    };
-    if (v_stream) {
-      for (int t = 0; t < T; ++t) load_v(t);
+    if ((v_stream && TMA_V) || (!v_stream && TMA_K)) {
+      // Warp 5 feeds the K ring, warp 7 the V ring (6 and 8 have nothing to do).  Lane = (64-wide d chunk, group of four
+      // consecutive key slots): one gather4 per lane puts its four rows at rows 4 g .. 4 g + 3 of the chunk's block, in
+      // the same swizzled layout the MMA descriptors expect, so a whole tile is requested by one warp-wide instruction.
+      if (warp == 5 || warp == 7) {
+        constexpr int GROUPS = GS / 4;             // 16
+        const int grp = lane % GROUPS, chunk = lane / GROUPS;
+        const bool active = chunk < C::CHUNKS;
+        const int col = (v_stream ? v_col : k_col) + 64 * chunk;
+        const uint32_t dst_off = static_cast<uint32_t>(chunk) * (GS * 128) + static_cast<uint32_t>(grp) * 512u;
+        int slot = 0;
+        uint32_t phase = 0;
+        constexpr int NSLOT = C::NK;               // NK == NV
+        for (int t = 0; t < T; ++t) {
+          int4 kk = make_int4(0, 0, 0, 0);
+          if (active) {
+            if (t < G_MAX_STAGED_STEPS) kk = *reinterpret_cast<const int4*>(keys_s + t * GS + 4 * grp);
+            else kk = __ldg(reinterpret_cast<const int4*>(p.keys + (static_cast<int64_t>(s_beg) + t) * GS) + grp);
+          }
+          const uint32_t empty = v_stream ? v_empty(slot) : k_empty(slot);
+          const uint32_t full = v_stream ? v_full(slot) : k_full(slot);
+          const uint32_t base_s = (v_stream ? v_smem : k_smem) + slot * C::SLOT_BYTES;
+          mbar_wait(empty, phase ^ 1u);
+          if (lane == 0) { GC_GTR(v_stream ? 5 : 0, ld_ev); ++ld_ev; }
+          if (lane == 0) mbar_arrive_expect_tx(full, C::SLOT_BYTES);
+          __syncwarp();
+          if (active) tma_gather4_2d(base_s + dst_off, &row_map, full, col, kk.x, kk.y, kk.z, kk.w);
+          if (++slot == NSLOT) { slot = 0; phase ^= 1u; }
+        }
+      }
     } else {
-      for (int t = 0; t < T; ++t) load_k(t);
+      constexpr int UNITS = D / 8;                 // 16-byte units per row
+      constexpr int RPI = 32 / UNITS;              // rows per warp instruction
+      constexpr int ITER = 32 / RPI;
+      const int lw = (warp - 5) & 1;               // which half of the tile's rows
+      const int unit = lane % UNITS;
+      const int row_in = lane / UNITS;
+      const uint32_t dst_unit = static_cast<uint32_t>(unit >> 3) * (GS * 128);   // 64-wide d chunk of this unit
+      const uint32_t u8 = static_cast<uint32_t>(unit & 7);
+      auto key_of = [&](int t, int rl) -> int64_t {
+        if (t < G_MAX_STAGED_STEPS) return keys_s[t * GS + rl];
+        return __ldg(p.keys + (static_cast<int64_t>(s_beg) + t) * GS + rl);
+      };
+      // A gather warp never waits for its own copies: every lane's cp.async.mbarrier.arrive.noinc makes the tile's
+      // "full" barrier count that lane's copies when they land.  (Waiting with cp.async.wait_group and arriving with a
+      // plain mbarrier.arrive costs a MEMBAR.ALL that also waits for the NEXT tile's copies issued just before: one tile
+      // in flight per warp and 2 700 clk from issue to signal, which made the softmax warps wait for S half of the time.)
+      auto produce = [&](uint32_t empty_bar, uint32_t parity, uint32_t full_bar, uint32_t slot_base, int col0, int t) {
+        if (lane == 0) mbar_wait(empty_bar, parity);
+        __syncwarp();
+        if (lane == 0 && lw == 0) { GC_GTR(v_stream ? 5 : 0, ld_ev); ++ld_ev; }
+  #pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+          const int rl = lw * 32 + i * RPI + row_in;
+          const int64_t key = key_of(t, rl);
+          const __nv_bfloat16* src = p.qkv + key * p.ld_qkv + col0 + unit * 8;
+          const uint32_t dst = slot_base + dst_unit + static_cast<uint32_t>(rl) * 128u + ((u8 ^ (static_cast<uint32_t>(rl) & 7u)) << 4);
+          cp_async_16(dst, src);
+        }
+        cp_async_arrive_noinc(full_bar);
+      };
+      int kslot = 0, vslot = 0;
+      uint32_t kphase = 0, vphase = 0;
+      auto load_k = [&](int t) {
+        produce(k_empty(kslot), kphase ^ 1u, k_full(kslot), k_smem + kslot * C::SLOT_BYTES, k_col, t);
+        if (++kslot == C::NK) { kslot = 0; kphase ^= 1u; }
+      };
+      auto load_v = [&](int t) {
+        produce(v_empty(vslot), vphase ^ 1u, v_full(vslot), v_smem + vslot * C::SLOT_BYTES, v_col, t);
+        if (++vslot == C::NV) { vslot = 0; vphase ^= 1u; }
+      };
+      if (v_stream) {
+        for (int t = 0; t < T; ++t) load_v(t);
+      } else {
+        for (int t = 0; t < T; ++t) load_k(t);
+      }
     }
   }
   if (threadIdx.x == 32) GC_GTR(4, 2);
@@ -431,13 +470,29 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const Ga
   if (threadIdx.x == 0) GC_GTR(4, 3);
 }
 
-template <int D>
-int launch_gather(cudaStream_t st, const CUtensorMap& map, const GatherAttParams& p, int num_q_tiles) {
+// How the K / V rows of a step reach shared memory.  GENCAST_ATT_ROWS = cpasync (default): 16-byte cp.async copies by
+// four gather warps; tma: TMA row gathers (tile::gather4) for both streams, one warp each; split: K by TMA, V by cp.async.
+// Measured on B200 at 1 deg x 4 members (3 628 steps x 4 heads): 115.6 / 117.7 / 121.2 us - the same within noise.  A
+// gather4 costs its issuing warp ~80 clk (32 of them = one K tile block the loader for ~2 500 clk), i.e. the TMA unit
+// takes ~20 clk per 128-byte row; either way a 16 KB tile of 256-byte row pieces arrives ~3 000 clk after it is
+// requested and the kernel moves 475 MB of such pieces per launch (4 TB/s out of L2): that traffic is the floor.
+int rows_mode() {
+  static const int mode = []() {
+    const char* v = getenv("GENCAST_ATT_ROWS");
+    if (v != nullptr && v[0] == 't') return 1;
+    if (v != nullptr && v[0] == 's') return 2;
+    return 0;
+  }();
+  return mode;
+}
+
+template <int D, int ROWS>
+int launch_gather(cudaStream_t st, const CUtensorMap& map, const CUtensorMap& row_map, const GatherAttParams& p, int num_q_tiles) {
   using C = GCfg<D>;
-  cudaError_t e = cudaFuncSetAttribute(khop_attention_gather_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+  cudaError_t e = cudaFuncSetAttribute(khop_attention_gather_kernel<D, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(khop_attention_gather_kernel)");
-  GC_CHECK_CUDA(launch_kernel(khop_attention_gather_kernel<D>, dim3(num_q_tiles * p.heads), dim3(G_THREADS), (size_t)C::SMEM, st,
-                              map, p), "khop_attention_gather_kernel");
+  GC_CHECK_CUDA(launch_kernel(khop_attention_gather_kernel<D, ROWS>, dim3(num_q_tiles * p.heads), dim3(G_THREADS), (size_t)C::SMEM,
+                              st, map, row_map, p), "khop_attention_gather_kernel");
   return GC_OK;
 }
 
@@ -475,6 +530,18 @@ extern "C" int gc_khop_attention_gather(void* stream, const void* qkv, int64_t l
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)head_dim);
   p.trace = g_attention_gather_trace;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (head_dim == 64) return launch_gather<64>(st, map, p, num_q_tiles);
-  return launch_gather<128>(st, map, p, num_q_tiles);
+  const int mode = rows_mode();
+  CUtensorMap row_map = map;
+  if (mode != 0) {           // one row of 64 columns per box: the unit of a gather4 request
+    rc = make_tmap_bf16_2d(&row_map, qkv, (uint64_t)nodes, (uint64_t)(3LL * heads * head_dim), (uint64_t)ld_qkv, 64, 1);
+    if (rc != GC_OK) return rc;
+  }
+  if (head_dim == 64) {
+    if (mode == 0) return launch_gather<64, 0>(st, map, row_map, p, num_q_tiles);
+    if (mode == 1) return launch_gather<64, 1>(st, map, row_map, p, num_q_tiles);
+    return launch_gather<64, 2>(st, map, row_map, p, num_q_tiles);
+  }
+  if (mode == 0) return launch_gather<128, 0>(st, map, row_map, p, num_q_tiles);
+  if (mode == 1) return launch_gather<128, 1>(st, map, row_map, p, num_q_tiles);
+  return launch_gather<128, 2>(st, map, row_map, p, num_q_tiles);
 }

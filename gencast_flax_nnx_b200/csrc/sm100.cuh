@@ -88,6 +88,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
       : "memory");
 }
 
+// Row gather: four rows r0..r3 of a 2D tensor (tensor map with a {box_cols, 1} box), the box_cols elements starting at
+// column c0 of each, land in four consecutive box-sized rows of shared memory (128B swizzle by address as usual) and
+// count 4 * box bytes on the barrier.  Verified on B200 with tools/experiments/try_gather4.cu.
+__device__ __forceinline__ void tma_gather4_2d(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int c0, int r0, int r1,
+                                               int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+
 // ----------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
