@@ -105,6 +105,7 @@ class DenoiserWorkspace(Structure):
 GC_ATTENTION_CSR, GC_ATTENTION_TILES, GC_ATTENTION_GATHER = 0, 1, 2
 GC_FORWARD_FUSE_M2G = 1
 GC_FORWARD_FUSE_LN = 2
+GC_FORWARD_FUSE_G2M = 4
 FORWARD_STRUCTS = (DenoiserModel, DenoiserGraph, SigmaContextC, DenoiserWorkspace, Mlp2, TransformerLayer)
 
 # name -> (restype, argtypes); also the list of symbols tests check for.
@@ -145,6 +146,8 @@ SIGNATURES = {
     "gc_edge_mlp_sum3": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                    c_int64, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_int32,
                                    c_int64, c_int64, c_int32]),
+    "gc_edge_mlp_rows": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int64,
+                                   c_void_p, c_void_p, c_int64, c_int64, c_int32]),
     "gc_denoiser_forward": (c_int32, [c_void_p, POINTER(DenoiserModel), POINTER(DenoiserGraph), POINTER(SigmaContextC),
                                       POINTER(DenoiserWorkspace)]),
     "gc_sizeof_forward_structs": (c_int32, [c_int32]),

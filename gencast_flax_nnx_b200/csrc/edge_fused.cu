@@ -62,19 +62,22 @@ constexpr int EF_PATCH_STRIDE = 36;                     // floats per row of the
 constexpr int EF_PATCH_BYTES = 32 * EF_PATCH_STRIDE * 4;
 constexpr float EF_LN_EPS = 1e-6f;
 
-template <int L, bool FAST = false>
+// MODE 0: all operands through registers; 1 (FAST): base / receiver rows by TMA (degree-3 tiles of 40 receivers);
+// 2 (ROWS): tiles of 128 consecutive edges of one member, base rows by TMA, one gather, plain row output (gc_edge_mlp_rows)
+template <int L, int MODE = 0>
 struct EFCfg {
+  static constexpr bool FAST = MODE != 0;
   static constexpr int NI = L < 256 ? L : 256;          // columns per MMA instruction
   static constexpr int NH = L / NI;                     // instructions per K step
   static constexpr int KB = L / 64;                     // k-blocks (the hidden layer is L wide)
   static constexpr int W_STAGE_BYTES = NI * 64 * 2;
   static constexpr int A_STAGES = EF_A_STAGES;
-  static constexpr int A_STRIDE = EF_A_STAGE_BYTES + (FAST ? EF_GR_BYTES : 0);     // multiple of 1024 either way
+  static constexpr int A_STRIDE = EF_A_STAGE_BYTES + (MODE == 1 ? EF_GR_BYTES : 0);   // multiple of 1024 either way
   static constexpr int A_OFF = 0;
   static constexpr int W_OFF = A_STAGES * A_STRIDE;
   static constexpr int PATCH_OFF = W_OFF + EF_W_STAGES * W_STAGE_BYTES;
-  // the transposition patches are used by linear_ln_cond_kernel only (FAST = false there)
-  static constexpr int VEC_OFF = PATCH_OFF + (FAST ? 0 : EF_EPI_WARPS * EF_PATCH_BYTES);   // b2 [L] | scale [L] | offset [L] floats
+  // MODE 0: the transposition patches of linear_ln_cond_kernel; MODE 2: one 4 KB TMA-store staging buffer per epilogue warp
+  static constexpr int VEC_OFF = PATCH_OFF + (MODE == 0 ? EF_EPI_WARPS * EF_PATCH_BYTES : MODE == 2 ? EF_EPI_WARPS * 4096 : 0);   // b2 [L] | scale [L] | offset [L] floats
   static constexpr int STAT_OFF = VEC_OFF + 3 * L * 4;                            // [2 halves][128 rows] float2
   static constexpr int BAR_OFF = STAT_OFF + 2 * 128 * 8;
   static constexpr int SMEM = BAR_OFF + 256 + 1024;
@@ -93,6 +96,7 @@ struct EdgeFusedParams {
   int64_t num_receivers;
   int num_tiles;
   int members, tiles_per_member;   // tile order: see tile_of()
+  int64_t num_rows;                // ROWS mode: members * period edges
   long long* trace;
 };
 
@@ -105,12 +109,13 @@ __device__ __forceinline__ int tile_of(const EdgeFusedParams& p, int slot) {
   return (slot % p.members) * p.tiles_per_member + slot / p.members;
 }
 
-template <int L, bool FAST>
+template <int L, int MODE>
 __global__ void __launch_bounds__(EF_THREADS, 1)
 edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant__ CUtensorMap base_map,
                      const __grid_constant__ CUtensorMap gr_map, const EdgeFusedParams p) {
   using namespace sm100;
-  using C = EFCfg<L, FAST>;
+  using C = EFCfg<L, MODE>;
+  constexpr bool FAST = MODE != 0, ROWS = MODE == 2;
   constexpr int A_STAGES = C::A_STAGES;
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
@@ -135,7 +140,8 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&w_map);
-    if (FAST) { prefetch_tensormap(&base_map); prefetch_tensormap(&gr_map); }
+    if (FAST) prefetch_tensormap(&base_map);
+    if (MODE != 0) prefetch_tensormap(&gr_map);     // MODE 2: this slot carries the tensor map of the output rows
     for (int s = 0; s < A_STAGES; ++s) {
       mbar_init(a_full(s), EF_PRODUCER_WARPS);
       mbar_init(a_empty(s), 1);
@@ -231,13 +237,32 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
         for (int j = 0; j < 4; ++j) ps[j] = p.gs;
         if (slot < p.num_tiles) {
           const int tile = tile_of(p, slot);
+          if constexpr (ROWS) {
+            // row 32 j + i of the tile = edge (tile % tiles_per_member) * 128 + 32 j + i of member tile / tiles_per_member
+            const int64_t member = tile / p.tiles_per_member;
+            const int64_t local0 = static_cast<int64_t>(tile % p.tiles_per_member) * 128 + i;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int64_t recv = static_cast<int64_t>(tile) * EF_RECV_PER_TILE + 10 * j + grow;
-            if (i < 30 && recv < p.num_receivers) {
-              const int64_t e = static_cast<int64_t>(tile) * (3 * EF_RECV_PER_TILE) + 30 * j + i;
-              ps[j] = p.gs + static_cast<int64_t>(__ldg(p.idx_s + e)) * p.ld_gs + u * 8;
-              vmask |= 1u << j;
+            for (int j = 0; j < 4; ++j) {
+              const int64_t local = local0 + 32 * j;
+              if (local < p.period) {
+                const __nv_bfloat16* row = p.gs + static_cast<int64_t>(__ldg(p.idx_s + member * p.period + local)) * p.ld_gs;
+                ps[j] = row + u * 8;
+                vmask |= 1u << j;
+                // The sender table (all members' grid nodes: 267 MB at 1 deg x 4) does not live in L2 and a k-block only
+                // touches 128 bytes of a row: without this, each of the 8 slices of a row is its own DRAM access at use
+                // time.  The setup runs a tile ahead: the 8 threads of a row pull its 8 lines into L2 now.
+                if (u * 64 < L) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + u * 64));
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int64_t recv = static_cast<int64_t>(tile) * EF_RECV_PER_TILE + 10 * j + grow;
+              if (i < 30 && recv < p.num_receivers) {
+                const int64_t e = static_cast<int64_t>(tile) * (3 * EF_RECV_PER_TILE) + 30 * j + i;
+                ps[j] = p.gs + static_cast<int64_t>(__ldg(p.idx_s + e)) * p.ld_gs + u * 8;
+                vmask |= 1u << j;
+              }
             }
           }
         }
@@ -272,11 +297,13 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
             const uint32_t addr = stage + row * 128u + ((static_cast<uint32_t>(u) ^ (row & 7u)) << 4);
             uint4 o = make_uint4(0u, 0u, 0u, 0u);
             if (vm & (1u << j)) {
-              const uint32_t rr = static_cast<uint32_t>(10 * j + grow);
-              const uint32_t raddr = stage + EF_A_STAGE_BYTES + rr * 128u + ((static_cast<uint32_t>(u) ^ (rr & 7u)) << 4);
-              uint4 xb, xr;
+              uint4 xb, xr = make_uint4(0u, 0u, 0u, 0u);      // ROWS: no receiver operand (bf16 zeros)
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xb.x), "=r"(xb.y), "=r"(xb.z), "=r"(xb.w) : "r"(addr));
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xr.x), "=r"(xr.y), "=r"(xr.z), "=r"(xr.w) : "r"(raddr));
+              if constexpr (!ROWS) {
+                const uint32_t rr = static_cast<uint32_t>(10 * j + grow);
+                const uint32_t raddr = stage + EF_A_STAGE_BYTES + rr * 128u + ((static_cast<uint32_t>(u) ^ (rr & 7u)) << 4);
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xr.x), "=r"(xr.y), "=r"(xr.z), "=r"(xr.w) : "r"(raddr));
+              }
               const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&xb);
               const __nv_bfloat162* hs = reinterpret_cast<const __nv_bfloat162*>(&cur[j]);
               const __nv_bfloat162* hr = reinterpret_cast<const __nv_bfloat162*>(&xr);
@@ -284,7 +311,8 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const float2 fb = __bfloat1622float2(hb[k]), fs = __bfloat1622float2(hs[k]), fr = __bfloat1622float2(hr[k]);
-                float v0 = fb.x + fs.x + fr.x, v1 = fb.y + fs.y + fr.y;
+                float v0 = fb.x + fs.x, v1 = fb.y + fs.y;
+                if constexpr (!ROWS) { v0 += fr.x; v1 += fr.y; }
                 v0 = apply_act<true>(v0, p.act);
                 v1 = apply_act<true>(v1, p.act);
                 ho[k] = __floats2bfloat162_rn(v0, v1);
@@ -382,15 +410,21 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           b_row[j] = static_cast<int>((static_cast<int64_t>(tile) * (3 * EF_RECV_PER_TILE) + 30 * j) % p.period);
-        const int r_row = tile * EF_RECV_PER_TILE;
+        const int r_row = ROWS ? (tile % p.tiles_per_member) * 128 : tile * EF_RECV_PER_TILE;
         for (int kb = 0; kb < C::KB; ++kb) {
           mbar_wait(a_empty(sa), pa ^ 1u);
           if (elect_one()) {
             const uint32_t stage = a_smem + sa * C::A_STRIDE;
-            mbar_arrive_expect_tx(raw_full(sa), 4 * 30 * 128 + EF_GR_BYTES);
+            if constexpr (ROWS) {
+              // the tile's 128 base rows in one box (rows past the member's last edge are zero-filled)
+              mbar_arrive_expect_tx(raw_full(sa), EF_A_STAGE_BYTES);
+              tma_load_2d(stage, &base_map, raw_full(sa), kb * 64, r_row);
+            } else {
+              mbar_arrive_expect_tx(raw_full(sa), 4 * 30 * 128 + EF_GR_BYTES);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_2d(stage + j * 4096, &base_map, raw_full(sa), kb * 64, b_row[j]);
-            tma_load_2d(stage + EF_A_STAGE_BYTES, &gr_map, raw_full(sa), kb * 64, r_row);
+              for (int j = 0; j < 4; ++j) tma_load_2d(stage + j * 4096, &base_map, raw_full(sa), kb * 64, b_row[j]);
+              tma_load_2d(stage + EF_A_STAGE_BYTES, &gr_map, raw_full(sa), kb * 64, r_row);
+            }
           }
           __syncwarp();
           if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
@@ -419,6 +453,77 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
     const float* ofs = vec_s + 2 * L + half * CH;
     const float inv_n = 1.0f / static_cast<float>(L);
     int lt = 0;
+    if constexpr (ROWS) {
+      // ---- plain row output: y = acc + b2 as bf16, one pass.  Each lane owns a row; 64-column groups are staged in a
+      // 128B-swizzled 4 KB buffer per warp and leave by TMA (a lane-per-row st.global touches 32 lines per instruction:
+      // 13 800 clk per tile in the first version, most of it LSU time).  The last, partial tile of a member stores
+      // directly (a TMA box would run into the next member's rows).
+      const uint32_t stage_buf = smem_base + C::PATCH_OFF + static_cast<uint32_t>(ew) * 4096u;
+      const uint32_t sw = static_cast<uint32_t>(lane & 7);
+      for (int slot = blockIdx.x; slot < p.num_tiles; slot += gridDim.x, ++lt) {
+        const int tile = tile_of(p, slot);
+        const int64_t member = tile / p.tiles_per_member;
+        const int64_t local0 = static_cast<int64_t>(tile % p.tiles_per_member) * 128;
+        const int64_t local = local0 + q * 32 + lane;
+        const bool whole = local0 + 128 <= p.period;
+        const bool store = local < p.period;
+        const int64_t grow0 = member * p.period + local0 + q * 32;
+        __nv_bfloat16* dst_row = reinterpret_cast<__nv_bfloat16*>(p.out) + (grow0 + lane) * p.ldo + half * CH;
+        if (et == 0) GC_ETR(3, 4 * lt);
+        mbar_wait(acc_full, static_cast<uint32_t>(lt) & 1u);
+        if (et == 0) GC_ETR(3, 4 * lt + 1);
+        tc_fence_after();
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr, r);
+#pragma unroll 1
+        for (int c = 0; c < CH; c += 32) {
+          float v[32];
+          tc_wait_ld();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+          if (c + 32 < CH) {
+            tmem_ld_32x32b_x32(taddr + c + 32, r);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+          }
+          const int hc = (c >> 5) & 1;                 // which half of the 64-column group
+          if (whole && hc == 0) {
+            if (lane == 0) bulk_wait_group_read<0>();  // the previous group's store has finished reading the buffer
+            __syncwarp();
+          }
+#pragma unroll
+          for (int k = 0; k < 32; k += 8) {
+            const float4 b0 = *reinterpret_cast<const float4*>(b2s + c + k);
+            const float4 b1 = *reinterpret_cast<const float4*>(b2s + c + k + 4);
+            uint4 o;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+            h[0] = __floats2bfloat162_rn(v[k] + b0.x, v[k + 1] + b0.y);
+            h[1] = __floats2bfloat162_rn(v[k + 2] + b0.z, v[k + 3] + b0.w);
+            h[2] = __floats2bfloat162_rn(v[k + 4] + b1.x, v[k + 5] + b1.y);
+            h[3] = __floats2bfloat162_rn(v[k + 6] + b1.z, v[k + 7] + b1.w);
+            if (whole) {
+              const uint32_t unit = static_cast<uint32_t>(hc * 4 + (k >> 3)) ^ sw;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_buf + static_cast<uint32_t>(lane) * 128u + unit * 16u),
+                           "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+            } else if (store) {
+              *reinterpret_cast<uint4*>(dst_row + c + k) = o;
+            }
+          }
+          if (whole && hc == 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&gr_map, stage_buf, half * CH + (c & ~63), static_cast<int>(grow0));
+              bulk_commit_group();
+            }
+          }
+        }
+        if (et == 0) GC_ETR(3, 4 * lt + 3);
+      }
+      if (lane == 0) bulk_wait_group_all();
+    } else
     for (int slot = blockIdx.x; slot < p.num_tiles; slot += gridDim.x, ++lt) {
       const int tile = tile_of(p, slot);
       if (et == 0) GC_ETR(3, 4 * lt);
@@ -829,17 +934,17 @@ bool edge_tma_enabled() {
   return on;
 }
 
-template <int L, bool FAST>
+template <int L, int MODE>
 int launch_edge_fused(cudaStream_t st, const CUtensorMap& w_map, const CUtensorMap& base_map, const CUtensorMap& gr_map,
                       const EdgeFusedParams& p) {
-  using C = EFCfg<L, FAST>;
+  using C = EFCfg<L, MODE>;
   static_assert(C::SMEM <= 232448, "edge_mlp_sum3_kernel: shared memory plan does not fit");
-  GC_CHECK_CUDA(cudaFuncSetAttribute(edge_mlp_sum3_kernel<L, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM),
+  GC_CHECK_CUDA(cudaFuncSetAttribute(edge_mlp_sum3_kernel<L, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM),
                 "cudaFuncSetAttribute(edge_mlp_sum3_kernel)");
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = static_cast<unsigned>(p.num_tiles < sms ? p.num_tiles : sms);
-  GC_CHECK_CUDA(launch_kernel(edge_mlp_sum3_kernel<L, FAST>, dim3(grid), dim3(EF_THREADS), (size_t)C::SMEM, st, w_map, base_map,
+  GC_CHECK_CUDA(launch_kernel(edge_mlp_sum3_kernel<L, MODE>, dim3(grid), dim3(EF_THREADS), (size_t)C::SMEM, st, w_map, base_map,
                               gr_map, p),
                 "edge_mlp_sum3_kernel");
   return GC_OK;
@@ -905,7 +1010,7 @@ extern "C" int gc_edge_mlp_sum3(void* stream, const void* base, int64_t ld_base,
   p.act = act; p.b2 = b2; p.scale_offset = scale_offset; p.do_ln = do_layer_norm;
   p.out = out; p.out_dtype = out_dtype; p.ldo = ldo; p.num_receivers = num_receivers;
   p.num_tiles = (int)((num_receivers + EF_RECV_PER_TILE - 1) / EF_RECV_PER_TILE);
-  p.members = 1; p.tiles_per_member = p.num_tiles;
+  p.members = 1; p.tiles_per_member = p.num_tiles; p.num_rows = 0;
   p.trace = g_edge_fused_trace;
   {
     const int64_t edges = 3 * num_receivers, per_tile = 3 * EF_RECV_PER_TILE;
@@ -923,11 +1028,47 @@ extern "C" int gc_edge_mlp_sum3(void* stream, const void* base, int64_t ld_base,
     if (rc != GC_OK) return rc;
     rc = make_tmap_bf16_2d(&gr_map, gr, (uint64_t)num_receivers, (uint64_t)cols, (uint64_t)ld_gr, 64, EF_RECV_PER_TILE);
     if (rc != GC_OK) return rc;
-    if (cols == 128) return launch_edge_fused<128, true>(st, w_map, base_map, gr_map, p);
-    if (cols == 256) return launch_edge_fused<256, true>(st, w_map, base_map, gr_map, p);
-    return launch_edge_fused<512, true>(st, w_map, base_map, gr_map, p);
+    if (cols == 128) return launch_edge_fused<128, 1>(st, w_map, base_map, gr_map, p);
+    if (cols == 256) return launch_edge_fused<256, 1>(st, w_map, base_map, gr_map, p);
+    return launch_edge_fused<512, 1>(st, w_map, base_map, gr_map, p);
   }
-  if (cols == 128) return launch_edge_fused<128, false>(st, w_map, w_map, w_map, p);
-  if (cols == 256) return launch_edge_fused<256, false>(st, w_map, w_map, w_map, p);
-  return launch_edge_fused<512, false>(st, w_map, w_map, w_map, p);
+  if (cols == 128) return launch_edge_fused<128, 0>(st, w_map, w_map, w_map, p);
+  if (cols == 256) return launch_edge_fused<256, 0>(st, w_map, w_map, w_map, p);
+  return launch_edge_fused<512, 0>(st, w_map, w_map, w_map, p);
+}
+
+extern "C" int gc_edge_mlp_rows(void* stream, const void* base, int64_t ld_base, int64_t period, const void* gs,
+                                const int32_t* idx_s, int64_t ld_gs, int32_t act, const void* w2, int64_t ld_w2,
+                                const float* b2, void* out, int64_t ldo, int64_t num_rows, int32_t cols) {
+  using namespace gc;
+  GC_REQUIRE(base && gs && idx_s && w2 && out, "gc_edge_mlp_rows: null buffer");
+  GC_REQUIRE(cols == 128 || cols == 256 || cols == 512, "gc_edge_mlp_rows: cols=%d (supported: 128, 256, 512)", cols);
+  GC_REQUIRE(period > 0 && num_rows >= 0 && num_rows % period == 0 && num_rows < (1LL << 31),
+             "gc_edge_mlp_rows: num_rows must be a multiple of period");
+  GC_REQUIRE(ld_base % 8 == 0 && ld_gs % 8 == 0 && ld_w2 % 8 == 0 && ldo % 8 == 0 && aligned16(base) && aligned16(gs) &&
+                 aligned16(w2) && aligned16(out), "gc_edge_mlp_rows: alignment");
+  GC_REQUIRE(act == GC_ACT_NONE || act == GC_ACT_SWISH || act == GC_ACT_GELU_TANH, "gc_edge_mlp_rows: act=%d", act);
+  if (num_rows == 0) return GC_OK;
+  CUtensorMap w_map, base_map, out_map;
+  int rc = make_tmap_bf16_2d(&w_map, w2, (uint64_t)cols, (uint64_t)cols, (uint64_t)ld_w2, 64, 128);
+  if (rc != GC_OK) return rc;
+  rc = make_tmap_bf16_2d(&base_map, base, (uint64_t)period, (uint64_t)cols, (uint64_t)ld_base, 64, 128);
+  if (rc != GC_OK) return rc;
+  rc = make_tmap_bf16_2d(&out_map, out, (uint64_t)num_rows, (uint64_t)cols, (uint64_t)ldo, 64, 32);
+  if (rc != GC_OK) return rc;
+  EdgeFusedParams p;
+  p.base = reinterpret_cast<const __nv_bfloat16*>(base); p.ld_base = ld_base; p.period = period;
+  p.gs = reinterpret_cast<const __nv_bfloat16*>(gs); p.idx_s = idx_s; p.ld_gs = ld_gs;
+  p.gr = nullptr; p.idx_r = nullptr; p.ld_gr = 0;
+  p.act = act; p.b2 = b2; p.scale_offset = nullptr; p.do_ln = 0;
+  p.out = out; p.out_dtype = GC_BF16; p.ldo = ldo; p.num_receivers = 0; p.num_rows = num_rows;
+  p.members = (int)(num_rows / period);
+  p.tiles_per_member = (int)((period + 127) / 128);
+  p.num_tiles = p.members * p.tiles_per_member;
+  p.trace = g_edge_fused_trace;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // the kernel's third tensor-map slot (receiver rows in the degree-3 variant) carries the output map here
+  if (cols == 128) return launch_edge_fused<128, 2>(st, w_map, base_map, out_map, p);
+  if (cols == 256) return launch_edge_fused<256, 2>(st, w_map, base_map, out_map, p);
+  return launch_edge_fused<512, 2>(st, w_map, base_map, out_map, p);
 }

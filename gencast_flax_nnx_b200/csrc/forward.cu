@@ -118,7 +118,12 @@ extern "C" int gc_denoiser_forward(void* stream, const gc_denoiser_model* m, con
   {
     const Seg sp{ws->g0, L, m->g2m_w1s, L};
     GC_TRY(run_gemm(c, st, &sp, 1, G, L, ws->g_p, dt, nullptr, GC_ACT_NONE, nullptr, 0, nullptr, nullptr, nullptr, nullptr, true));
-    if (sc->g2m_base != nullptr) {
+    const bool fuse_g2m = (ws->flags & GC_FORWARD_FUSE_G2M) != 0 && sc->g2m_base != nullptr && dt == GC_BF16;
+    if (fuse_g2m) {
+      // the table already holds e' W1e' + b1 + (m0 W1r)[receivers]: hidden layer, second layer and bias in one kernel
+      GC_TRY(gc_edge_mlp_rows(st, sc->g2m_base, L, sc->g2m_base_rows, ws->g_p, g->g2m_senders, L, GC_ACT_SWISH, m->g2m_w2, L,
+                              m->g2m_b2, ws->e_y, L, E1, L));
+    } else if (sc->g2m_base != nullptr) {
       GC_TRY(gc_edge_hidden(st, sc->g2m_base, L, sc->g2m_base_rows, ws->g_p, g->g2m_senders, L, sc->m_p, g->g2m_receivers, L,
                             GC_ACT_SWISH, ws->e_h, L, E1, L));
     } else {
@@ -126,8 +131,10 @@ extern "C" int gc_denoiser_forward(void* stream, const gc_denoiser_model* m, con
       GC_TRY(run_gemm(c, st, &se, 1, E1, L, ws->e_h, dt, sc->g2m_b1, GC_ACT_SWISH, nullptr, 0, ws->g_p, g->g2m_senders, sc->m_p,
                       g->g2m_receivers, false));
     }
-    const Seg s2{ws->e_h, L, m->g2m_w2, L};
-    GC_TRY(run_gemm(c, st, &s2, 1, E1, L, ws->e_y, dt, m->g2m_b2, GC_ACT_NONE, nullptr, 0, nullptr, nullptr, nullptr, nullptr, true));
+    if (!fuse_g2m) {
+      const Seg s2{ws->e_h, L, m->g2m_w2, L};
+      GC_TRY(run_gemm(c, st, &s2, 1, E1, L, ws->e_y, dt, m->g2m_b2, GC_ACT_NONE, nullptr, 0, nullptr, nullptr, nullptr, nullptr, true));
+    }
     GC_TRY(gc_ln_cond_segment_sum(st, ws->e_y, dt, L, T(GC_COND_G2M_EDGE_UPDATE), 1 | GC_SEGSUM_IRREGULAR, g->g2m_row_ptr,
                                   g->g2m_perm, ws->m_agg, dt, L, V, L));
   }

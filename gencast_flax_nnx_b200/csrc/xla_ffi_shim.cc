@@ -132,6 +132,21 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(gc_edge_mlp_sum3_ffi, EdgeMlpSum3Impl,
                                   .Attr<int32_t>("act"),
                               {ffi::Traits::kCmdBufferCompatible});
 
+// Edge MLP with a tabulated first layer, rows out (gc_edge_mlp_rows): the grid2mesh encoder's edge MLP in one call.
+static ffi::Error EdgeMlpRowsImpl(cudaStream_t stream, ffi::Buffer<ffi::BF16> base, ffi::Buffer<ffi::BF16> gs, ffi::Buffer<ffi::S32> is,
+                                  ffi::Buffer<ffi::BF16> w2, ffi::Buffer<ffi::F32> b2, ffi::Result<ffi::Buffer<ffi::BF16>> out,
+                                  int32_t act) {
+  const int32_t cols = (int32_t)out->dimensions()[1];
+  return status(gc_edge_mlp_rows(stream, base.typed_data(), cols, base.dimensions()[0], gs.typed_data(), is.typed_data(), cols, act,
+                                 w2.typed_data(), cols, b2.typed_data(), out->typed_data(), cols, out->dimensions()[0], cols));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(gc_edge_mlp_rows_ffi, EdgeMlpRowsImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>().Arg<ffi::Buffer<ffi::BF16>>().Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>().Arg<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::BF16>>()
+                                  .Attr<int32_t>("act"),
+                              {ffi::Traits::kCmdBufferCompatible});
+
 // Preconditioning + DPM-Solver++ 2S update (gc_dpm_update): x_out and the next call's c_in-scaled input.
 static ffi::Error DpmUpdateImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> f, ffi::Buffer<ffi::F32> x_cur, ffi::Buffer<ffi::F32> x_base,
                                 ffi::Buffer<ffi::F32> sched, ffi::Result<ffi::Buffer<ffi::F32>> x_out,

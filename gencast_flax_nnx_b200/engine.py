@@ -176,6 +176,10 @@ class DenoiserEngine:
         # mesh2grid edge update + aggregation in one kernel (gc_edge_mlp_sum3); GENCAST_EDGE_FUSED=0 keeps the
         # three-kernel path (gc_edge_hidden / edge GEMM with gathers -> second-layer GEMM -> gc_ln_cond_segment_sum)
         self.fuse_m2g = compute_dtype == "bf16" and os.environ.get("GENCAST_EDGE_FUSED", "1") != "0"
+        # grid2mesh: the receivers are mesh nodes, whose part of the first edge-MLP layer depends on the noise level only;
+        # with the per-level edge tables it is folded into the table (added in fp32 in the table GEMM's epilogue) and
+        # gc_edge_mlp_rows computes hidden layer + second layer in one kernel (no [E, L] hidden tensor in HBM)
+        self.fuse_g2m = self.fuse_m2g
         # second MLP layer + LayerNorm + affine + residual of the node MLPs in one kernel (gc_linear_ln_cond): opt-in
         # (GENCAST_LN_FUSED=1).  Measured at 1 deg x 4 (260 640 rows): 271 us against 231 us for GEMM -> gc_ln_cond
         # (389 vs 312 us with a residual): with the whole row in TMEM the accumulator cannot be double buffered and the
@@ -511,7 +515,8 @@ class DenoiserEngine:
             if branch_stream is not None:
                 ws.branch_stream = branch_stream.cuda_stream
                 ws.fork_event, ws.join_event = self._fork_ev.cuda_event, self._join_ev.cuda_event
-            ws.flags = (ops._lib.GC_FORWARD_FUSE_M2G if self.fuse_m2g else 0) | (ops._lib.GC_FORWARD_FUSE_LN if self.fuse_ln else 0)
+            ws.flags = ((ops._lib.GC_FORWARD_FUSE_M2G if self.fuse_m2g else 0) | (ops._lib.GC_FORWARD_FUSE_LN if self.fuse_ln else 0)
+                        | (ops._lib.GC_FORWARD_FUSE_G2M if self.fuse_g2m else 0))
             self._c_workspaces[key] = ws
         return ws
 
@@ -573,7 +578,8 @@ class DenoiserEngine:
             if self.cd == torch.bfloat16 and need <= budget and (pin or len(self._sigma_pinned) == 0):
                 ctx.g2m_base = torch.empty(self.E1, L, dtype=self.cd, device=self.device)
                 # g_w / d_w were written by the fold kernels queued just above: not static weights (no early W fetch)
-                ops.gemm([(self.g2m_e_ln[:self.E1], g_w)], ctx.g2m_base, bias=g_b)
+                ops.gemm([(self.g2m_e_ln[:self.E1], g_w)], ctx.g2m_base, bias=g_b,
+                         gathers=[(ctx.m_p, self.g2m_r[:self.E1])] if self.fuse_g2m else ())
                 ctx.m2g_base = torch.empty(self.E2, L, dtype=self.cd, device=self.device)
                 ops.gemm([(self.m2g_e_ln[:self.E2], d_w)], ctx.m2g_base, bias=d_b)
         self._sigma_cache[sigma] = ctx
@@ -685,13 +691,17 @@ class DenoiserEngine:
                 self._grid_branch(ctx)
         _gemm([(self.g0, w["eu_w1s"])], self.g_p)
         e_h, e_y = self.e_h[:E1], self.e_y[:E1]
-        if ctx.g2m_base is not None:
+        if ctx.g2m_base is not None and self.fuse_g2m:
+            # the table holds e' W1e' + b1 + (m0 W1r)[receivers]; hidden layer + second layer in one kernel
+            ops.edge_mlp_rows(ctx.g2m_base, (self.g_p, self.g2m_s), w["eu_w2"], w["eu_b2"], e_y)
+        elif ctx.g2m_base is not None:
             ops.edge_hidden(ctx.g2m_base, [(self.g_p, self.g2m_s), (ctx.m_p, self.g2m_r)], e_h, act="swish")
         else:
             # folded per-level weight: produced by queued work (sigma_context), so no early W fetch
             ops.gemm([(self.g2m_e_ln, ctx.g2m_w1e)], e_h, bias=ctx.g2m_b1, act="swish",
                      gathers=[(self.g_p, self.g2m_s), (ctx.m_p, self.g2m_r)])
-        _gemm([(e_h, w["eu_w2"])], e_y, bias=w["eu_b2"])
+        if not (ctx.g2m_base is not None and self.fuse_g2m):
+            _gemm([(e_h, w["eu_w2"])], e_y, bias=w["eu_b2"])
         ops.ln_cond_segment_sum(e_y, self.m_agg, T[self.C_G2M_EU], self.g2m_row_ptr, self.g2m_perm, irregular=True)
         self._mlp_ln([(ctx.m0, w["mu_w1a"]), (self.m_agg, w["mu_w1b"])], w["mu_b1"], w["mu_w2"], w["mu_b2"],
                      self.m_h, self.m_y, self.x, T[self.C_G2M_MU], residual=ctx.m0)

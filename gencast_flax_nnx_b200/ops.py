@@ -383,6 +383,24 @@ def edge_mlp_sum3(base: torch.Tensor, gathers: Sequence[Tuple[torch.Tensor, torc
     return out
 
 
+def edge_mlp_rows(base: torch.Tensor, gather: Tuple[torch.Tensor, torch.Tensor], w2: torch.Tensor, b2: Optional[torch.Tensor],
+                  out: torch.Tensor, *, act: Optional[str] = "swish") -> torch.Tensor:
+    """out[e] = act(base[e % len(base)] + gs[idx_s[e]]) @ w2^T + b2 in one kernel (see gc_edge_mlp_rows)."""
+    lib = _lib.load()
+    gs, idx_s = gather
+    if any(t.dtype != torch.bfloat16 for t in (base, gs, w2, out)):
+        raise TypeError("edge_mlp_rows: bf16 operands expected")
+    rows, cols = out.shape
+    if idx_s.dtype != torch.int32 or idx_s.numel() != rows or rows % base.shape[0] != 0:
+        raise ValueError("edge_mlp_rows: idx_s must be int32 [rows], rows a multiple of len(base)")
+    if w2.shape != (cols, cols):
+        raise ValueError("edge_mlp_rows: w2 must be [cols, cols]")
+    _lib.check(lib.gc_edge_mlp_rows(_stream(), base.data_ptr(), _row_major(base, "base"), base.shape[0], gs.data_ptr(),
+                                    idx_s.data_ptr(), _row_major(gs, "gs"), ACT[act], w2.data_ptr(), _row_major(w2, "w2"),
+                                    _p(b2), out.data_ptr(), _row_major(out, "out"), rows, cols), "gc_edge_mlp_rows")
+    return out
+
+
 def denoiser_forward(model, graph, sigma, workspace) -> None:
     """One whole network evaluation through gc_denoiser_forward (descriptors: _lib.DenoiserModel, DenoiserGraph,
     SigmaContextC, DenoiserWorkspace, filled by the engine)."""

@@ -325,6 +325,20 @@ GC_API int gc_edge_mlp_sum3(void* stream, const void* base, int64_t ld_base, int
                             int32_t cols);
 
 /*
+ * Edge MLP whose first layer is known up to one gathered operand, rows out (no [E, cols] hidden tensor in HBM):
+ *   y_e = act( base[e mod period] + gs[idx_s[e]] ) . W2^T + b2              bf16 [num_rows, cols]
+ * for edge lists where the receiver's contribution to the first layer is static and already part of `base`
+ * (GenCast's grid2mesh encoder: the receivers are mesh nodes, whose embedding depends on the noise level only,
+ * gencast/denoiser.py:662-675; the table is then e' W1e' + b1 + (m0 W1r)[receivers]).  Same operators as
+ * gc_edge_mlp_sum3 (common/typed_graph_net.py:134-159, :295-305; common/mlp.py:115-147 up to the LayerNorm), same
+ * kernel: tiles of 128 consecutive edges of one member, base rows by TMA, gs gathered, W2 by TMA, whole rows in tensor
+ * memory; LayerNorm + aggregation follow in gc_ln_cond_segment_sum.  num_rows is a multiple of period (members).
+ */
+GC_API int gc_edge_mlp_rows(void* stream, const void* base, int64_t ld_base, int64_t period, const void* gs,
+                            const int32_t* idx_s, int64_t ld_gs, int32_t act, const void* w2, int64_t ld_w2,
+                            const float* b2, void* out, int64_t ldo, int64_t num_rows, int32_t cols);
+
+/*
  * Inverse real spherical-harmonic transform of random coefficients -> isotropic white noise fields in the sampler's
  * state layout.  Replaces dinosaur's RealSphericalHarmonics.to_nodal as called by the reference's noise generator
  * (gencast/samplers_utils.py:99-118, :250-346; the per-l amplitudes of :316-322 are folded into `table`):
@@ -387,6 +401,8 @@ GC_API int gc_ensemble_accumulate(void* stream, const float* x, float* sum, floa
 
 #define GC_FORWARD_FUSE_M2G 1    /* mesh2grid edge update + aggregation through gc_edge_mlp_sum3 */
 #define GC_FORWARD_FUSE_LN 2     /* second MLP layer + LayerNorm + affine + residual through gc_linear_ln_cond */
+#define GC_FORWARD_FUSE_G2M 4    /* sigma->g2m_base already contains the receivers' part (base[e] + m_p[receivers[e]]):
+                                    the grid2mesh edge MLP runs through gc_edge_mlp_rows */
 
 /* Linear -> swish -> Linear (common/mlp.py:152-203); the first layer may be split in K-segments (concatenated
  * operands of the reference, common/typed_graph_net.py:301-305, :315-326) */

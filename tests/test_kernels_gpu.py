@@ -383,6 +383,40 @@ def test_edge_mlp_sum3_fused(cuda_device, cols, nrecv, members, out_dtype):
     assert _rel(out.cpu(), (h @ w2.double().T).reshape(R, 3, cols).sum(1)) < 8e-3
 
 
+@pytest.mark.parametrize("cols,period,members", [(128, 100, 1), (256, 1000, 3), (512, 5003, 2), (512, 128 * 7, 4)])
+def test_edge_mlp_rows_fused(cuda_device, cols, period, members):
+    """Tabulated first layer + gather + swish -> second layer (tcgen05) -> bf16 rows in one kernel against the same chain in
+    fp64 on the bf16-rounded operands; member blocks that are not a whole number of 128-edge tiles; bitwise repeatable."""
+    from gencast_flax_nnx_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(cols + period)
+    d = cuda_device
+    E = period * members
+    n_s = 611
+    bf = lambda t: t.to(torch.bfloat16)
+    base = bf(torch.randn(period, cols, generator=g))
+    gs = bf(torch.randn(n_s, cols, generator=g))
+    idx_s = torch.randint(0, n_s, (E,), generator=g, dtype=torch.int32)
+    w2 = bf(torch.randn(cols, cols, generator=g) / math.sqrt(cols))
+    b2 = torch.randn(cols, generator=g) * 0.1
+    h = base.double()[torch.arange(E) % period] + gs.double()[idx_s.long()]
+    h = bf((h * torch.sigmoid(h)).float()).double()
+    ref = h @ w2.double().T + b2.double()
+    outs = []
+    for _ in range(2):
+        out = torch.full((E, cols), float("nan"), dtype=torch.bfloat16, device=d)
+        ops.edge_mlp_rows(base.to(d), (gs.to(d), idx_s.to(d)), w2.to(d), b2.to(d), out)
+        torch.cuda.synchronize()
+        outs.append(out.cpu())
+    assert _rel(outs[0], ref) < 1.2e-2
+    assert torch.equal(outs[0], outs[1])
+    # against the two-kernel path it replaces (gc_edge_hidden -> gc_gemm): same hidden layer, same products
+    e_h = torch.empty(E, cols, dtype=torch.bfloat16, device=d)
+    e_y = torch.empty(E, cols, dtype=torch.bfloat16, device=d)
+    ops.edge_hidden(base.to(d), [(gs.to(d), idx_s.to(d))], e_h, act="swish")
+    ops.gemm([(e_h, w2.to(d))], e_y, bias=b2.to(d))
+    assert _rel(outs[0], e_y.cpu().double()) < 4e-3
+
+
 @pytest.mark.parametrize("cols,rows", [(128, 100), (256, 5000), (512, 20001), (512, 128)])
 @pytest.mark.parametrize("res_dtype,out_dtype", [(None, torch.bfloat16), (torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32),
                                                  (torch.float32, torch.float32)])
