@@ -248,10 +248,6 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
                 const __nv_bfloat16* row = p.gs + static_cast<int64_t>(__ldg(p.idx_s + member * p.period + local)) * p.ld_gs;
                 ps[j] = row + u * 8;
                 vmask |= 1u << j;
-                // The sender table (all members' grid nodes: 267 MB at 1 deg x 4) does not live in L2 and a k-block only
-                // touches 128 bytes of a row: without this, each of the 8 slices of a row is its own DRAM access at use
-                // time.  The setup runs a tile ahead: the 8 threads of a row pull its 8 lines into L2 now.
-                if (u * 64 < L) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + u * 64));
               }
             }
           } else {

@@ -383,6 +383,13 @@ def edge_mlp_sum3(base: torch.Tensor, gathers: Sequence[Tuple[torch.Tensor, torc
     return out
 
 
+def _edge_rows_cost(base, gather, w2, b2, out, **kw):
+    rows, cols = out.shape
+    # FLOPs of the second layer; bytes: the base table once, one gathered row and one index per edge, the rows written
+    return 2.0 * rows * cols * cols, _nbytes(base, out, w2) + rows * cols * 2.0 + 4.0 * rows
+
+
+@_recorded("edge_mlp_rows", _edge_rows_cost)
 def edge_mlp_rows(base: torch.Tensor, gather: Tuple[torch.Tensor, torch.Tensor], w2: torch.Tensor, b2: Optional[torch.Tensor],
                   out: torch.Tensor, *, act: Optional[str] = "swish") -> torch.Tensor:
     """out[e] = act(base[e % len(base)] + gs[idx_s[e]]) @ w2^T + b2 in one kernel (see gc_edge_mlp_rows)."""

@@ -29,6 +29,8 @@ def main():
     fam = {}
     for l in one:
         name = next((f for f in FAMILIES if f in l["name"]), None)
+        if name == "edge_mlp_sum3" and ", 2>" in l["name"]:
+            name = "edge_mlp_rows"          # MODE 2 of the same kernel template = gc_edge_mlp_rows
         if name is None:
             continue
         f = fam.setdefault(name, {"launches": 0, "dram_bytes_read": 0, "dram_bytes_written": 0, "us": 0.0})
