@@ -116,7 +116,7 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&v)[32], uint32_t mw, 
 template <int D, int ROWS>
 __global__ void __launch_bounds__(G_THREADS, 2)
 khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap row_map,
-                             const GatherAttParams p) {
+                             const __grid_constant__ CUtensorMap out_map, const GatherAttParams p) {
   using namespace sm100;
   using C = GCfg<D>;
   constexpr bool TMA_K = ROWS != 0, TMA_V = ROWS == 1;     // which streams use TMA row gathers
@@ -153,6 +153,7 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const __
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&q_map);
+    prefetch_tensormap(&out_map);
     if (TMA_ROWS) prefetch_tensormap(&row_map);
     mbar_init(q_full, 1);
     // "full" barriers: one arrive.expect_tx (TMA), or one arrival per copying lane (cp.async)
@@ -353,18 +354,19 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const __
     }
     if (threadIdx.x == 32) GC_GTR(4, 1);
     const int64_t row = static_cast<int64_t>(qt) * GQ + r;
+    if (T > 0) {
+      // O / l as bf16 into the Q tile's shared memory (every MMA that read Q has completed: o_full), in the 128B-swizzled
+      // layout of a {64 columns, 32 rows} TMA box per warp and 64-column block, then out by TMA: a lane-per-row st.global
+      // touches 32 lines per instruction (2 700 clk of the CTA's 4 500-clk epilogue in the trace).  Rows past the last
+      // node are clipped by the tensor map.
+      const uint32_t sw = static_cast<uint32_t>(r & 7);
 #pragma unroll
-    for (int c = 0; c < D; c += 32) {
-      uint32_t v[32];
-      if (T > 0) {
+      for (int c = 0; c < D; c += 32) {
+        uint32_t v[32];
         tmem_ld_32x32b_x32(o_addr + c, v);
         tc_wait_ld();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0u;
-      }
-      if (row < p.nodes) {
-        __nv_bfloat16* dst = p.out + row * p.ldo + head * D + c;
+        const uint32_t blk = q_smem + static_cast<uint32_t>(c >> 6) * (GQ * 128);
+        const int hc = (c >> 5) & 1;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 o;
@@ -372,9 +374,25 @@ khop_attention_gather_kernel(const __grid_constant__ CUtensorMap q_map, const __
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             h[j] = __floats2bfloat162_rn(__uint_as_float(v[i + 2 * j]) * inv_l, __uint_as_float(v[i + 2 * j + 1]) * inv_l);
-          *reinterpret_cast<uint4*>(dst + i) = o;
+          const uint32_t unit = static_cast<uint32_t>(hc * 4 + (i >> 3)) ^ sw;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + static_cast<uint32_t>(r) * 128u + unit * 16u), "r"(o.x),
+                       "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+        }
+        if (hc == 1) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&out_map, blk + static_cast<uint32_t>(q * 32) * 128u, head * D + (c & ~63), qt * GQ + q * 32);
+            bulk_commit_group();
+          }
         }
       }
+      if (lane == 0) bulk_wait_group_read<0>();      // the stores have read this CTA's shared memory before it exits
+    } else if (row < p.nodes) {
+      // a query tile without keys: zeros (the Q load may still be in flight, so shared memory is left alone)
+      __nv_bfloat16* dst = p.out + row * p.ldo + head * D;
+#pragma unroll
+      for (int i = 0; i < D; i += 8) *reinterpret_cast<uint4*>(dst + i) = make_uint4(0u, 0u, 0u, 0u);
     }
   } else {
     // ---------------- K / V row gather: two independent streams, so a K tile is requested the moment its slot frees
@@ -487,12 +505,13 @@ int rows_mode() {
 }
 
 template <int D, int ROWS>
-int launch_gather(cudaStream_t st, const CUtensorMap& map, const CUtensorMap& row_map, const GatherAttParams& p, int num_q_tiles) {
+int launch_gather(cudaStream_t st, const CUtensorMap& map, const CUtensorMap& row_map, const CUtensorMap& out_map,
+                  const GatherAttParams& p, int num_q_tiles) {
   using C = GCfg<D>;
   cudaError_t e = cudaFuncSetAttribute(khop_attention_gather_kernel<D, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(khop_attention_gather_kernel)");
   GC_CHECK_CUDA(launch_kernel(khop_attention_gather_kernel<D, ROWS>, dim3(num_q_tiles * p.heads), dim3(G_THREADS), (size_t)C::SMEM,
-                              st, map, row_map, p), "khop_attention_gather_kernel");
+                              st, map, row_map, out_map, p), "khop_attention_gather_kernel");
   return GC_OK;
 }
 
@@ -530,6 +549,9 @@ extern "C" int gc_khop_attention_gather(void* stream, const void* qkv, int64_t l
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)head_dim);
   p.trace = g_attention_gather_trace;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUtensorMap out_map;      // {64 columns, 32 rows}: one warp's share of a 64-column block of the output tile
+  rc = make_tmap_bf16_2d(&out_map, out, (uint64_t)nodes, (uint64_t)(1LL * heads * head_dim), (uint64_t)ldo, 64, 32);
+  if (rc != GC_OK) return rc;
   const int mode = rows_mode();
   CUtensorMap row_map = map;
   if (mode != 0) {           // one row of 64 columns per box: the unit of a gather4 request
@@ -537,11 +559,11 @@ extern "C" int gc_khop_attention_gather(void* stream, const void* qkv, int64_t l
     if (rc != GC_OK) return rc;
   }
   if (head_dim == 64) {
-    if (mode == 0) return launch_gather<64, 0>(st, map, row_map, p, num_q_tiles);
-    if (mode == 1) return launch_gather<64, 1>(st, map, row_map, p, num_q_tiles);
-    return launch_gather<64, 2>(st, map, row_map, p, num_q_tiles);
+    if (mode == 0) return launch_gather<64, 0>(st, map, row_map, out_map, p, num_q_tiles);
+    if (mode == 1) return launch_gather<64, 1>(st, map, row_map, out_map, p, num_q_tiles);
+    return launch_gather<64, 2>(st, map, row_map, out_map, p, num_q_tiles);
   }
-  if (mode == 0) return launch_gather<128, 0>(st, map, row_map, p, num_q_tiles);
-  if (mode == 1) return launch_gather<128, 1>(st, map, row_map, p, num_q_tiles);
-  return launch_gather<128, 2>(st, map, row_map, p, num_q_tiles);
+  if (mode == 0) return launch_gather<128, 0>(st, map, row_map, out_map, p, num_q_tiles);
+  if (mode == 1) return launch_gather<128, 1>(st, map, row_map, out_map, p, num_q_tiles);
+  return launch_gather<128, 2>(st, map, row_map, out_map, p, num_q_tiles);
 }
