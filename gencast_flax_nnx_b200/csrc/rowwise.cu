@@ -50,7 +50,9 @@ __device__ __forceinline__ void layer_norm_inplace(float (&v)[NV], int cols) {
   for (int i = 0; i < NV; ++i) v[i] = (v[i] - mean) * rstd;
 }
 
-template <int NV>
+// RES: a residual row is added; it is then requested together with the input row (one load latency per row instead of
+// two) at the price of 18 more registers, which the variant without residual does not pay.
+template <int NV, bool RES>
 __global__ void __launch_bounds__(256) ln_cond_kernel(const void* __restrict__ x, int x_dtype, int64_t ldx,
                                                       const float* __restrict__ scale_offset, int do_ln,
                                                       const void* __restrict__ residual, int res_dtype, int64_t ld_res,
@@ -61,24 +63,26 @@ __global__ void __launch_bounds__(256) ln_cond_kernel(const void* __restrict__ x
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  // (1 + s | o) live in shared memory, not in 2 x NV registers per lane: the kernel is bound by the row bytes each SM keeps
+  // in flight, i.e. by resident warps (78 -> 46 registers: 3 -> 5 blocks per SM at L = 512)
+  __shared__ __align__(16) float so_s[2 * cols];
   pdl_wait();
-  float sc[NV], of[NV];
-  if (scale_offset != nullptr) {
-    load_row<NV>(scale_offset, GC_F32, 0, lane, sc);
-    load_row<NV>(scale_offset, GC_F32, cols, lane, of);
-  } else {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) { sc[i] = 1.0f; of[i] = 0.0f; }
-  }
+  for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x)
+    so_s[c] = scale_offset != nullptr ? __ldg(scale_offset + c) : (c < cols ? 1.0f : 0.0f);
+  __syncthreads();
   for (int64_t row = warp0; row < rows; row += nwarps) {
-    float v[NV];
+    float v[NV], r[NV];
     load_row<NV>(x, x_dtype, row * ldx, lane, v);
+    if constexpr (RES) load_row<NV>(residual, res_dtype, row * ld_res, lane, r);
     if (do_ln) layer_norm_inplace<NV>(v, cols);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = fmaf(v[i], sc[i], of[i]);
-    if (residual != nullptr) {
-      float r[NV];
-      load_row<NV>(residual, res_dtype, row * ld_res, lane, r);
+    for (int j = 0; j < NV / 4; ++j) {
+      const float4 sc = *reinterpret_cast<const float4*>(&so_s[(j * 32 + lane) * 4]);
+      const float4 of = *reinterpret_cast<const float4*>(&so_s[cols + (j * 32 + lane) * 4]);
+      v[j * 4] = fmaf(v[j * 4], sc.x, of.x); v[j * 4 + 1] = fmaf(v[j * 4 + 1], sc.y, of.y);
+      v[j * 4 + 2] = fmaf(v[j * 4 + 2], sc.z, of.z); v[j * 4 + 3] = fmaf(v[j * 4 + 3], sc.w, of.w);
+    }
+    if constexpr (RES) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) v[i] += r[i];
     }
@@ -658,11 +662,26 @@ int gc_ln_cond(void* stream, const void* x, int32_t x_dtype, int64_t ldx, const 
   if (residual) GC_REQUIRE(dtype_ok(res_dtype) && ld_res % 4 == 0 && aligned16(residual), "gc_ln_cond: residual alignment");
   if (rows <= 0) return GC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const unsigned grid = grid_for(rows, 8, 8);
+  // grid-stride kernel: one wave of exactly the blocks that are resident at once (a partial second wave is a tail)
+  auto resident = [](auto kernel) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 256, 0) != cudaSuccess || n < 1) n = 4;
+    return n;
+  };
 #define GC_LAUNCH_LN(NV)                                                                                        \
-  GC_CHECK_CUDA(launch_kernel(ln_cond_kernel<NV>, dim3(grid), dim3(256), 0, st, x, x_dtype, ldx, scale_offset,    \
-                              do_layer_norm, residual, res_dtype, ld_res, out, out_dtype, ldo, rows),           \
-                "ln_cond_kernel")
+  do {                                                                                                          \
+  if (residual != nullptr) {                                                                                    \
+    static const int occ = resident(ln_cond_kernel<NV, true>);                                                  \
+    GC_CHECK_CUDA(launch_kernel(ln_cond_kernel<NV, true>, dim3(grid_for(rows, 8, occ)), dim3(256), 0, st, x, x_dtype, ldx, \
+                                scale_offset, do_layer_norm, residual, res_dtype, ld_res, out, out_dtype, ldo, rows), \
+                  "ln_cond_kernel");                                                                            \
+  } else {                                                                                                      \
+    static const int occ = resident(ln_cond_kernel<NV, false>);                                                 \
+    GC_CHECK_CUDA(launch_kernel(ln_cond_kernel<NV, false>, dim3(grid_for(rows, 8, occ)), dim3(256), 0, st, x, x_dtype, ldx, \
+                                scale_offset, do_layer_norm, residual, res_dtype, ld_res, out, out_dtype, ldo, rows), \
+                  "ln_cond_kernel");                                                                            \
+  }                                                                                                             \
+  } while (0)
   if (cols == 128) GC_LAUNCH_LN(4);
   else if (cols == 256) GC_LAUNCH_LN(8);
   else GC_LAUNCH_LN(16);
