@@ -402,17 +402,35 @@ __global__ void __launch_bounds__(256) dpm_update_kernel(const float* __restrict
   pdl_wait();
   const float c_out = __ldg(sched), c_skip = __ldg(sched + 1), a = __ldg(sched + 2), c_in_next = __ldg(sched + 3);
   const int64_t total = rows * cols;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / cols;
-    const int c = static_cast<int>(i - r * cols);
-    const float d = c_out * __ldg(f + r * ldf + c) + c_skip * __ldg(x_cur + r * ldx + c);
-    const float xn = a * __ldg(x_base + r * ldx + c) + (1.0f - a) * d;
-    x_out[r * ldx + c] = xn;
-    if (xin_out != nullptr) {
-      const float xi = c_in_next * xn;
-      if (xin_dtype == GC_BF16) reinterpret_cast<__nv_bfloat16*>(xin_out)[r * ld_xin + c] = __float2bfloat16_rn(xi);
-      else reinterpret_cast<float*>(xin_out)[r * ld_xin + c] = xi;
+  const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  // four independent elements per thread and iteration: 12 loads in flight per thread (the kernel is latency-bound)
+  for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * nthreads) {
+    float fv[4], xc[4], xb[4];
+    int64_t off_x[4], off_in[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * nthreads;
+      ok[u] = i < total;
+      const int64_t r = ok[u] ? i / cols : 0;
+      const int c = ok[u] ? static_cast<int>(i - r * cols) : 0;
+      off_x[u] = r * ldx + c;
+      off_in[u] = r * ld_xin + c;
+      fv[u] = __ldg(f + r * ldf + c);
+      xc[u] = __ldg(x_cur + off_x[u]);
+      xb[u] = __ldg(x_base + off_x[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
+      const float d = c_out * fv[u] + c_skip * xc[u];
+      const float xn = a * xb[u] + (1.0f - a) * d;
+      x_out[off_x[u]] = xn;
+      if (xin_out != nullptr) {
+        const float xi = c_in_next * xn;
+        if (xin_dtype == GC_BF16) reinterpret_cast<__nv_bfloat16*>(xin_out)[off_in[u]] = __float2bfloat16_rn(xi);
+        else reinterpret_cast<float*>(xin_out)[off_in[u]] = xi;
+      }
     }
   }
 }
