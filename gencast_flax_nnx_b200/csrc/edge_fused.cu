@@ -629,6 +629,482 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Column-split CTA pair for gc_edge_mlp_sum3 (FAST preconditions).  In the single-CTA kernel above the accumulator of a
+// tile is 128 rows x L = 512 fp32 columns, i.e. all of tensor memory: the epilogue (two passes over it at the TMEM read
+// rate of 64 B/clk/SM = 2 x 4 096 clk, plus two shuffles per element) and the tile's MMAs cannot overlap, and the
+// tensor pipe is busy a quarter of the time.  Here a cluster of two CTAs owns a tile: both hold the same hidden-layer
+// tile A (128 x L bf16, k-block by k-block) and CTA r computes the output columns [r L/2, (r+1) L/2), so an accumulator is
+// L/2 = 256 columns and two of them fit: the MMAs of tile t+1 run under the epilogue of tile t.
+//   * A k-block kb is produced by CTA kb % 2 (its producers gather / add / swish exactly as above) and forwarded to the
+//     peer's ring by a shared-memory -> peer-shared-memory bulk copy that completes on the peer's `x_full` barrier.
+//     The ring has an even number of stages, so stage s always holds k-blocks of parity s % 2: every barrier is used
+//     exactly once per ring cycle and phases are (use index / stages) & 1.  Stages of the CTA's own parity (with room
+//     for the TMA-fed receiver rows) and stages filled by the peer are two arrays: [own 0..2 | peer 0..2] in both CTAs.
+//   * A CTA tells its peer that a peer-filled stage is free (and its x_full armed) by a remote arrive on `p_empty`.
+//   * LayerNorm: each CTA reduces its half of the columns, writes the per-row (sum, sum of squares) into the peer's
+//     shared memory, and both add the two partials in rank order (the same bits on both sides).
+// Warps (640 threads): 0 W2 TMA, 1 MMA, 2-9 producers, 10-17 epilogue, 18 operand TMA + flow control, 19 forwarder.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int EP_THREADS = 640;
+constexpr int EP_A_STAGES = 6;                           // 3 filled locally (with receiver rows), 3 by the peer
+
+template <int L>
+struct EPCfg {
+  static constexpr int NC = L / 2;                      // output columns per CTA
+  static constexpr int KB = L / 64;
+  static constexpr int OWN_STRIDE = EF_A_STAGE_BYTES + EF_GR_BYTES;     // locally produced: A k-block + receiver rows
+  static constexpr int PEER_OFF = (EP_A_STAGES / 2) * OWN_STRIDE;       // stages the peer fills: A k-block only
+  static constexpr int W_STAGE_BYTES = NC * 64 * 2;
+  static constexpr int A_OFF = 0;
+  static constexpr int W_OFF = PEER_OFF + (EP_A_STAGES / 2) * EF_A_STAGE_BYTES;
+  static constexpr int VEC_OFF = W_OFF + EF_W_STAGES * W_STAGE_BYTES;      // b2 | scale | offset of this CTA's columns
+  static constexpr int STAT_OFF = VEC_OFF + 3 * NC * 4;                     // [2 buffers][2 halves][128] float2
+  static constexpr int XSTAT_OFF = STAT_OFF + 2 * 2 * 128 * 8;              // [2 buffers][128] float2, written by the peer
+  static constexpr int BAR_OFF = XSTAT_OFF + 2 * 128 * 8;
+  static constexpr int SMEM = BAR_OFF + 512 + 1024;
+  static_assert(KB % 2 == 0 && EP_A_STAGES % 2 == 0, "k-block parity = stage parity");
+  static_assert(SMEM <= 232448, "edge_mlp_sum3_pair_kernel: shared memory plan does not fit");
+};
+
+__device__ __forceinline__ uint32_t map_to_peer(uint32_t local_smem_addr, uint32_t peer_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(peer_rank));
+  return r;
+}
+
+template <int L>
+__global__ void __launch_bounds__(EP_THREADS, 1)
+edge_mlp_sum3_pair_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant__ CUtensorMap base_map,
+                          const __grid_constant__ CUtensorMap gr_map, const EdgeFusedParams p) {
+  using namespace sm100;
+  using C = EPCfg<L>;
+  constexpr int S = EP_A_STAGES, KB = C::KB, NC = C::NC;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_smem = smem_base + C::A_OFF;
+  const uint32_t w_smem = smem_base + C::W_OFF;
+  const uint32_t bars = smem_base + C::BAR_OFF;
+  float* vec_s = reinterpret_cast<float*>(smem_gen + C::VEC_OFF);
+  float2* stat_s = reinterpret_cast<float2*>(smem_gen + C::STAT_OFF);
+  float2* xstat_s = reinterpret_cast<float2*>(smem_gen + C::XSTAT_OFF);
+  auto a_full = [&](int s) { return bars + 8u * s; };                      // local producers done (8 warps)
+  auto x_full = [&](int s) { return bars + 8u * (S + s); };                // peer's copy landed (1 arrive + bytes)
+  auto a_empty = [&](int s) { return bars + 8u * (2 * S + s); };           // local MMAs have read the stage
+  auto p_empty = [&](int s) { return bars + 8u * (3 * S + s); };           // peer's stage s is free and armed (remote arrive)
+  auto raw_full = [&](int s) { return bars + 8u * (4 * S + s); };          // TMA-fed operands of an own stage landed
+  auto w_full = [&](int s) { return bars + 8u * (5 * S + s); };
+  auto w_empty = [&](int s) { return bars + 8u * (5 * S + EF_W_STAGES + s); };
+  auto acc_full = [&](int b) { return bars + 8u * (5 * S + 2 * EF_W_STAGES + b); };
+  auto acc_empty = [&](int b) { return bars + 8u * (5 * S + 2 * EF_W_STAGES + 2 + b); };
+  auto stat_full = [&](int b) { return bars + 8u * (5 * S + 2 * EF_W_STAGES + 4 + b); };   // peer's row statistics arrived
+  const uint32_t tmem_ptr_smem = bars + 8u * (5 * S + 2 * EF_W_STAGES + 6);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t peer = rank ^ 1u;
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  // shared-memory address of ring stage s in this CTA: produced here (s % 2 == rank) or filled by the peer
+  auto stage_addr = [&](int s) {
+    return (static_cast<uint32_t>(s) & 1u) == rank ? a_smem + static_cast<uint32_t>(s >> 1) * C::OWN_STRIDE
+                                                    : a_smem + C::PEER_OFF + static_cast<uint32_t>(s >> 1) * EF_A_STAGE_BYTES;
+  };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&w_map);
+    prefetch_tensormap(&base_map);
+    prefetch_tensormap(&gr_map);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(a_full(s), EF_PRODUCER_WARPS);
+      mbar_init(x_full(s), 1);
+      mbar_init(a_empty(s), 1);
+      mbar_init(p_empty(s), 1);
+      mbar_init(raw_full(s), 1);
+    }
+    for (int s = 0; s < EF_W_STAGES; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), EF_EPI_WARPS); mbar_init(stat_full(b), 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, 2 * NC);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                           // both CTAs' barriers exist before anything remote happens
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    // ---------------- this CTA's half of W2 (rows rank * NC .. + NC), k-block by k-block
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int slot = pair_id; slot < p.num_tiles; slot += num_pairs) {
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(w_empty(stage), phase ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(w_full(stage), C::W_STAGE_BYTES);
+#pragma unroll
+          for (int j = 0; j < NC / 128; ++j)
+            tma_load_2d(w_smem + stage * C::W_STAGE_BYTES + j * (128 * 128), &w_map, w_full(stage), kb * 64,
+                        static_cast<int>(rank) * NC + j * 128);
+        }
+        __syncwarp();
+        if (++stage == EF_W_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer: M = 128, N = NC, accumulator buffer lt & 1
+    constexpr uint32_t idesc = idesc_bf16_f32(128, NC, 0, 0);
+    int sw = 0;
+    uint32_t pw = 0;
+    int lt = 0;
+    int64_t g = 0;                                // running k-block index: stage g % S, phase (g / S) & 1
+    for (int slot = pair_id; slot < p.num_tiles; slot += num_pairs, ++lt) {
+      const int b = lt & 1;
+      GC_ETR(0, 3 * lt);
+      mbar_wait(acc_empty(b), ((static_cast<uint32_t>(lt) >> 1) & 1u) ^ 1u);
+      GC_ETR(0, 3 * lt + 1);
+      tc_fence_after();
+      for (int kb = 0; kb < KB; ++kb, ++g) {
+        const int sa = static_cast<int>(g % S);
+        const uint32_t pa = static_cast<uint32_t>(g / S) & 1u;
+        const bool own = (static_cast<uint32_t>(kb) & 1u) == rank;
+        mbar_wait(own ? a_full(sa) : x_full(sa), pa);
+        GC_ETR(1, lt * KB + kb);
+        if (own) fence_proxy_async_smem();        // local generic-proxy stores -> async-proxy reads (peer copies are async already)
+        const uint64_t da = desc_kmajor_sw128(stage_addr(sa));
+        mbar_wait(w_full(sw), pw);
+        tc_fence_after();
+        const uint64_t dw = desc_kmajor_sw128(w_smem + sw * C::W_STAGE_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + b * NC, da + 2u * k, dw + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(w_empty(sw));
+          umma_commit(a_empty(sa));
+        }
+        __syncwarp();
+        if (++sw == EF_W_STAGES) { sw = 0; pw ^= 1u; }
+      }
+      if (elect_one()) umma_commit(acc_full(b));
+      __syncwarp();
+      GC_ETR(0, 3 * lt + 2);
+    }
+  } else if (warp < 2 + EF_PRODUCER_WARPS) {
+    // ---------------- A producers for the k-blocks of this CTA's parity (as in the single-CTA FAST path)
+    const int pt = threadIdx.x - 64;
+    const int u = pt & 7;
+    const int i = pt >> 3;
+    const int grow = i / 3;
+    pdl_wait();
+    auto setup = [&](int slot, const __nv_bfloat16* (&ps)[4], uint32_t& vmask) {
+      vmask = 0u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ps[j] = p.gs;
+      if (slot < p.num_tiles) {
+        const int tile = tile_of(p, slot);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t recv = static_cast<int64_t>(tile) * EF_RECV_PER_TILE + 10 * j + grow;
+          if (i < 30 && recv < p.num_receivers) {
+            const int64_t e = static_cast<int64_t>(tile) * (3 * EF_RECV_PER_TILE) + 30 * j + i;
+            ps[j] = p.gs + static_cast<int64_t>(__ldg(p.idx_s + e)) * p.ld_gs + u * 8;
+            vmask |= 1u << j;
+          }
+        }
+      }
+    };
+    auto issue = [&](const __nv_bfloat16* const (&ps)[4], uint32_t vmask, int kb, uint4 (&x)[4]) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (vmask & (1u << j)) x[j] = __ldg(reinterpret_cast<const uint4*>(ps[j] + kb * 64));
+    };
+    const __nv_bfloat16* ps[4];
+    uint32_t vm;
+    uint4 xs[2][4];
+    const int kb0 = static_cast<int>(rank);       // own k-blocks: kb0, kb0 + 2, ...
+    setup(pair_id, ps, vm);
+    issue(ps, vm, kb0, xs[0]);
+    issue(ps, vm, kb0 + 2, xs[1]);
+    int lt = 0;
+    for (int slot = pair_id; slot < p.num_tiles; slot += num_pairs, ++lt) {
+      const __nv_bfloat16* pn[4];
+      uint32_t vn;
+      setup(slot + num_pairs, pn, vn);
+#pragma unroll 2
+      for (int n = 0; n < KB / 2; ++n) {           // n-th own k-block of the tile
+        const int kb = kb0 + 2 * n;
+        const int64_t g = static_cast<int64_t>(lt) * KB + kb;
+        const int sa = static_cast<int>(g % S);
+        const uint32_t pa = static_cast<uint32_t>(g / S) & 1u;
+        uint4 (&cur)[4] = xs[n & 1];
+        if (threadIdx.x == 64) GC_ETR(2, 3 * (lt * (KB / 2) + n));
+        mbar_wait(raw_full(sa), pa);
+        if (threadIdx.x == 64) GC_ETR(2, 3 * (lt * (KB / 2) + n) + 1);
+        const uint32_t stage = stage_addr(sa);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t row = static_cast<uint32_t>(32 * j + i);
+          const uint32_t addr = stage + row * 128u + ((static_cast<uint32_t>(u) ^ (row & 7u)) << 4);
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);
+          if (vm & (1u << j)) {
+            const uint32_t rr = static_cast<uint32_t>(10 * j + grow);
+            const uint32_t raddr = stage + EF_A_STAGE_BYTES + rr * 128u + ((static_cast<uint32_t>(u) ^ (rr & 7u)) << 4);
+            uint4 xb, xr;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xb.x), "=r"(xb.y), "=r"(xb.z), "=r"(xb.w) : "r"(addr));
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xr.x), "=r"(xr.y), "=r"(xr.z), "=r"(xr.w) : "r"(raddr));
+            const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&xb);
+            const __nv_bfloat162* hs = reinterpret_cast<const __nv_bfloat162*>(&cur[j]);
+            const __nv_bfloat162* hr = reinterpret_cast<const __nv_bfloat162*>(&xr);
+            __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 fb = __bfloat1622float2(hb[k]), fs = __bfloat1622float2(hs[k]), fr = __bfloat1622float2(hr[k]);
+              float v0 = fb.x + fs.x + fr.x, v1 = fb.y + fs.y + fr.y;
+              v0 = apply_act<true>(v0, p.act);
+              v1 = apply_act<true>(v1, p.act);
+              ho[k] = __floats2bfloat162_rn(v0, v1);
+            }
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full(sa));
+        if (threadIdx.x == 64) GC_ETR(2, 3 * (lt * (KB / 2) + n) + 2);
+        // refill the register slot with the sender rows of the own k-block after next (of the next tile at the end)
+        if (n + 2 < KB / 2) issue(ps, vm, kb + 4, xs[n & 1]);
+        else issue(pn, vn, kb + 4 - KB, xs[n & 1]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ps[j] = pn[j];
+      vm = vn;
+    }
+  } else if (warp < 2 + EF_PRODUCER_WARPS + EF_EPI_WARPS) {
+    // ---------------- epilogue on this CTA's NC columns: statistics (exchanged with the peer), normalise, 3-row sums
+    const int ew = warp - (2 + EF_PRODUCER_WARPS);
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    constexpr int CH = NC / 2;                           // columns per warp
+    const int et = threadIdx.x - 32 * (2 + EF_PRODUCER_WARPS);
+    const int col0 = static_cast<int>(rank) * NC;        // first output column of this CTA
+    pdl_wait();
+    for (int c = et; c < 3 * NC; c += 32 * EF_EPI_WARPS) {
+      const int which = c / NC, cc = c - which * NC;
+      float v;
+      if (which == 0) v = p.b2 != nullptr ? __ldg(p.b2 + col0 + cc) : 0.0f;
+      else if (p.scale_offset != nullptr) v = __ldg(p.scale_offset + (which - 1) * L + col0 + cc);
+      else v = which == 1 ? 1.0f : 0.0f;
+      vec_s[c] = v;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float* b2s = vec_s + half * CH;
+    const float* scs = vec_s + NC + half * CH;
+    const float* ofs = vec_s + 2 * NC + half * CH;
+    const float inv_n = 1.0f / static_cast<float>(L);
+    const uint32_t xstat_peer = map_to_peer(smem_base + C::XSTAT_OFF, peer);
+    int lt = 0;
+    for (int slot = pair_id; slot < p.num_tiles; slot += num_pairs, ++lt) {
+      const int tile = tile_of(p, slot);
+      const int b = lt & 1;
+      const uint32_t ph = (static_cast<uint32_t>(lt) >> 1) & 1u;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * NC + half * CH;
+      const int rrow = q * 32 + lane;
+      if (et == 0) GC_ETR(3, 4 * lt);
+      mbar_wait(acc_full(b), ph);
+      if (et == 0) GC_ETR(3, 4 * lt + 1);
+      tc_fence_after();
+      // ---- pass 1: row statistics over this warp's columns
+      float s = 0.0f, ss = 0.0f;
+      {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr, r);
+#pragma unroll 1
+        for (int c = 0; c < CH; c += 32) {
+          float v[32];
+          tc_wait_ld();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+          if (c + 32 < CH) tmem_ld_32x32b_x32(taddr + c + 32, r);
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            const float4 bb = *reinterpret_cast<const float4*>(b2s + c + k);
+            const float y0 = v[k] + bb.x, y1 = v[k + 1] + bb.y, y2 = v[k + 2] + bb.z, y3 = v[k + 3] + bb.w;
+            s += (y0 + y1) + (y2 + y3);
+            ss = fmaf(y0, y0, ss); ss = fmaf(y1, y1, ss); ss = fmaf(y2, y2, ss); ss = fmaf(y3, y3, ss);
+          }
+        }
+      }
+      stat_s[(b * 2 + half) * 128 + rrow] = make_float2(s, ss);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // this CTA's partial over its NC columns (halves in fixed order: the same value in both half-warps)
+      const float2 h0 = stat_s[(b * 2 + 0) * 128 + rrow], h1 = stat_s[(b * 2 + 1) * 128 + rrow];
+      const float own_s = h0.x + h1.x, own_ss = h0.y + h1.y;
+      if (half == 0) {
+        // hand it to the peer: store into its shared memory, then arrive (release at cluster scope) on its barrier
+        asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(xstat_peer + static_cast<uint32_t>(b * 128 + rrow) * 8u),
+                     "f"(own_s), "f"(own_ss) : "memory");
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t rb = map_to_peer(stat_full(b), peer);
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rb) : "memory");
+        }
+      }
+      {
+        // wait for the peer's partial (acquire at cluster scope)
+        uint32_t ok = 0;
+        const long long t0 = clock64();
+        while (!ok) {
+          asm volatile(
+              "{\n\t.reg .pred P;\n\t"
+              "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n\t"
+              "selp.u32 %0, 1, 0, P;\n\t}"
+              : "=r"(ok) : "r"(stat_full(b)), "r"(ph), "r"(0x989680u) : "memory");
+          if (!ok && clock64() - t0 > 6000000000LL) __trap();
+        }
+      }
+      if (et == 0) GC_ETR(3, 4 * lt + 2);
+      float mean = 0.0f, rstd = 1.0f;
+      if (p.do_ln) {
+        const float2 o = xstat_s[b * 128 + rrow];
+        // rank order, so that both CTAs form the same sums
+        const float ts = rank == 0 ? own_s + o.x : o.x + own_s;
+        const float tss = rank == 0 ? own_ss + o.y : o.y + own_ss;
+        mean = ts * inv_n;
+        rstd = rsqrtf(fmaxf(tss * inv_n - mean * mean, 0.0f) + EF_LN_EPS);
+      }
+      // ---- pass 2: normalise, 3-row sums across lanes, affine, store (as in the single-CTA kernel)
+      const bool leader = lane < 30 && lane % 3 == 0;
+      const int64_t recv = static_cast<int64_t>(tile) * EF_RECV_PER_TILE + 10 * q + lane / 3;
+      const bool store = leader && recv < p.num_receivers;
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr, r);
+#pragma unroll 1
+      for (int c = 0; c < CH; c += 32) {
+        float v[32];
+        tc_wait_ld();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+        if (c + 32 < CH) {
+          tmem_ld_32x32b_x32(taddr + c + 32, r);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(b));
+        }
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+          const float4 bq = *reinterpret_cast<const float4*>(b2s + c + k);
+          const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float x = (v[k + j] + bb[j] - mean) * rstd;
+            const float x1 = __shfl_down_sync(0xffffffffu, x, 1);
+            const float x2 = __shfl_down_sync(0xffffffffu, x, 2);
+            v[k + j] = (x + x1) + x2;
+          }
+        }
+        if (store) {
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(scs + c + k);
+            const float4 of = *reinterpret_cast<const float4*>(ofs + c + k);
+            v[k] = fmaf(v[k], sc.x, 3.0f * of.x); v[k + 1] = fmaf(v[k + 1], sc.y, 3.0f * of.y);
+            v[k + 2] = fmaf(v[k + 2], sc.z, 3.0f * of.z); v[k + 3] = fmaf(v[k + 3], sc.w, 3.0f * of.w);
+          }
+          const int64_t off = recv * p.ldo + col0 + half * CH + c;
+          if (p.out_dtype == GC_BF16) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) {
+              uint4 o;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[k + 2 * j], v[k + 2 * j + 1]);
+              dst[k >> 3] = o;
+            }
+          } else {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) dst[k >> 2] = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+          }
+        }
+      }
+      if (et == 0) GC_ETR(3, 4 * lt + 3);
+    }
+  } else if (warp == 2 + EF_PRODUCER_WARPS + EF_EPI_WARPS) {
+    // ---------------- operand TMA + flow control, every k-block in order: once the local stage is free, either request
+    // the base / receiver rows of an own k-block, or arm x_full for the peer's copy and tell the peer to go ahead
+    pdl_wait();
+    int lt = 0;
+    for (int slot = pair_id; slot < p.num_tiles; slot += num_pairs, ++lt) {
+      const int tile = tile_of(p, slot);
+      int b_row[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        b_row[j] = static_cast<int>((static_cast<int64_t>(tile) * (3 * EF_RECV_PER_TILE) + 30 * j) % p.period);
+      const int r_row = tile * EF_RECV_PER_TILE;
+      for (int kb = 0; kb < KB; ++kb) {
+        const int64_t g = static_cast<int64_t>(lt) * KB + kb;
+        const int sa = static_cast<int>(g % S);
+        const uint32_t pa = static_cast<uint32_t>(g / S) & 1u;
+        const bool own = (static_cast<uint32_t>(kb) & 1u) == rank;
+        mbar_wait(a_empty(sa), pa ^ 1u);
+        // An own stage is also read by the forwarder's copy of the previous cycle, whose completion is only visible at the
+        // peer.  The peer's go-ahead for THIS cycle (p_empty) comes after its MMAs consumed that copy: wait for it too
+        // before the stage is overwritten.
+        if (own) mbar_wait(p_empty(sa), pa);
+        if (elect_one()) {
+          const uint32_t stage = stage_addr(sa);
+          if (own) {
+            mbar_arrive_expect_tx(raw_full(sa), 4 * 30 * 128 + EF_GR_BYTES);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_2d(stage + j * 4096, &base_map, raw_full(sa), kb * 64, b_row[j]);
+            tma_load_2d(stage + EF_A_STAGE_BYTES, &gr_map, raw_full(sa), kb * 64, r_row);
+          } else {
+            mbar_arrive_expect_tx(x_full(sa), EF_A_STAGE_BYTES);
+            mbar_arrive_cluster(p_empty(sa), peer);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---------------- forwarder: a finished own k-block goes to the same stage of the peer's ring
+    int lt = 0;
+    for (int slot = pair_id; slot < p.num_tiles; slot += num_pairs, ++lt) {
+      for (int kb = static_cast<int>(rank); kb < KB; kb += 2) {
+        const int64_t g = static_cast<int64_t>(lt) * KB + kb;
+        const int sa = static_cast<int>(g % S);
+        const uint32_t pa = static_cast<uint32_t>(g / S) & 1u;
+        mbar_wait(a_full(sa), pa);                 // local producers are done with the stage
+        if (lane == 0) GC_ETR(5, 2 * (lt * (KB / 2) + (kb >> 1)));
+        mbar_wait(p_empty(sa), pa);                // the peer's stage is free and its x_full armed
+        if (lane == 0) GC_ETR(5, 2 * (lt * (KB / 2) + (kb >> 1)) + 1);
+        fence_proxy_async_smem();                  // producers' generic-proxy stores -> the bulk copy's async-proxy reads
+        if (elect_one()) {
+          const uint32_t src = stage_addr(sa);
+          // in the peer this stage is one of the peer-filled ones: same layout in both CTAs, [own | peer-filled]
+          const uint32_t dst = map_to_peer(a_smem + C::PEER_OFF + static_cast<uint32_t>(sa >> 1) * EF_A_STAGE_BYTES, peer);
+          const uint32_t bar = map_to_peer(x_full(sa), peer);
+          asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst), "r"(src), "r"(static_cast<uint32_t>(EF_A_STAGE_BYTES)), "r"(bar) : "memory");
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                           // the peer may still be copying into / reading from this CTA
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * NC);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Second MLP layer + LayerNorm + conditional affine (+ residual) in one kernel, for the node MLPs:
 //     out = LN(A W2^T + b2) * (1 + s) + o (+ residual)            MLPWithNormConditioning, common/mlp.py:115-147,
 //                                                                  residual of common/deep_typed_graph_net.py:569-581
@@ -921,6 +1397,42 @@ int launch_linear_ln(cudaStream_t st, const CUtensorMap& a_map, const CUtensorMa
   return GC_OK;
 }
 
+template <int L>
+int launch_edge_pair(cudaStream_t st, const CUtensorMap& w_map, const CUtensorMap& base_map, const CUtensorMap& gr_map,
+                     const EdgeFusedParams& p) {
+  using C = EPCfg<L>;
+  GC_CHECK_CUDA(cudaFuncSetAttribute(edge_mlp_sum3_pair_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM),
+                "cudaFuncSetAttribute(edge_mlp_sum3_pair_kernel)");
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int pairs = sms / 2;
+  if (p.num_tiles < pairs) pairs = p.num_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(EP_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  GC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, edge_mlp_sum3_pair_kernel<L>, w_map, base_map, gr_map, p), "edge_mlp_sum3_pair_kernel");
+  return GC_OK;
+}
+
+// GENCAST_EDGE_PAIR=1: column-split CTA pair (two accumulators per CTA), for L in {256, 512}.  Opt-in: measured equal to
+// the single-CTA kernel (733 vs 737 us at 1 deg x 4): with the phases overlapped, producers and epilogue both slow
+// down - what saturates is the SM's LSU data pipe (61 % of peak averaged over the single-CTA kernel, ~100 % while its
+// epilogue runs: broadcast LDS.128 of the bias / scale / offset vectors = 4 wavefronts each, two SHFL per element),
+// and that work per tile is the same in both variants.  Read at every call so that tests can switch it.
+bool edge_pair_enabled() {
+  const char* v = getenv("GENCAST_EDGE_PAIR");
+  return v != nullptr && v[0] == '1';
+}
+
 // GENCAST_EDGE_TMA=0: all three operands through registers (the round-2 first version), for A/B measurements
 bool edge_tma_enabled() {
   static const bool on = []() {
@@ -1024,6 +1536,11 @@ extern "C" int gc_edge_mlp_sum3(void* stream, const void* base, int64_t ld_base,
     if (rc != GC_OK) return rc;
     rc = make_tmap_bf16_2d(&gr_map, gr, (uint64_t)num_receivers, (uint64_t)cols, (uint64_t)ld_gr, 64, EF_RECV_PER_TILE);
     if (rc != GC_OK) return rc;
+    if (edge_pair_enabled() && cols >= 256) {
+      // W2 boxes of 128 rows as above; each CTA of a pair loads its half of the rows
+      if (cols == 256) return launch_edge_pair<256>(st, w_map, base_map, gr_map, p);
+      return launch_edge_pair<512>(st, w_map, base_map, gr_map, p);
+    }
     if (cols == 128) return launch_edge_fused<128, 1>(st, w_map, base_map, gr_map, p);
     if (cols == 256) return launch_edge_fused<256, 1>(st, w_map, base_map, gr_map, p);
     return launch_edge_fused<512, 1>(st, w_map, base_map, gr_map, p);
