@@ -1,3 +1,5 @@
+"""Clock-stamp timeline of CTA 0 (rank 0 of pair 0) of the column-split CTA-pair variant of gc_edge_mlp_sum3
+(GENCAST_EDGE_PAIR=1): MMA issuer, producers, forwarder, epilogue.  Usage (GPU box, repo root): python tools/trace_edge_pair.py"""
 import os, sys
 os.environ["GENCAST_EDGE_PAIR"] = "1"
 sys.argv = [sys.argv[0], "4"]
