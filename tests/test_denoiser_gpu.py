@@ -301,6 +301,34 @@ def test_c_forward_equals_python_sequencing(cuda_device, monkeypatch, name, memb
     assert np.array_equal(outs["c"][1], outs["c"][2])
 
 
+@pytest.mark.parametrize("name,members", [("tiny", 2), ("nano", 3)])
+@pytest.mark.parametrize("impl", ["py", "c"])
+def test_fused_edge_kernels_equal_unfused_paths(cuda_device, monkeypatch, name, members, impl):
+    """bf16 evaluation with the fused edge kernels (gc_edge_mlp_rows for grid2mesh with the receivers' part folded into
+    the per-level table, gc_edge_mlp_sum3 for mesh2grid) against GENCAST_EDGE_FUSED=0 (gc_edge_hidden -> gc_gemm ->
+    gc_ln_cond_segment_sum): the same network up to bf16 rounding of intermediates, through both sequencers."""
+    from gencast_flax_nnx_b200.engine import DenoiserEngine
+    case = make_case(name)
+    B, G = members, case.graphs.num_grid_nodes
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((B * G, 82)).astype(np.float32)
+    inp = np.concatenate([case.inp_nodes[:, 0] * (1 + 0.1 * b) for b in range(B)])
+    frc = np.concatenate([case.frc_nodes[:, 0]] * B)
+    monkeypatch.setenv("GENCAST_FORWARD", impl)
+    outs = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("GENCAST_EDGE_FUSED", fused)
+        eng = DenoiserEngine(case.graphs, case.arch, case.params, case.layout, compute_dtype="bf16", members=B)
+        assert eng.fuse_m2g == (fused == "1") and eng.fuse_g2m == (fused == "1")
+        eng.set_constant_features(inp, frc)
+        eng.set_network_input(x)
+        outs[fused] = eng.read_output(eng.forward(eng.sigma_context(0.7, pin=True)))
+    a, b = outs["1"], outs["0"]
+    assert np.isfinite(a).all() and np.isfinite(b).all()
+    scale = np.abs(b).max(axis=0) + 1e-6
+    assert (np.abs(a - b).max(axis=0) / scale).max() < 1.5e-2       # bf16 noise of two roundings of the edge latents
+
+
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
 def test_sampler_with_stochastic_churn_matches_oracle(cuda_device, dtype):
     """DPM-Solver++ 2S with stochastic churn (gencast/samplers_utils.py:414-452, dpm...2s.py:127-137): churned steps
