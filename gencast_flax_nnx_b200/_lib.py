@@ -119,6 +119,8 @@ SIGNATURES = {
                              c_void_p, c_int32, c_int64, c_int64, c_int32]),
     "gc_ln_cond_segment_sum": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_int32, c_void_p, c_void_p,
                                          c_void_p, c_int32, c_int64, c_int64, c_int32]),
+    "gc_ln_cond_segment_sum_stats": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_int32, c_void_p, c_void_p,
+                                               c_void_p, c_int32, c_int64, c_int64, c_int32, c_void_p]),
     "gc_khop_attention": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_int32, c_void_p,
                                     c_int64, c_int64, c_int32, c_int32]),
     "gc_khop_attention_tiles": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -147,7 +149,7 @@ SIGNATURES = {
                                    c_int64, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_int32,
                                    c_int64, c_int64, c_int32]),
     "gc_edge_mlp_rows": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int64,
-                                   c_void_p, c_void_p, c_int64, c_int64, c_int32]),
+                                   c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p]),
     "gc_denoiser_forward": (c_int32, [c_void_p, POINTER(DenoiserModel), POINTER(DenoiserGraph), POINTER(SigmaContextC),
                                       POINTER(DenoiserWorkspace)]),
     "gc_sizeof_forward_structs": (c_int32, [c_int32]),

@@ -97,6 +97,7 @@ struct EdgeFusedParams {
   int num_tiles;
   int members, tiles_per_member;   // tile order: see tile_of()
   int64_t num_rows;                // ROWS mode: members * period edges
+  float* row_stats;                // ROWS mode, optional: [num_rows][2 halves] (sum, sum of squares) of y over the half's columns
   long long* trace;
 };
 
@@ -471,6 +472,7 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
         tc_fence_after();
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr, r);
+        float rs = 0.0f, rss = 0.0f;                   // this row's sum / sum of squares of y over this warp's columns
 #pragma unroll 1
         for (int c = 0; c < CH; c += 32) {
           float v[32];
@@ -493,12 +495,19 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
           for (int k = 0; k < 32; k += 8) {
             const float4 b0 = *reinterpret_cast<const float4*>(b2s + c + k);
             const float4 b1 = *reinterpret_cast<const float4*>(b2s + c + k + 4);
+            const float y0 = v[k] + b0.x, y1 = v[k + 1] + b0.y, y2 = v[k + 2] + b0.z, y3 = v[k + 3] + b0.w;
+            const float y4 = v[k + 4] + b1.x, y5 = v[k + 5] + b1.y, y6 = v[k + 6] + b1.z, y7 = v[k + 7] + b1.w;
+            if (p.row_stats != nullptr) {              // warp-uniform; statistics of the fp32 values, before rounding
+              rs += ((y0 + y1) + (y2 + y3)) + ((y4 + y5) + (y6 + y7));
+              rss = fmaf(y0, y0, rss); rss = fmaf(y1, y1, rss); rss = fmaf(y2, y2, rss); rss = fmaf(y3, y3, rss);
+              rss = fmaf(y4, y4, rss); rss = fmaf(y5, y5, rss); rss = fmaf(y6, y6, rss); rss = fmaf(y7, y7, rss);
+            }
             uint4 o;
             __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
-            h[0] = __floats2bfloat162_rn(v[k] + b0.x, v[k + 1] + b0.y);
-            h[1] = __floats2bfloat162_rn(v[k + 2] + b0.z, v[k + 3] + b0.w);
-            h[2] = __floats2bfloat162_rn(v[k + 4] + b1.x, v[k + 5] + b1.y);
-            h[3] = __floats2bfloat162_rn(v[k + 6] + b1.z, v[k + 7] + b1.w);
+            h[0] = __floats2bfloat162_rn(y0, y1);
+            h[1] = __floats2bfloat162_rn(y2, y3);
+            h[2] = __floats2bfloat162_rn(y4, y5);
+            h[3] = __floats2bfloat162_rn(y6, y7);
             if (whole) {
               const uint32_t unit = static_cast<uint32_t>(hc * 4 + (k >> 3)) ^ sw;
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_buf + static_cast<uint32_t>(lane) * 128u + unit * 16u),
@@ -516,6 +525,8 @@ edge_mlp_sum3_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_con
             }
           }
         }
+        if (p.row_stats != nullptr && store)
+          *reinterpret_cast<float2*>(p.row_stats + (grow0 + lane) * 4 + half * 2) = make_float2(rs, rss);
         if (et == 0) GC_ETR(3, 4 * lt + 3);
       }
       if (lane == 0) bulk_wait_group_all();
@@ -1518,7 +1529,7 @@ extern "C" int gc_edge_mlp_sum3(void* stream, const void* base, int64_t ld_base,
   p.act = act; p.b2 = b2; p.scale_offset = scale_offset; p.do_ln = do_layer_norm;
   p.out = out; p.out_dtype = out_dtype; p.ldo = ldo; p.num_receivers = num_receivers;
   p.num_tiles = (int)((num_receivers + EF_RECV_PER_TILE - 1) / EF_RECV_PER_TILE);
-  p.members = 1; p.tiles_per_member = p.num_tiles; p.num_rows = 0;
+  p.members = 1; p.tiles_per_member = p.num_tiles; p.num_rows = 0; p.row_stats = nullptr;
   p.trace = g_edge_fused_trace;
   {
     const int64_t edges = 3 * num_receivers, per_tile = 3 * EF_RECV_PER_TILE;
@@ -1552,7 +1563,7 @@ extern "C" int gc_edge_mlp_sum3(void* stream, const void* base, int64_t ld_base,
 
 extern "C" int gc_edge_mlp_rows(void* stream, const void* base, int64_t ld_base, int64_t period, const void* gs,
                                 const int32_t* idx_s, int64_t ld_gs, int32_t act, const void* w2, int64_t ld_w2,
-                                const float* b2, void* out, int64_t ldo, int64_t num_rows, int32_t cols) {
+                                const float* b2, void* out, int64_t ldo, int64_t num_rows, int32_t cols, float* row_stats) {
   using namespace gc;
   GC_REQUIRE(base && gs && idx_s && w2 && out, "gc_edge_mlp_rows: null buffer");
   GC_REQUIRE(cols == 128 || cols == 256 || cols == 512, "gc_edge_mlp_rows: cols=%d (supported: 128, 256, 512)", cols);
@@ -1561,6 +1572,7 @@ extern "C" int gc_edge_mlp_rows(void* stream, const void* base, int64_t ld_base,
   GC_REQUIRE(ld_base % 8 == 0 && ld_gs % 8 == 0 && ld_w2 % 8 == 0 && ldo % 8 == 0 && aligned16(base) && aligned16(gs) &&
                  aligned16(w2) && aligned16(out), "gc_edge_mlp_rows: alignment");
   GC_REQUIRE(act == GC_ACT_NONE || act == GC_ACT_SWISH || act == GC_ACT_GELU_TANH, "gc_edge_mlp_rows: act=%d", act);
+  GC_REQUIRE(row_stats == nullptr || aligned16(row_stats), "gc_edge_mlp_rows: row_stats alignment");
   if (num_rows == 0) return GC_OK;
   CUtensorMap w_map, base_map, out_map;
   int rc = make_tmap_bf16_2d(&w_map, w2, (uint64_t)cols, (uint64_t)cols, (uint64_t)ld_w2, 64, 128);
@@ -1575,6 +1587,7 @@ extern "C" int gc_edge_mlp_rows(void* stream, const void* base, int64_t ld_base,
   p.gr = nullptr; p.idx_r = nullptr; p.ld_gr = 0;
   p.act = act; p.b2 = b2; p.scale_offset = nullptr; p.do_ln = 0;
   p.out = out; p.out_dtype = GC_BF16; p.ldo = ldo; p.num_receivers = 0; p.num_rows = num_rows;
+  p.row_stats = row_stats;
   p.members = (int)(num_rows / period);
   p.tiles_per_member = (int)((period + 127) / 128);
   p.num_tiles = p.members * p.tiles_per_member;

@@ -121,8 +121,9 @@ extern "C" int gc_denoiser_forward(void* stream, const gc_denoiser_model* m, con
     const bool fuse_g2m = (ws->flags & GC_FORWARD_FUSE_G2M) != 0 && sc->g2m_base != nullptr && dt == GC_BF16;
     if (fuse_g2m) {
       // the table already holds e' W1e' + b1 + (m0 W1r)[receivers]: hidden layer, second layer and bias in one kernel
+      // the rows' LayerNorm statistics go to the hidden-layer buffer, which this path does not use (16 bytes per edge)
       GC_TRY(gc_edge_mlp_rows(st, sc->g2m_base, L, sc->g2m_base_rows, ws->g_p, g->g2m_senders, L, GC_ACT_SWISH, m->g2m_w2, L,
-                              m->g2m_b2, ws->e_y, L, E1, L));
+                              m->g2m_b2, ws->e_y, L, E1, L, reinterpret_cast<float*>(ws->e_h)));
     } else if (sc->g2m_base != nullptr) {
       GC_TRY(gc_edge_hidden(st, sc->g2m_base, L, sc->g2m_base_rows, ws->g_p, g->g2m_senders, L, sc->m_p, g->g2m_receivers, L,
                             GC_ACT_SWISH, ws->e_h, L, E1, L));
@@ -135,8 +136,9 @@ extern "C" int gc_denoiser_forward(void* stream, const gc_denoiser_model* m, con
       const Seg s2{ws->e_h, L, m->g2m_w2, L};
       GC_TRY(run_gemm(c, st, &s2, 1, E1, L, ws->e_y, dt, m->g2m_b2, GC_ACT_NONE, nullptr, 0, nullptr, nullptr, nullptr, nullptr, true));
     }
-    GC_TRY(gc_ln_cond_segment_sum(st, ws->e_y, dt, L, T(GC_COND_G2M_EDGE_UPDATE), 1 | GC_SEGSUM_IRREGULAR, g->g2m_row_ptr,
-                                  g->g2m_perm, ws->m_agg, dt, L, V, L));
+    GC_TRY(gc_ln_cond_segment_sum_stats(st, ws->e_y, dt, L, T(GC_COND_G2M_EDGE_UPDATE), 1 | GC_SEGSUM_IRREGULAR, g->g2m_row_ptr,
+                                        g->g2m_perm, ws->m_agg, dt, L, V, L,
+                                        fuse_g2m ? reinterpret_cast<const float*>(ws->e_h) : nullptr));
   }
   // mesh-node update (+ residual) -> fp32 transformer stream
   {

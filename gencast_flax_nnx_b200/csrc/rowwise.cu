@@ -111,21 +111,33 @@ __global__ void __launch_bounds__(256) ln_cond_kernel(const void* __restrict__ x
 constexpr int SEG_WARPS = 8;
 constexpr int HEAVY = 32;
 constexpr int SEG_UNROLL = 3;
+constexpr int SEG_RING = 6;                 // rows per warp in flight in the shared-memory ring variant
 constexpr int SEG_HEAVY_PER_WARP = 64;   // heavy receivers a warp can defer to the block (beyond: it sums them itself)
 
-// OCC = resident blocks per SM the register budget is cut for.  Regular low-degree graphs (mesh2grid: three
+// OCC = resident blocks per SM the register budget is cut for; the grid is one wave of exactly those blocks (receivers
+// are strided over the blocks, so a partial last wave - 2.67 waves with the former 8 blocks per SM - was a pure tail and
+// left the warps of a block waiting at the barrier before the heavy-receiver pass).  Regular low-degree graphs (mesh2grid: three
 // rows per receiver, no permutation) run best with the full budget (2 blocks, no spills: 305 us vs 365 us
 // at 1 deg x 4); irregular ones (grid2mesh: degrees 3 .. 594 through edge_perm) gain more from a third
 // block of warps than they lose to a few spilled registers (205 us vs 246 us).
-template <int NV, bool BF16, int OCC>
+// STATS: the producer of y (gc_edge_mlp_rows) also wrote, per row, the sum and the sum of squares of the row's two column
+// halves from its fp32 accumulator (row_stats[row] = {s0, ss0, s1, ss1}).  The row's mean and rstd then cost a broadcast
+// 16-byte load instead of 32 multiply-adds and two warp reductions, and the kernel moves from instruction-bound (249
+// instructions per row) towards the HBM roofline.
+// RING (bf16 rows stored receiver-sorted, no edge permutation): pass 1 streams the rows of a warp's receivers through a
+// per-warp ring of SEG_RING rows in shared memory filled by cp.async, so a warp always has that many rows in flight,
+// whatever the in-degrees, without holding them in registers: the register-batch version exposed one load latency per
+// batch of three rows (long_scoreboard 10 stall cycles per issued instruction in ncu, 2.3-2.6 TB/s).
+template <int NV, bool BF16, int OCC, bool STATS = false, bool RING = false>
 __global__ void __launch_bounds__(SEG_WARPS * 32, OCC) ln_cond_segment_sum_kernel(
     const void* __restrict__ y, int64_t ldy, const float* __restrict__ scale_offset, int do_ln,
     const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ edge_perm, void* __restrict__ out,
-    int out_dtype, int64_t ldo, int64_t num_segments) {
+    int out_dtype, int64_t ldo, int64_t num_segments, const float* __restrict__ row_stats) {
   constexpr int cols = NV * 32;
   constexpr int W = NV % 8 == 0 ? 8 : 4;            // consecutive elements per lane and chunk
   constexpr int NCH = NV / W;
-  constexpr int RAW = BF16 ? NV / 2 : NV;           // 32-bit registers of one row per lane, as loaded
+  constexpr int RAWD = BF16 ? NV / 2 : NV;          // 32-bit registers of one row per lane, as loaded
+  constexpr int RAW = RAWD + (STATS ? 2 : 0);       // ... followed by the row's (sum, sum of squares), the same in every lane
   __shared__ __align__(16) float partial[SEG_WARPS][cols];
   __shared__ __align__(16) float so_s[2 * cols];
   __shared__ int heavy_list[SEG_WARPS][SEG_HEAVY_PER_WARP];
@@ -162,6 +174,11 @@ __global__ void __launch_bounds__(SEG_WARPS * 32, OCC) ln_cond_segment_sum_kerne
         }
       }
     }
+    if constexpr (STATS) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(row_stats) + e);
+      raw[RAWD] = __float_as_uint(q.x + q.z);          // halves in fixed order
+      raw[RAWD + 1] = __float_as_uint(q.y + q.w);
+    }
   };
   // rows [j0, min(j0 + SEG_UNROLL, end)) of the edge list -> raw
   auto load_batch = [&](int j0, int end, uint32_t (&raw)[SEG_UNROLL][RAW]) {
@@ -173,37 +190,44 @@ __global__ void __launch_bounds__(SEG_WARPS * 32, OCC) ln_cond_segment_sum_kerne
       }
     }
   };
-  // acc += LN(row) (or row) for the rows of one batch, in edge order
+  // acc += LN(row) (or row)
+  auto consume_row = [&](const uint32_t (&raw)[RAW], float (&acc)[NV]) {
+    float v[NV];
+    if constexpr (BF16) {
+#pragma unroll
+      for (int i = 0; i < NV / 2; ++i) {         // bf16 -> fp32 is a 16-bit shift
+        v[2 * i] = __uint_as_float(raw[i] << 16);
+        v[2 * i + 1] = __uint_as_float(raw[i] & 0xffff0000u);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = __uint_as_float(raw[i]);
+    }
+    if (do_ln) {
+      float s = 0.0f, ss = 0.0f;
+      if constexpr (STATS) {
+        s = __uint_as_float(raw[RAWD]);
+        ss = __uint_as_float(raw[RAWD + 1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { s += v[i]; ss = fmaf(v[i], v[i], ss); }
+        s = warp_sum(s);
+        ss = warp_sum(ss);
+      }
+      const float mean = s * inv_n;
+      const float rstd = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.0f) + LN_EPS);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] = fmaf(v[i] - mean, rstd, acc[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] += v[i];
+    }
+  };
+  // the rows of one batch, in edge order
   auto consume_batch = [&](int j0, int end, const uint32_t (&raw)[SEG_UNROLL][RAW], float (&acc)[NV]) {
 #pragma unroll
     for (int u = 0; u < SEG_UNROLL; ++u) {
-      if (j0 + u < end) {
-        float v[NV];
-        if constexpr (BF16) {
-#pragma unroll
-          for (int i = 0; i < NV / 2; ++i) {     // bf16 -> fp32 is a 16-bit shift
-            v[2 * i] = __uint_as_float(raw[u][i] << 16);
-            v[2 * i + 1] = __uint_as_float(raw[u][i] & 0xffff0000u);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < NV; ++i) v[i] = __uint_as_float(raw[u][i]);
-        }
-        if (do_ln) {
-          float s = 0.0f, ss = 0.0f;
-#pragma unroll
-          for (int i = 0; i < NV; ++i) { s += v[i]; ss = fmaf(v[i], v[i], ss); }
-          s = warp_sum(s);
-          ss = warp_sum(ss);
-          const float mean = s * inv_n;
-          const float rstd = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.0f) + LN_EPS);
-#pragma unroll
-          for (int i = 0; i < NV; ++i) acc[i] = fmaf(v[i] - mean, rstd, acc[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < NV; ++i) acc[i] += v[i];
-        }
-      }
+      if (j0 + u < end) consume_row(raw[u], acc);
     }
   };
   // remaining batches of a range whose first batch is already in `first`
@@ -247,6 +271,119 @@ __global__ void __launch_bounds__(SEG_WARPS * 32, OCC) ln_cond_segment_sum_kerne
     if (sg < num_segments) { b = __ldg(row_ptr + sg); e = __ldg(row_ptr + sg + 1); }
   };
   int my_heavy = 0;
+  if constexpr (RING) {
+    // One rolling stream of rows per warp: the rows of its receivers k, k + 8, ... concatenated.  A slot of the ring
+    // carries its receiver and, on the receiver's last row, the in-degree; it is refilled as soon as it has been read.
+    // Rows are added in row order per receiver, as in the register version: the same bits.
+    extern __shared__ __align__(16) uint8_t ring_raw[];
+    constexpr int ROWB = cols * 2;                  // bytes of a bf16 row
+    constexpr int SLOTB = ROWB + 16;                // + the row's statistics
+    constexpr int R = SEG_RING;
+    const uint32_t ring = static_cast<uint32_t>(__cvta_generic_to_shared(ring_raw)) + static_cast<uint32_t>(warp) * (R * SLOTB);
+    int64_t g_k = static_cast<int64_t>(warp) - SEG_WARPS;
+    int g_row = 0, g_end = 0, g_deg = 0;
+    int64_t g_seg = 0;
+    bool g_done = false;
+    int nb0, ne0, nb1, ne1, nb2, ne2;               // bounds of the next three receivers, requested ahead
+    load_bounds(warp, nb0, ne0);
+    load_bounds(warp + SEG_WARPS, nb1, ne1);
+    load_bounds(warp + 2 * SEG_WARPS, nb2, ne2);
+    auto next_row = [&](int& row, int64_t& seg, int& last_deg) -> bool {
+      while (!g_done && g_row == g_end) {
+        g_k += SEG_WARPS;
+        const int b = nb0, e = ne0;
+        nb0 = nb1; ne0 = ne1; nb1 = nb2; ne1 = ne2;
+        load_bounds(g_k + 3 * SEG_WARPS, nb2, ne2);
+        if (e < b) { g_done = true; break; }
+        const int64_t sg = seg_of(g_k);
+        const int deg = e - b;
+        if (deg == 0) {                             // receiver without edges: (1 + s) * 0 + 0 * o
+          float zero[NV];
+#pragma unroll
+          for (int i = 0; i < NV; ++i) zero[i] = 0.0f;
+          finish(sg, 0, zero);
+          continue;
+        }
+        if (deg > HEAVY && my_heavy < SEG_HEAVY_PER_WARP) {
+          if (lane == 0) heavy_list[warp][my_heavy] = static_cast<int>(g_k);
+          ++my_heavy;
+          continue;
+        }
+        g_row = b; g_end = e; g_seg = sg; g_deg = deg;
+      }
+      if (g_done) return false;
+      row = g_row++;
+      seg = g_seg;
+      last_deg = g_row == g_end ? g_deg : 0;
+      return true;
+    };
+    int64_t slot_seg[R];
+    int slot_deg[R];                                // -1: empty; 0: inner row; > 0: last row of a receiver of that degree
+    auto fill = [&](int u) {
+      int row;
+      slot_deg[u] = -1;
+      if (next_row(row, slot_seg[u], slot_deg[u])) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(y) + static_cast<int64_t>(row) * ldy * 2;
+        const uint32_t dst = ring + static_cast<uint32_t>(u) * SLOTB;
+#pragma unroll
+        for (int j = 0; j < ROWB / 512; ++j)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + j * 512 + lane * 16), "l"(src + j * 512 + lane * 16) : "memory");
+        if constexpr (ROWB % 512 != 0) {
+          if (lane * 16 < ROWB % 512)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (ROWB / 512) * 512 + lane * 16),
+                         "l"(src + (ROWB / 512) * 512 + lane * 16) : "memory");
+        }
+        if constexpr (STATS) {
+          if (lane == 0)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + ROWB), "l"(row_stats + static_cast<int64_t>(row) * 4) : "memory");
+        }
+      } else {
+        slot_deg[u] = -1;
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");     // one group per call, empty or not: wait counts stay uniform
+    };
+#pragma unroll
+    for (int u = 0; u < R; ++u) fill(u);
+    float acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
+    while (slot_deg[0] >= 0) {                      // slots are filled in order: slot 0 empty = stream exhausted
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        if (slot_deg[u] >= 0) {                     // warp-uniform
+          asm volatile("cp.async.wait_group %0;" ::"n"(R - 1) : "memory");    // the oldest group = this slot's
+          __syncwarp();
+          uint32_t raw[RAW];
+          const uint32_t src = ring + static_cast<uint32_t>(u) * SLOTB;
+#pragma unroll
+          for (int j = 0; j < NCH; ++j) {
+            const uint32_t a = src + static_cast<uint32_t>((j * 32 + lane) * W) * 2u;
+            if constexpr (W == 8) {
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(raw[4 * j]), "=r"(raw[4 * j + 1]), "=r"(raw[4 * j + 2]),
+                           "=r"(raw[4 * j + 3]) : "r"(a));
+            } else {
+              asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(raw[2 * j]), "=r"(raw[2 * j + 1]) : "r"(a));
+            }
+          }
+          if constexpr (STATS) {
+            float4 q;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(src + ROWB));
+            raw[RAWD] = __float_as_uint(q.x + q.z);
+            raw[RAWD + 1] = __float_as_uint(q.y + q.w);
+          }
+          consume_row(raw, acc);
+          if (slot_deg[u] > 0) {
+            finish(slot_seg[u], slot_deg[u], acc);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
+          }
+          __syncwarp();                             // every lane has read the slot before it is refilled
+          fill(u);
+        }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else {
   // decides what to do with receiver kk given its bounds; light ones get their first rows requested
   auto open_segment = [&](int64_t kk, int b, int e, bool& is_light, uint32_t (&raw)[SEG_UNROLL][RAW]) {
     is_light = false;
@@ -285,6 +422,7 @@ __global__ void __launch_bounds__(SEG_WARPS * 32, OCC) ln_cond_segment_sum_kerne
 #pragma unroll
       for (int i = 0; i < RAW; ++i) cur[u][i] = nxt[u][i];
   }
+  }
   if (lane == 0) heavy_count[warp] = my_heavy;
   __syncthreads();
 
@@ -297,9 +435,71 @@ __global__ void __launch_bounds__(SEG_WARPS * 32, OCC) ln_cond_segment_sum_kerne
       const int per = (he - hb + SEG_WARPS - 1) / SEG_WARPS;
       const int b = min(hb + warp * per, he), e = min(b + per, he);
       float acc[NV];
-      uint32_t first[SEG_UNROLL][RAW];
-      load_batch(b, e, first);
-      accumulate_rest(b, e, first, acc);
+      if constexpr (RING) {
+        // this warp's slice of the receiver's rows through its shared-memory ring (rows in flight: SEG_RING instead of one
+        // batch of three; a 594-edge receiver was ~27 us of tail for its block)
+        extern __shared__ __align__(16) uint8_t ring_raw[];
+        constexpr int ROWB = cols * 2, SLOTB = ROWB + 16, R = SEG_RING;
+        const uint32_t ring = static_cast<uint32_t>(__cvta_generic_to_shared(ring_raw)) + static_cast<uint32_t>(warp) * (R * SLOTB);
+        auto request = [&](int row, int u) {
+          if (row < e) {
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(y) + static_cast<int64_t>(row) * ldy * 2;
+            const uint32_t dst = ring + static_cast<uint32_t>(u) * SLOTB;
+#pragma unroll
+            for (int j = 0; j < ROWB / 512; ++j)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + j * 512 + lane * 16), "l"(src + j * 512 + lane * 16) : "memory");
+            if constexpr (ROWB % 512 != 0) {
+              if (lane * 16 < ROWB % 512)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (ROWB / 512) * 512 + lane * 16),
+                             "l"(src + (ROWB / 512) * 512 + lane * 16) : "memory");
+            }
+            if constexpr (STATS) {
+              if (lane == 0)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + ROWB), "l"(row_stats + static_cast<int64_t>(row) * 4) : "memory");
+            }
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] = 0.0f;
+#pragma unroll
+        for (int u = 0; u < R; ++u) request(b + u, u);
+        for (int r0 = b; r0 < e; r0 += R) {
+#pragma unroll
+          for (int u = 0; u < R; ++u) {
+            if (r0 + u < e) {                       // warp-uniform
+              asm volatile("cp.async.wait_group %0;" ::"n"(R - 1) : "memory");
+              __syncwarp();
+              uint32_t raw[RAW];
+              const uint32_t src = ring + static_cast<uint32_t>(u) * SLOTB;
+#pragma unroll
+              for (int j = 0; j < NCH; ++j) {
+                const uint32_t a = src + static_cast<uint32_t>((j * 32 + lane) * W) * 2u;
+                if constexpr (W == 8) {
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(raw[4 * j]), "=r"(raw[4 * j + 1]), "=r"(raw[4 * j + 2]),
+                               "=r"(raw[4 * j + 3]) : "r"(a));
+                } else {
+                  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(raw[2 * j]), "=r"(raw[2 * j + 1]) : "r"(a));
+                }
+              }
+              if constexpr (STATS) {
+                float4 q;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(src + ROWB));
+                raw[RAWD] = __float_as_uint(q.x + q.z);
+                raw[RAWD + 1] = __float_as_uint(q.y + q.w);
+              }
+              consume_row(raw, acc);
+              __syncwarp();
+              request(r0 + u + R, u);
+            }
+          }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      } else {
+        uint32_t first[SEG_UNROLL][RAW];
+        load_batch(b, e, first);
+        accumulate_rest(b, e, first, acc);
+      }
 #pragma unroll
       for (int i = 0; i < NV; ++i) partial[warp][i * 32 + lane] = acc[i];
       __syncthreads();
@@ -708,36 +908,65 @@ int gc_ln_cond(void* stream, const void* x, int32_t x_dtype, int64_t ldx, const 
   return GC_OK;
 }
 
-int gc_ln_cond_segment_sum(void* stream, const void* y, int32_t y_dtype, int64_t ldy, const float* scale_offset,
-                           int32_t do_layer_norm, const int32_t* row_ptr, const int32_t* edge_perm, void* out,
-                           int32_t out_dtype, int64_t ldo, int64_t num_segments, int32_t cols) {
+int gc_ln_cond_segment_sum_stats(void* stream, const void* y, int32_t y_dtype, int64_t ldy, const float* scale_offset,
+                                 int32_t do_layer_norm, const int32_t* row_ptr, const int32_t* edge_perm, void* out,
+                                 int32_t out_dtype, int64_t ldo, int64_t num_segments, int32_t cols, const float* row_stats) {
   GC_REQUIRE(y && out && row_ptr, "gc_ln_cond_segment_sum: null buffer");
   GC_REQUIRE(cols == 128 || cols == 256 || cols == 512, "gc_ln_cond_segment_sum: cols=%d (supported: 128, 256, 512)", cols);
   GC_REQUIRE(dtype_ok(y_dtype) && dtype_ok(out_dtype), "gc_ln_cond_segment_sum: bad dtype");
   GC_REQUIRE(ldy % 8 == 0 && ldo % 8 == 0 && aligned16(y) && aligned16(out), "gc_ln_cond_segment_sum: alignment");
   if (scale_offset) GC_REQUIRE(aligned16(scale_offset), "gc_ln_cond_segment_sum: scale_offset alignment");
+  if (row_stats) GC_REQUIRE(aligned16(row_stats) && y_dtype == GC_BF16 && (do_layer_norm & 1),
+                            "gc_ln_cond_segment_sum_stats: row statistics need 16-byte alignment, bf16 rows and LayerNorm");
   if (num_segments <= 0) return GC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const unsigned grid = grid_for(num_segments, SEG_WARPS, 8);
   const int do_ln = do_layer_norm & 1;
   const bool irregular = edge_perm != nullptr || (do_layer_norm & GC_SEGSUM_IRREGULAR) != 0;
-#define GC_LAUNCH_SEG(NV, BF, OCC)                                                                             \
-  GC_CHECK_CUDA(launch_kernel(ln_cond_segment_sum_kernel<NV, BF, OCC>, dim3(grid), dim3(SEG_WARPS * 32), 0, st, y, ldy, \
-                              scale_offset, do_ln, row_ptr, edge_perm, out, out_dtype, ldo, num_segments),              \
-                "ln_cond_segment_sum_kernel")
-  if (y_dtype == GC_BF16) {
-    if (cols == 128) GC_LAUNCH_SEG(4, true, 2);
-    else if (cols == 256) GC_LAUNCH_SEG(8, true, 2);
-    else if (irregular) GC_LAUNCH_SEG(16, true, 3);
-    else GC_LAUNCH_SEG(16, true, 2);
+#define GC_LAUNCH_SEG(NV, BF, OCC, ST, RG)                                                                      \
+  do {                                                                                                          \
+    auto kernel = ln_cond_segment_sum_kernel<NV, BF, OCC, ST, RG>;                                               \
+    const size_t ring_bytes = RG ? static_cast<size_t>(SEG_WARPS) * SEG_RING * (NV * 32 * 2 + 16) : 0;          \
+    if (RG) GC_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes), \
+                          "cudaFuncSetAttribute(ln_cond_segment_sum_kernel)");                                  \
+    GC_CHECK_CUDA(launch_kernel(kernel, dim3(grid_for(num_segments, SEG_WARPS, OCC)), dim3(SEG_WARPS * 32), ring_bytes, st, \
+                                y, ldy, scale_offset, do_ln, row_ptr, edge_perm, out, out_dtype, ldo, num_segments,    \
+                                row_stats), "ln_cond_segment_sum_kernel");                                      \
+  } while (0)
+  // bf16 rows without an edge permutation stream through the shared-memory ring (GENCAST_SEGSUM_RING=0: register batches)
+  static const bool ring_on = []() { const char* v = getenv("GENCAST_SEGSUM_RING"); return !(v != nullptr && v[0] == '0'); }();
+  const bool ring = ring_on && y_dtype == GC_BF16 && edge_perm == nullptr;
+  if (ring && row_stats != nullptr) {
+    if (cols == 128) GC_LAUNCH_SEG(4, true, 3, true, true);
+    else if (cols == 256) GC_LAUNCH_SEG(8, true, 3, true, true);
+    else GC_LAUNCH_SEG(16, true, 3, true, true);
+  } else if (ring) {
+    if (cols == 128) GC_LAUNCH_SEG(4, true, 3, false, true);
+    else if (cols == 256) GC_LAUNCH_SEG(8, true, 3, false, true);
+    else GC_LAUNCH_SEG(16, true, 3, false, true);
+  } else if (y_dtype == GC_BF16 && row_stats != nullptr) {
+    if (cols == 128) GC_LAUNCH_SEG(4, true, 2, true, false);
+    else if (cols == 256) GC_LAUNCH_SEG(8, true, 2, true, false);
+    else GC_LAUNCH_SEG(16, true, 3, true, false);
+  } else if (y_dtype == GC_BF16) {
+    if (cols == 128) GC_LAUNCH_SEG(4, true, 2, false, false);
+    else if (cols == 256) GC_LAUNCH_SEG(8, true, 2, false, false);
+    else if (irregular) GC_LAUNCH_SEG(16, true, 3, false, false);
+    else GC_LAUNCH_SEG(16, true, 2, false, false);
   } else {
-    if (cols == 128) GC_LAUNCH_SEG(4, false, 2);
-    else if (cols == 256) GC_LAUNCH_SEG(8, false, 2);
-    else GC_LAUNCH_SEG(16, false, 2);
+    if (cols == 128) GC_LAUNCH_SEG(4, false, 2, false, false);
+    else if (cols == 256) GC_LAUNCH_SEG(8, false, 2, false, false);
+    else GC_LAUNCH_SEG(16, false, 2, false, false);
   }
 #undef GC_LAUNCH_SEG
   GC_CHECK_LAUNCH("ln_cond_segment_sum_kernel");
   return GC_OK;
+}
+
+int gc_ln_cond_segment_sum(void* stream, const void* y, int32_t y_dtype, int64_t ldy, const float* scale_offset,
+                           int32_t do_layer_norm, const int32_t* row_ptr, const int32_t* edge_perm, void* out,
+                           int32_t out_dtype, int64_t ldo, int64_t num_segments, int32_t cols) {
+  return gc_ln_cond_segment_sum_stats(stream, y, y_dtype, ldy, scale_offset, do_layer_norm, row_ptr, edge_perm, out, out_dtype,
+                                      ldo, num_segments, cols, nullptr);
 }
 
 int gc_cond_tables(void* stream, const float* sigma, int32_t num_sigma, const float* w0, const float* b0,

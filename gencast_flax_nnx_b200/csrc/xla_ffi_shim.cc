@@ -138,7 +138,8 @@ static ffi::Error EdgeMlpRowsImpl(cudaStream_t stream, ffi::Buffer<ffi::BF16> ba
                                   int32_t act) {
   const int32_t cols = (int32_t)out->dimensions()[1];
   return status(gc_edge_mlp_rows(stream, base.typed_data(), cols, base.dimensions()[0], gs.typed_data(), is.typed_data(), cols, act,
-                                 w2.typed_data(), cols, b2.typed_data(), out->typed_data(), cols, out->dimensions()[0], cols));
+                                 w2.typed_data(), cols, b2.typed_data(), out->typed_data(), cols, out->dimensions()[0], cols,
+                                 nullptr));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(gc_edge_mlp_rows_ffi, EdgeMlpRowsImpl,
                               ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()

@@ -693,16 +693,23 @@ class DenoiserEngine:
         e_h, e_y = self.e_h[:E1], self.e_y[:E1]
         if ctx.g2m_base is not None and self.fuse_g2m:
             # the table holds e' W1e' + b1 + (m0 W1r)[receivers]; hidden layer + second layer in one kernel
-            ops.edge_mlp_rows(ctx.g2m_base, (self.g_p, self.g2m_s), w["eu_w2"], w["eu_b2"], e_y)
+            # the kernel also leaves each row's LayerNorm statistics (from its fp32 accumulator) for the segment sum; they
+            # live in the hidden-layer buffer this path does not need (16 bytes per edge)
+            stats = self.e_h.view(-1)[:8 * E1].view(torch.float32).view(E1, 4)
+            ops.edge_mlp_rows(ctx.g2m_base, (self.g_p, self.g2m_s), w["eu_w2"], w["eu_b2"], e_y, row_stats=stats)
         elif ctx.g2m_base is not None:
             ops.edge_hidden(ctx.g2m_base, [(self.g_p, self.g2m_s), (ctx.m_p, self.g2m_r)], e_h, act="swish")
         else:
             # folded per-level weight: produced by queued work (sigma_context), so no early W fetch
             ops.gemm([(self.g2m_e_ln, ctx.g2m_w1e)], e_h, bias=ctx.g2m_b1, act="swish",
                      gathers=[(self.g_p, self.g2m_s), (ctx.m_p, self.g2m_r)])
-        if not (ctx.g2m_base is not None and self.fuse_g2m):
+        stats = None
+        if ctx.g2m_base is not None and self.fuse_g2m:
+            stats = self.e_h.view(-1)[:8 * E1].view(torch.float32).view(E1, 4)
+        else:
             _gemm([(e_h, w["eu_w2"])], e_y, bias=w["eu_b2"])
-        ops.ln_cond_segment_sum(e_y, self.m_agg, T[self.C_G2M_EU], self.g2m_row_ptr, self.g2m_perm, irregular=True)
+        ops.ln_cond_segment_sum(e_y, self.m_agg, T[self.C_G2M_EU], self.g2m_row_ptr, self.g2m_perm, irregular=True,
+                                row_stats=stats)
         self._mlp_ln([(ctx.m0, w["mu_w1a"]), (self.m_agg, w["mu_w1b"])], w["mu_b1"], w["mu_w2"], w["mu_b2"],
                      self.m_h, self.m_y, self.x, T[self.C_G2M_MU], residual=ctx.m0)
         if branch_stream is None:

@@ -165,17 +165,20 @@ def ln_cond(x: torch.Tensor, out: torch.Tensor, scale_offset: Optional[torch.Ten
 @_recorded(lambda y, out, so, rp, perm, **kw: "ln_cond_segment_sum", lambda y, out, so, rp, perm, **kw: (0.0, _nbytes(y, out, rp, perm)))
 def ln_cond_segment_sum(y: torch.Tensor, out: torch.Tensor, scale_offset: Optional[torch.Tensor],
                         row_ptr: torch.Tensor, edge_perm: Optional[torch.Tensor], *, layer_norm: bool = True,
-                        irregular: bool = False):
+                        irregular: bool = False, row_stats: Optional[torch.Tensor] = None):
     """`irregular`: hint that segment lengths vary widely (grid2mesh: 3 .. 594 edges per mesh node); selects the
-    higher-occupancy kernel variant (GC_SEGSUM_IRREGULAR)."""
+    higher-occupancy kernel variant (GC_SEGSUM_IRREGULAR).  `row_stats`: fp32 [rows of y, 4] written by edge_mlp_rows
+    (gc_ln_cond_segment_sum_stats)."""
     lib = _lib.load()
     nseg, cols = out.shape
     if row_ptr.dtype != torch.int32 or row_ptr.numel() != nseg + 1:
         raise ValueError("row_ptr must be int32 [num_segments + 1]")
-    _lib.check(lib.gc_ln_cond_segment_sum(_stream(), y.data_ptr(), _dt(y), _row_major(y, "y"), _p(scale_offset),
-                                          int(layer_norm) | (2 if irregular else 0), row_ptr.data_ptr(), _p(edge_perm),
-                                          out.data_ptr(), _dt(out),
-                                          _row_major(out, "out"), nseg, cols), "gc_ln_cond_segment_sum")
+    if row_stats is not None and (row_stats.dtype != torch.float32 or row_stats.shape != (y.shape[0], 4) or not row_stats.is_contiguous()):
+        raise ValueError("row_stats must be contiguous fp32 [rows of y, 4]")
+    _lib.check(lib.gc_ln_cond_segment_sum_stats(_stream(), y.data_ptr(), _dt(y), _row_major(y, "y"), _p(scale_offset),
+                                                int(layer_norm) | (2 if irregular else 0), row_ptr.data_ptr(), _p(edge_perm),
+                                                out.data_ptr(), _dt(out), _row_major(out, "out"), nseg, cols, _p(row_stats)),
+               "gc_ln_cond_segment_sum")
     return out
 
 
@@ -383,7 +386,7 @@ def edge_mlp_sum3(base: torch.Tensor, gathers: Sequence[Tuple[torch.Tensor, torc
     return out
 
 
-def _edge_rows_cost(base, gather, w2, b2, out, **kw):
+def _edge_rows_cost(base, gather, w2, b2, out, **kw):  # noqa: row_stats adds 16 bytes per row
     rows, cols = out.shape
     # FLOPs of the second layer; bytes: the base table once, one gathered row and one index per edge, the rows written
     return 2.0 * rows * cols * cols, _nbytes(base, out, w2) + rows * cols * 2.0 + 4.0 * rows
@@ -391,8 +394,9 @@ def _edge_rows_cost(base, gather, w2, b2, out, **kw):
 
 @_recorded("edge_mlp_rows", _edge_rows_cost)
 def edge_mlp_rows(base: torch.Tensor, gather: Tuple[torch.Tensor, torch.Tensor], w2: torch.Tensor, b2: Optional[torch.Tensor],
-                  out: torch.Tensor, *, act: Optional[str] = "swish") -> torch.Tensor:
-    """out[e] = act(base[e % len(base)] + gs[idx_s[e]]) @ w2^T + b2 in one kernel (see gc_edge_mlp_rows)."""
+                  out: torch.Tensor, *, act: Optional[str] = "swish", row_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[e] = act(base[e % len(base)] + gs[idx_s[e]]) @ w2^T + b2 in one kernel (see gc_edge_mlp_rows).  `row_stats`: optional
+    fp32 [rows, 4] output, per row {sum, sum of squares} of the two column halves (for ln_cond_segment_sum)."""
     lib = _lib.load()
     gs, idx_s = gather
     if any(t.dtype != torch.bfloat16 for t in (base, gs, w2, out)):
@@ -404,7 +408,7 @@ def edge_mlp_rows(base: torch.Tensor, gather: Tuple[torch.Tensor, torch.Tensor],
         raise ValueError("edge_mlp_rows: w2 must be [cols, cols]")
     _lib.check(lib.gc_edge_mlp_rows(_stream(), base.data_ptr(), _row_major(base, "base"), base.shape[0], gs.data_ptr(),
                                     idx_s.data_ptr(), _row_major(gs, "gs"), ACT[act], w2.data_ptr(), _row_major(w2, "w2"),
-                                    _p(b2), out.data_ptr(), _row_major(out, "out"), rows, cols), "gc_edge_mlp_rows")
+                                    _p(b2), out.data_ptr(), _row_major(out, "out"), rows, cols, _p(row_stats)), "gc_edge_mlp_rows")
     return out
 
 

@@ -140,6 +140,17 @@ GC_API int gc_ln_cond_segment_sum(void* stream, const void* y, int32_t y_dtype, 
                            const int32_t* row_ptr, const int32_t* edge_perm,
                            void* out, int32_t out_dtype, int64_t ldo,
                            int64_t num_segments, int32_t cols);
+/*
+ * The same with the rows' LayerNorm statistics supplied by the kernel that produced y (gc_edge_mlp_rows): row_stats is
+ * fp32 [rows of y, 4] = {sum, sum of squares} of the first and of the second half of the columns (NULL = the plain entry
+ * above).  Mean and variance are then formed from the producer's fp32 accumulator instead of from the rounded bf16 row,
+ * and the kernel no longer spends its instructions on reductions (bf16 rows with LayerNorm only).
+ */
+GC_API int gc_ln_cond_segment_sum_stats(void* stream, const void* y, int32_t y_dtype, int64_t ldy,
+                           const float* scale_offset, int32_t do_layer_norm,
+                           const int32_t* row_ptr, const int32_t* edge_perm,
+                           void* out, int32_t out_dtype, int64_t ldo,
+                           int64_t num_segments, int32_t cols, const float* row_stats);
 
 /*
  * k-hop neighbourhood multi-head attention on the mesh (exact sparse pattern):
@@ -333,10 +344,12 @@ GC_API int gc_edge_mlp_sum3(void* stream, const void* base, int64_t ld_base, int
  * gc_edge_mlp_sum3 (common/typed_graph_net.py:134-159, :295-305; common/mlp.py:115-147 up to the LayerNorm), same
  * kernel: tiles of 128 consecutive edges of one member, base rows by TMA, gs gathered, W2 by TMA, whole rows in tensor
  * memory; LayerNorm + aggregation follow in gc_ln_cond_segment_sum.  num_rows is a multiple of period (members).
+ * row_stats (optional, fp32 [num_rows, 4], 16-byte aligned): per row {sum, sum of squares} of y over the first and over the
+ * second half of the columns, taken from the fp32 accumulator; gc_ln_cond_segment_sum_stats then skips its own reductions.
  */
 GC_API int gc_edge_mlp_rows(void* stream, const void* base, int64_t ld_base, int64_t period, const void* gs,
                             const int32_t* idx_s, int64_t ld_gs, int32_t act, const void* w2, int64_t ld_w2,
-                            const float* b2, void* out, int64_t ldo, int64_t num_rows, int32_t cols);
+                            const float* b2, void* out, int64_t ldo, int64_t num_rows, int32_t cols, float* row_stats);
 
 /*
  * Inverse real spherical-harmonic transform of random coefficients -> isotropic white noise fields in the sampler's

@@ -426,6 +426,28 @@ def test_edge_mlp_rows_fused(cuda_device, cols, period, members):
     ops.edge_hidden(base.to(d), [(gs.to(d), idx_s.to(d))], e_h, act="swish")
     ops.gemm([(e_h, w2.to(d))], e_y, bias=b2.to(d))
     assert _rel(outs[0], e_y.cpu().double()) < 4e-3
+    # per-row LayerNorm statistics from the fp32 accumulator: {sum, sum of squares} of each half of the columns ...
+    stats = torch.full((E, 4), float("nan"), dtype=torch.float32, device=d)
+    out_s = torch.empty(E, cols, dtype=torch.bfloat16, device=d)
+    ops.edge_mlp_rows(base.to(d), (gs.to(d), idx_s.to(d)), w2.to(d), b2.to(d), out_s, row_stats=stats)
+    torch.cuda.synchronize()
+    assert torch.equal(out_s.cpu(), outs[0])
+    h2 = cols // 2
+    want = torch.stack([ref[:, :h2].sum(1), (ref[:, :h2] ** 2).sum(1), ref[:, h2:].sum(1), (ref[:, h2:] ** 2).sum(1)], dim=1)
+    got = stats.cpu().double()
+    assert torch.isfinite(got).all()
+    assert ((got - want).abs() / (want.abs() + 1.0 * math.sqrt(cols))).max() < 2e-3
+    # ... which the segment sum consumes instead of reducing the rounded rows itself: same LayerNorm up to bf16 noise
+    nseg = 97
+    cuts = torch.sort(torch.randint(0, E + 1, (nseg - 1,), generator=g)).values
+    rp = torch.cat([torch.zeros(1, dtype=torch.int64), cuts, torch.tensor([E])]).to(torch.int32).to(d)
+    so = torch.cat([1 + 0.1 * torch.randn(cols, generator=g), torch.randn(cols, generator=g)]).to(d)
+    agg_a = torch.empty(nseg, cols, dtype=torch.float32, device=d)
+    agg_b = torch.empty(nseg, cols, dtype=torch.float32, device=d)
+    ops.ln_cond_segment_sum(out_s, agg_a, so, rp, None, irregular=True)
+    ops.ln_cond_segment_sum(out_s, agg_b, so, rp, None, irregular=True, row_stats=stats)
+    torch.cuda.synchronize()
+    assert _rel(agg_b.cpu(), agg_a.cpu().double()) < 5e-3
 
 
 @pytest.mark.parametrize("cols,rows", [(128, 100), (256, 5000), (512, 20001), (512, 128)])

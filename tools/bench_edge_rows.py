@@ -22,8 +22,11 @@ e_h = torch.empty(E, L, dtype=bf, device=d)
 e_y = torch.empty(E, L, dtype=bf, device=d)
 
 
+stats = torch.empty(E, 4, dtype=torch.float32, device=d)
+
+
 def fused():
-    ops.edge_mlp_rows(base, (gs, idx_s), w2, b2, e_y)
+    ops.edge_mlp_rows(base, (gs, idx_s), w2, b2, e_y, row_stats=stats)
 
 
 def unfused():

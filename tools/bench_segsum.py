@@ -12,15 +12,15 @@ L = 512
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=d)
 
 
-def run(name, y, out, so, rp, perm):
+def run(name, y, out, so, rp, perm, stats=None):
     for _ in range(3):
-        ops.ln_cond_segment_sum(y, out, so, rp, perm)
+        ops.ln_cond_segment_sum(y, out, so, rp, perm, row_stats=stats)
     torch.cuda.synchronize()
     ts = []
     for i in range(10):
         flush.fill_(i)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); ops.ln_cond_segment_sum(y, out, so, rp, perm); b.record()
+        a.record(); ops.ln_cond_segment_sum(y, out, so, rp, perm, row_stats=stats); b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     t = float(np.median(ts)) * 1e-3
@@ -51,3 +51,8 @@ run("g2m (perm)", y, out, so, torch.from_numpy(rp_np).to(d), torch.from_numpy(pe
 # same edges physically receiver-sorted
 ys = y[torch.from_numpy(perm_np).long().to(d)].contiguous()
 run("g2m (sorted rows)", ys, out, so, torch.from_numpy(rp_np).to(d), None)
+# the same with the rows' statistics supplied by the producer (gc_edge_mlp_rows writes them; synthetic values here)
+yf = ys.float()
+h = L // 2
+stats = torch.stack([yf[:, :h].sum(1), (yf[:, :h] ** 2).sum(1), yf[:, h:].sum(1), (yf[:, h:] ** 2).sum(1)], dim=1).contiguous()
+run("g2m (sorted rows, statistics supplied)", ys, out, so, torch.from_numpy(rp_np).to(d), None, stats)
