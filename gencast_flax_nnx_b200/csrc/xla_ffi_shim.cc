@@ -5,6 +5,8 @@
 // present, compile this file against that include directory and link it with
 // libgencast_b200.so; the handlers only translate FFI buffers into the
 // pointer/size arguments of the launchers and forward the caller's stream.
+// Here the file is type-checked against a stand-in for that header (tools/ffi_stub, tests/test_host_logic.py), so every
+// call into the C ABI below is checked against include/gencast_b200.h by the compiler.
 #if __has_include("xla/ffi/api/ffi.h")
 #include <cuda_runtime.h>
 

@@ -248,6 +248,24 @@ def test_library_exports_every_declared_symbol():
     assert loaded.gc_sizeof_gemm_args() == ctypes.sizeof(_lib.GemmArgs)      # struct layout agrees with the C side
 
 
+def test_xla_ffi_shim_type_checks_against_the_c_abi():
+    """The jax.ffi handlers (csrc/xla_ffi_shim.cc) cannot be compiled against jaxlib's headers here; a stand-in for the part
+    of the XLA FFI C++ API they use (tools/ffi_stub) lets g++ type-check every handler body, i.e. every call into
+    include/gencast_b200.h, so the shim cannot drift from the library's signatures unnoticed."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("needs g++ and the CUDA headers")
+    shim = os.path.join(ROOT, "gencast_flax_nnx_b200", "csrc", "xla_ffi_shim.cc")
+    cmd = [gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "tools", "ffi_stub"), "-I", "/usr/local/cuda/include", shim]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    pre = subprocess.run(cmd[:2] + ["-E"] + cmd[4:], capture_output=True, text=True).stdout
+    for name in ("gc_gemm(", "gc_edge_mlp_sum3(", "gc_edge_mlp_rows(", "gc_denoiser_forward(", "gc_khop_attention_gather("):
+        assert name in pre, name                     # the handler bodies were really compiled (the stub header was found)
+
+
 def test_param_interchange_round_trip(tmp_path):
     from gencast_flax_nnx_b200 import params
     res, arch = configs.named_config("tiny")
