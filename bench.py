@@ -435,6 +435,13 @@ def measure(args, config: str, MB: int, steps: int, warmup: int, dev, rank: int,
         if d["flops"] == 0:
             k["hbm_frac"] = k["gbs"] / peaks["hbm"]     # HBM-bound kernels: algorithmic bytes / time over the measured copy peak
         kernels[name] = k
+    ka = kernels.get("khop_attention_gather")
+    if ka is not None and getattr(eng, "attention_kind", "") == "gather":
+        # `tflops` counts the exact k-hop pattern (4 nnz(adj^k) L); what the tensor cores execute is dense 128 x 64 tiles
+        # over the compacted key steps: S = Q K^T and O += P V, 2 x (2 * 128 * 64 * head_dim) FLOP per step and head
+        exec_flops = float(eng.num_attention_steps) * eng.H * 4.0 * 128 * 64 * eng.head_dim
+        ka["tflops_executed"] = exec_flops / (ka["avg_us"] * 1e-6) / 1e12
+        ka["executed_frac_of_tensor_peak"] = ka["tflops_executed"] / peaks["tensor_sustained"]
     dom = next(iter(kernels))
     domk = kernels[dom]
     tensor_bound = dom.startswith("gemm_bf16") or dom.startswith("khop_attention_tc")
